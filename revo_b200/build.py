@@ -1,0 +1,79 @@
+"""Builds ``revo_b200/lib/librevo_b200.so`` (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+nvcc cross-compiles without a GPU; the built .so is git-ignored but travels to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "librevo_b200.so")
+SOURCES = ["capi.cu", "pyramid.cu", "track.cu"]
+HEADERS = ["internal.h", os.path.join("..", "..", "include", "revo_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
+    "-Xptxas", "-v",
+    "--expt-relaxed-constexpr",
+]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    objs = []
+    env = dict(os.environ)
+    # the image exports CC=/opt/gcc/bin/gcc (a wrapper); let nvcc use the system g++
+    host = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    procs = []
+    for s in SOURCES:
+        obj = os.path.join(LIBDIR, s.replace(".cu", ".o"))
+        cmd = [nvcc_path(), "-ccbin", host, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)))
+        objs.append(obj)
+    log = []
+    for s, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {s}\n{out}")
+        if p.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {s}")
+    cmd = [nvcc_path(), "-ccbin", host, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs,
+           "-cudart", "static"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    log.append(r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write("\n".join(log))
+        raise RuntimeError("link failed")
+    with open(os.path.join(LIBDIR, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,750 @@
+// capi.cu -- implementation of the C ABI declared in include/revo_b200.h.
+// Host-side orchestration only: memory layout in HBM, descriptor tables, launch sequencing.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "internal.h"
+
+using namespace revo;
+
+namespace revo {
+
+int cuda_fail(revo_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (ctx) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+        ctx->last_error = buf;
+    }
+    (void)cudaGetLastError();
+    return REVO_ERR_CUDA;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_scratch(revo_ctx *ctx, size_t bytes)
+{
+    if (ctx->scratch_bytes >= bytes) return REVO_OK;
+    if (ctx->scratch) {
+        REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        REVO_CUDA(ctx, cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+    }
+    bytes = align_up(bytes + bytes / 4, 1 << 20);
+    REVO_CUDA(ctx, cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return REVO_OK;
+}
+
+static int ensure_pinned(revo_ctx *ctx, size_t bytes)
+{
+    if (ctx->pinned_bytes >= bytes) return REVO_OK;
+    if (ctx->pinned) {
+        REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        REVO_CUDA(ctx, cudaFreeHost(ctx->pinned));
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+    }
+    bytes = align_up(bytes * 2, 1 << 16);
+    REVO_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_bytes = bytes;
+    return REVO_OK;
+}
+
+// Camera(fx,fy,cx,cy,w,h,scale) -- camerapyr.h:98-103 with scale = 1.0f/pow(2,lvl) (:141)
+static void level_camera(const revo_camera &c0, int lvl, revo_camera *out)
+{
+    if (lvl == 0) { *out = c0; return; }
+    const float scale = 1.0f / (float)pow(2.0, (double)lvl);
+    out->fx = c0.fx * scale; out->fy = c0.fy * scale; out->cx = c0.cx * scale; out->cy = c0.cy * scale;
+    out->width = (int32_t)((float)c0.width * scale);
+    out->height = (int32_t)((float)c0.height * scale);
+}
+
+}  // namespace revo
+
+// ---------------------------------------------------------------------------------------------------
+// defaults
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+void revo_pyr_config_default(revo_pyr_config *c)
+{
+    c->n_levels = 3; c->canny_threshold1 = 150; c->canny_threshold2 = 100;
+    c->depth_min = 0.1f; c->depth_max = 5.2f; c->use_edge_hist = 1; c->n_percentage = 0.3f; c->patch0 = 20;
+}
+
+void revo_opt_config_default(revo_opt_config *c)
+{
+    const float ed[6] = {30, 20, 10, 5, 5, 5};
+    c->lambda_success_fac = 0.5f; c->lambda_fail_fac = 2.0f;
+    for (int l = 0; l < REVO_MAX_LEVELS; ++l) {
+        c->lambda_initial[l] = 0.f; c->step_size_min[l] = 1e-16f; c->convergence_eps[l] = 0.999f;
+        c->max_its_per_lvl[l] = 100; c->edge_distance_lvl[l] = ed[l];
+    }
+    c->huber_edge = 0.3f; c->use_edge_filter = 1; c->max_lm_tries = 0;
+}
+
+void revo_tracker_config_default(revo_tracker_config *c)
+{
+    c->check_init_values = 1; c->pyr_min_lvl = 2; c->pyr_max_lvl = 0;
+    revo_opt_config_default(&c->opt);
+}
+
+const char *revo_strerror(int code)
+{
+    switch (code) {
+        case REVO_OK: return "ok";
+        case REVO_ERR_INVALID_ARG: return "invalid argument";
+        case REVO_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+        case REVO_ERR_CUDA: return "CUDA error (see revo_last_error)";
+        case REVO_ERR_NOT_KEYFRAME: return "optimization structure not built (makeKeyframe was not called)";
+        case REVO_ERR_NOT_ORTHOGONAL: return "R is not a rotation matrix";
+        case REVO_ERR_BAD_LEVEL: return "pyramid level out of range";
+        case REVO_ERR_BUFFER_TOO_SMALL: return "destination buffer too small";
+        case REVO_ERR_UNSUPPORTED: return "unsupported configuration";
+        case REVO_ERR_COMM: return "multi-GPU setup error";
+        default: return "unknown error";
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+int revo_ctx_create(int device, revo_ctx **out)
+{
+    if (!out) return REVO_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        (void)cudaGetLastError();
+        return REVO_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return REVO_ERR_INVALID_ARG;
+    revo_ctx *ctx = new (std::nothrow) revo_ctx();
+    if (!ctx) return REVO_ERR_INVALID_ARG;
+    ctx->device = device;
+    ctx->launches = 0;
+    ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+    ctx->track_ctas_per_pair = 0; ctx->track_threads = 0;
+    ctx->split_rank = 0; ctx->split_world = 1; ctx->split_local = nullptr; ctx->split_seq = 0;
+    for (auto &p : ctx->split_peers) p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete ctx;
+        return REVO_ERR_CUDA;
+    }
+    // keep freed stream-ordered allocations cached in the pool (no trimming at synchronisation points)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    (void)cudaGetLastError();
+    *out = ctx;
+    return REVO_OK;
+}
+
+int revo_ctx_destroy(revo_ctx *ctx)
+{
+    if (!ctx) return REVO_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 16; ++i)
+        if (ctx->split_peers[i] && ctx->split_peers[i] != ctx->split_local) cudaIpcCloseMemHandle(ctx->split_peers[i]);
+    if (ctx->split_local) cudaFree(ctx->split_local);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->stream);
+    (void)cudaGetLastError();
+    delete ctx;
+    return REVO_OK;
+}
+
+int revo_ctx_synchronize(revo_ctx *ctx)
+{
+    if (!ctx) return REVO_ERR_INVALID_ARG;
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return REVO_OK;
+}
+
+const char *revo_last_error(revo_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t revo_ctx_stream(revo_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+uint64_t revo_ctx_launch_count(revo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int revo_ctx_set_track_shape(revo_ctx *ctx, int ctas_per_pair, int threads_per_cta)
+{
+    if (!ctx) return REVO_ERR_INVALID_ARG;
+    if (ctas_per_pair != 0 && ctas_per_pair != 1 && ctas_per_pair != 2 && ctas_per_pair != 4 && ctas_per_pair != 8 &&
+        ctas_per_pair != 16)
+        return REVO_ERR_INVALID_ARG;
+    if (threads_per_cta != 0 && threads_per_cta != 128 && threads_per_cta != 256 && threads_per_cta != 512 &&
+        threads_per_cta != 1024)
+        return REVO_ERR_INVALID_ARG;
+    ctx->track_ctas_per_pair = ctas_per_pair;
+    ctx->track_threads = threads_per_cta;
+    return REVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pyramid construction
+// ---------------------------------------------------------------------------------------------------
+struct LevelGeom {
+    int w, h, patch, hist_w, hist_h, cap, n_tiles;
+    revo_camera cam;
+};
+
+static int level_geometry(const revo_pyr_config *cfg, const revo_camera *cam0, LevelGeom *g)
+{
+    if (cfg->n_levels < 1 || cfg->n_levels > REVO_MAX_LEVELS) return REVO_ERR_INVALID_ARG;
+    if (cam0->width < 8 || cam0->height < 8) return REVO_ERR_INVALID_ARG;
+    for (int l = 0; l < cfg->n_levels; ++l) {
+        level_camera(*cam0, l, &g[l].cam);
+        g[l].w = g[l].cam.width; g[l].h = g[l].cam.height;
+        if (g[l].w < 4 || g[l].h < 4) return REVO_ERR_UNSUPPORTED;
+        // the reference is only self-consistent for even sizes (pyrDown -> (n+1)/2, depth/Camera -> n/2:
+        // imgpyramidrgbd.cpp:79-85, camerapyr.h:100); refuse the others instead of reading out of bounds
+        if (l + 1 < cfg->n_levels && ((g[l].w & 1) || (g[l].h & 1))) return REVO_ERR_UNSUPPORTED;
+        g[l].patch = std::max(1, cfg->patch0 >> l);
+        g[l].hist_w = g[l].w / g[l].patch; g[l].hist_h = g[l].h / g[l].patch;
+        g[l].cap = g[l].w * g[l].h / 2 + 1024;
+        g[l].n_tiles = ((g[l].w + kTileW - 1) / kTileW) * ((g[l].h + kTileH - 1) / kTileH);
+    }
+    return REVO_OK;
+}
+
+int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera *cam0, int n, const uint8_t *bgr,
+                          int channels, const float *depth, const double *timestamps, revo_pyr **pyr_out)
+{
+    if (!ctx || !cfg || !cam0 || !bgr || !depth || !pyr_out || n < 1 || (channels != 3 && channels != 4))
+        return REVO_ERR_INVALID_ARG;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    LevelGeom g[REVO_MAX_LEVELS];
+    int rc = level_geometry(cfg, cam0, g);
+    if (rc) return rc;
+    const int NL = cfg->n_levels;
+    const int w0 = g[0].w, h0 = g[0].h;
+
+    // ---- slab layout: [array][level][frame], every chunk 256-byte aligned ------------------------
+    size_t off = 0;
+    auto take = [&](size_t per_frame) { size_t o = off; off += align_up(per_frame, 256) * (size_t)n; return o; };
+    size_t o_desc[REVO_MAX_LEVELS], o_gray[REVO_MAX_LEVELS], o_depth[REVO_MAX_LEVELS], o_edges[REVO_MAX_LEVELS],
+        o_eorig[REVO_MAX_LEVELS], o_hist[REVO_MAX_LEVELS], o_pts[REVO_MAX_LEVELS], o_toff[REVO_MAX_LEVELS];
+    for (int l = 0; l < NL; ++l) { o_desc[l] = off; off += align_up(sizeof(ImgLevel) * (size_t)n, 256); }
+    const size_t o_counters = off; off += align_up(sizeof(int) * 2 * NL * (size_t)n, 256);   // n_pts, nz_patches
+    for (int l = 0; l < NL; ++l) {
+        const size_t px = (size_t)g[l].w * g[l].h;
+        o_gray[l] = take(px); o_depth[l] = take(px * 4); o_edges[l] = take(px); o_eorig[l] = take(px);
+        o_hist[l] = take((size_t)std::max(1, g[l].hist_w * g[l].hist_h));
+        o_pts[l] = take((size_t)g[l].cap * 16);
+        o_toff[l] = take(((size_t)g[l].n_tiles + 1) * 4);
+    }
+    const size_t o_labels = take((size_t)w0 * h0 * 4);
+    const size_t o_flags = take((size_t)w0 * h0);
+    const size_t total = off;
+
+    Slab *slab = new (std::nothrow) Slab();
+    if (!slab) return REVO_ERR_INVALID_ARG;
+    slab->n_frames = n; slab->live = n; slab->bytes = total; slab->mem = nullptr;
+    cudaError_t e = cudaMallocAsync(&slab->mem, total, ctx->stream);
+    if (e != cudaSuccess) { delete slab; return cuda_fail(ctx, e, "cudaMallocAsync(slab)"); }
+    uint8_t *base = (uint8_t *)slab->mem;
+    auto chunk = [&](size_t o, size_t per_frame, int f) { return base + o + align_up(per_frame, 256) * (size_t)f; };
+
+    std::vector<revo_pyr *> pyrs(n);
+    std::vector<ImgLevel> host_desc((size_t)NL * n);
+    for (int f = 0; f < n; ++f) {
+        revo_pyr *p = new revo_pyr();
+        p->slab = slab; p->index_in_slab = f; p->n_levels = NL; p->cfg = *cfg; p->cam0 = *cam0;
+        p->timestamp = timestamps ? timestamps[f] : 0.0; p->kf_mem = nullptr; p->is_keyframe = false;
+        for (int l = 0; l < NL; ++l) {
+            ImgLevel &L = p->lv[l];
+            const size_t px = (size_t)g[l].w * g[l].h;
+            L.gray = chunk(o_gray[l], px, f);
+            L.depth = (float *)chunk(o_depth[l], px * 4, f);
+            L.edges = chunk(o_edges[l], px, f);
+            L.edges_orig = chunk(o_eorig[l], px, f);
+            L.hist = chunk(o_hist[l], (size_t)std::max(1, g[l].hist_w * g[l].hist_h), f);
+            L.pts = (float4 *)chunk(o_pts[l], (size_t)g[l].cap * 16, f);
+            L.n_pts = (int *)(base + o_counters) + ((size_t)f * NL + l) * 2;
+            L.nz_patches = L.n_pts + 1;
+            L.tile_off = (int *)chunk(o_toff[l], ((size_t)g[l].n_tiles + 1) * 4, f);
+            L.labels = (int *)chunk(o_labels, (size_t)w0 * h0 * 4, f);
+            L.flags = chunk(o_flags, (size_t)w0 * h0, f);
+            L.dt = nullptr; L.opt = nullptr;
+            L.w = g[l].w; L.h = g[l].h; L.pts_cap = g[l].cap; L.patch = g[l].patch;
+            L.hist_w = g[l].hist_w; L.hist_h = g[l].hist_h;
+            L.fx = g[l].cam.fx; L.fy = g[l].cam.fy; L.cx = g[l].cam.cx; L.cy = g[l].cam.cy;
+            host_desc[(size_t)l * n + f] = L;
+        }
+        pyrs[f] = p;
+    }
+    auto fail = [&](int code) {
+        for (auto *p : pyrs) delete p;
+        cudaFreeAsync(slab->mem, ctx->stream);
+        delete slab;
+        return code;
+    };
+    for (int l = 0; l < NL; ++l) {
+        slab->d_desc[l] = (ImgLevel *)(base + o_desc[l]);
+        e = cudaMemcpyAsync(slab->d_desc[l], &host_desc[(size_t)l * n], sizeof(ImgLevel) * (size_t)n, cudaMemcpyHostToDevice,
+                            ctx->stream);
+        if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memcpy(desc)"));
+    }
+    e = cudaMemsetAsync(base + o_counters, 0, sizeof(int) * 2 * NL * (size_t)n, ctx->stream);
+    if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memset(counters)"));
+
+    // ---- inputs -------------------------------------------------------------------------------------
+    const size_t bgr_frame = (size_t)w0 * h0 * channels;
+    const uint8_t *d_bgr = bgr;
+    if (!is_device_ptr(bgr)) {
+        rc = ensure_scratch(ctx, bgr_frame * (size_t)n);
+        if (rc) return fail(rc);
+        e = cudaMemcpyAsync(ctx->scratch, bgr, bgr_frame * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memcpy(bgr)"));
+        d_bgr = (const uint8_t *)ctx->scratch;
+    }
+    {
+        const size_t fb = (size_t)w0 * h0 * 4;
+        e = cudaMemcpy2DAsync(base + o_depth[0], align_up(fb, 256), depth, fb, fb, (size_t)n, cudaMemcpyDefault, ctx->stream);
+        if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memcpy(depth)"));
+    }
+
+    // ---- the pyramid (imgpyramidrgbd.cpp:43-96) -------------------------------------------------
+    const double t1 = cfg->canny_threshold1, t2 = cfg->canny_threshold2;
+    double lo = std::min(t1, t2), hi = std::max(t1, t2);
+    lo = std::min(32767.0, lo); hi = std::min(32767.0, hi);
+    if (lo > 0) lo *= lo;
+    if (hi > 0) hi *= hi;
+    const int low = (int)floor(lo), high = (int)floor(hi);
+
+    rc = launch_gray(ctx, d_bgr, (size_t)w0 * channels, channels, bgr_frame, slab->d_desc[0], n, w0, h0);
+    for (int l = 0; l < NL && !rc; ++l) {
+        if (l > 0) rc = launch_pyrdown_depth(ctx, slab->d_desc[l - 1], slab->d_desc[l], n, g[l].w, g[l].h, g[l - 1].w, g[l - 1].h);
+        if (!rc) rc = launch_canny(ctx, slab->d_desc[l], n, g[l].w, g[l].h, low, high);
+        // fill-in is only defined for the reference's 3 patch sizes (levels 1,2); see SURVEY D5
+        const bool fill = cfg->use_edge_hist && l >= 1 && l <= 2;
+        if (!rc) rc = launch_hist_fill(ctx, slab->d_desc[l], l > 0 ? slab->d_desc[l - 1] : nullptr, n, g[l].w, g[l].h,
+                                      g[l].patch, l > 0 ? g[l - 1].patch : g[l].patch, fill, cfg->n_percentage);
+        if (!rc) rc = launch_compact(ctx, slab->d_desc[l], n, g[l].w, g[l].h, cfg->depth_min, cfg->depth_max);
+    }
+    if (rc) return fail(rc);
+    for (int f = 0; f < n; ++f) pyr_out[f] = pyrs[f];
+    return REVO_OK;
+}
+
+int revo_pyr_create(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera *cam0, const uint8_t *bgr, size_t bgr_stride,
+                    int channels, const float *depth, size_t depth_stride, double timestamp, revo_pyr **pyr_out)
+{
+    if (!ctx || !cfg || !cam0 || !bgr || !depth || !pyr_out) return REVO_ERR_INVALID_ARG;
+    const size_t tight_bgr = (size_t)cam0->width * channels, tight_d = (size_t)cam0->width * 4;
+    if (bgr_stride == 0) bgr_stride = tight_bgr;
+    if (depth_stride == 0) depth_stride = tight_d;
+    if (bgr_stride == tight_bgr && depth_stride == tight_d)
+        return revo_pyr_create_batch(ctx, cfg, cam0, 1, bgr, channels, depth, &timestamp, pyr_out);
+    // strided inputs (cv::Mat ROI): repack rows on the host, then take the tight path
+    if (is_device_ptr(bgr) || is_device_ptr(depth)) return REVO_ERR_UNSUPPORTED;
+    std::vector<uint8_t> b(tight_bgr * cam0->height);
+    std::vector<float> d((size_t)cam0->width * cam0->height);
+    for (int y = 0; y < cam0->height; ++y) {
+        memcpy(b.data() + tight_bgr * y, bgr + bgr_stride * y, tight_bgr);
+        memcpy((uint8_t *)d.data() + tight_d * y, (const uint8_t *)depth + depth_stride * y, tight_d);
+    }
+    int rc = revo_pyr_create_batch(ctx, cfg, cam0, 1, b.data(), channels, d.data(), &timestamp, pyr_out);
+    if (!rc) cudaStreamSynchronize(ctx->stream);   // the temporaries die here
+    return rc;
+}
+
+static int alloc_keyframe_mem(revo_ctx *ctx, revo_pyr *p)
+{
+    if (p->kf_mem) return REVO_OK;
+    size_t bytes = 0;
+    for (int l = 0; l < p->n_levels; ++l) bytes += align_up((size_t)p->lv[l].w * p->lv[l].h * 20, 256);
+    REVO_CUDA(ctx, cudaMallocAsync(&p->kf_mem, bytes, ctx->stream));
+    uint8_t *m = (uint8_t *)p->kf_mem;
+    for (int l = 0; l < p->n_levels; ++l) {
+        const size_t px = (size_t)p->lv[l].w * p->lv[l].h;
+        p->lv[l].opt = (float4 *)m;
+        p->lv[l].dt = (float *)(m + px * 16);
+        m += align_up(px * 20, 256);
+    }
+    return REVO_OK;
+}
+
+int revo_pyr_make_keyframe_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs)
+{
+    if (!ctx || !pyrs || n < 0) return REVO_ERR_INVALID_ARG;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<revo_pyr *> todo;
+    for (int i = 0; i < n; ++i) {
+        if (!pyrs[i]) return REVO_ERR_INVALID_ARG;
+        if (!pyrs[i]->is_keyframe && std::find(todo.begin(), todo.end(), pyrs[i]) == todo.end()) todo.push_back(pyrs[i]);
+    }
+    if (todo.empty()) return REVO_OK;
+    const int m = (int)todo.size();
+    const int NL = todo[0]->n_levels;
+    for (auto *p : todo)
+        if (p->n_levels != NL || p->lv[0].w != todo[0]->lv[0].w || p->lv[0].h != todo[0]->lv[0].h) return REVO_ERR_INVALID_ARG;
+    for (auto *p : todo) {
+        int rc = alloc_keyframe_mem(ctx, p);
+        if (rc) return rc;
+    }
+    // temporary descriptor tables (with dt/opt set) in a stream-ordered allocation
+    std::vector<ImgLevel> host((size_t)NL * m);
+    for (int l = 0; l < NL; ++l)
+        for (int i = 0; i < m; ++i) host[(size_t)l * m + i] = todo[i]->lv[l];
+    ImgLevel *d_tab = nullptr;
+    REVO_CUDA(ctx, cudaMallocAsync((void **)&d_tab, sizeof(ImgLevel) * host.size(), ctx->stream));
+    REVO_CUDA(ctx, cudaMemcpyAsync(d_tab, host.data(), sizeof(ImgLevel) * host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = REVO_OK;
+    for (int l = 0; l < NL && !rc; ++l) rc = launch_keyframe(ctx, d_tab + (size_t)l * m, m, todo[0]->lv[l].w, todo[0]->lv[l].h);
+    cudaFreeAsync(d_tab, ctx->stream);
+    if (rc) return rc;
+    for (auto *p : todo) p->is_keyframe = true;
+    return REVO_OK;
+}
+
+int revo_pyr_make_keyframe(revo_ctx *ctx, revo_pyr *pyr) { return revo_pyr_make_keyframe_batch(ctx, 1, &pyr); }
+
+int revo_pyr_destroy(revo_ctx *ctx, revo_pyr *pyr)
+{
+    if (!pyr) return REVO_OK;
+    if (!ctx) return REVO_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    if (pyr->kf_mem) cudaFreeAsync(pyr->kf_mem, ctx->stream);
+    Slab *s = pyr->slab;
+    if (s && --s->live == 0) {
+        cudaFreeAsync(s->mem, ctx->stream);
+        delete s;
+    }
+    delete pyr;
+    (void)cudaGetLastError();
+    return REVO_OK;
+}
+
+int revo_pyr_is_keyframe(const revo_pyr *pyr) { return pyr && pyr->is_keyframe; }
+double revo_pyr_timestamp(const revo_pyr *pyr) { return pyr ? pyr->timestamp : 0.0; }
+
+int revo_pyr_level_camera(const revo_pyr *pyr, int lvl, revo_camera *cam_out)
+{
+    if (!pyr || !cam_out) return REVO_ERR_INVALID_ARG;
+    if (lvl < 0 || lvl >= pyr->n_levels) return REVO_ERR_BAD_LEVEL;
+    const ImgLevel &L = pyr->lv[lvl];
+    cam_out->fx = L.fx; cam_out->fy = L.fy; cam_out->cx = L.cx; cam_out->cy = L.cy; cam_out->width = L.w; cam_out->height = L.h;
+    return REVO_OK;
+}
+
+int revo_pyr_num_edges(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int *n_out)
+{
+    if (!ctx || !pyr || !n_out) return REVO_ERR_INVALID_ARG;
+    if (lvl < 0 || lvl >= pyr->n_levels) return REVO_ERR_BAD_LEVEL;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    REVO_CUDA(ctx, cudaMemcpyAsync(n_out, pyr->lv[lvl].n_pts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return REVO_OK;
+}
+
+int revo_pyr_download(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int which, void *dst, size_t dst_bytes, size_t *bytes_out)
+{
+    if (!ctx || !pyr) return REVO_ERR_INVALID_ARG;
+    if (lvl < 0 || lvl >= pyr->n_levels) return REVO_ERR_BAD_LEVEL;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const ImgLevel &L = pyr->lv[lvl];
+    const size_t px = (size_t)L.w * L.h;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (which) {
+        case REVO_ARRAY_GRAY: src = L.gray; bytes = px; break;
+        case REVO_ARRAY_DEPTH: src = L.depth; bytes = px * 4; break;
+        case REVO_ARRAY_EDGES: src = L.edges; bytes = px; break;
+        case REVO_ARRAY_EDGES_ORIG: src = L.edges_orig; bytes = px; break;
+        case REVO_ARRAY_HIST: src = L.hist; bytes = (size_t)L.hist_w * L.hist_h; break;
+        case REVO_ARRAY_DT:
+            if (!pyr->is_keyframe) return REVO_ERR_NOT_KEYFRAME;
+            src = L.dt; bytes = px * 4; break;
+        case REVO_ARRAY_OPTSTRUCT:
+            if (!pyr->is_keyframe) return REVO_ERR_NOT_KEYFRAME;
+            src = L.opt; bytes = px * 16; break;
+        case REVO_ARRAY_EDGES3D_DEVICE_ORDER: {
+            int n = 0;
+            int rc = revo_pyr_num_edges(ctx, pyr, lvl, &n);
+            if (rc) return rc;
+            src = L.pts; bytes = (size_t)n * 16; break;
+        }
+        case REVO_ARRAY_EDGES3D: {
+            // reference order: column-major scan (imgpyramidrgbd.cpp:203-205)
+            const size_t need = px * 16 + (size_t)(L.w + 4) * 4 + sizeof(ImgLevel) + 1024;
+            int rc = ensure_scratch(ctx, need);
+            if (rc) return rc;
+            uint8_t *s = (uint8_t *)ctx->scratch;
+            float4 *d_out = (float4 *)s;
+            int *d_col = (int *)(s + align_up(px * 16, 256));
+            int *d_n = d_col + L.w + 1;
+            ImgLevel *d_desc = (ImgLevel *)(s + align_up(px * 16, 256) + align_up((size_t)(L.w + 4) * 4, 256));
+            REVO_CUDA(ctx, cudaMemcpyAsync(d_desc, &L, sizeof(ImgLevel), cudaMemcpyHostToDevice, ctx->stream));
+            rc = launch_edges3d_reference_order(ctx, d_desc, L.w, L.h, pyr->cfg.depth_min, pyr->cfg.depth_max, d_out, d_n, d_col);
+            if (rc) return rc;
+            int n = 0;
+            REVO_CUDA(ctx, cudaMemcpyAsync(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            src = d_out; bytes = (size_t)n * 16; break;
+        }
+        default: return REVO_ERR_INVALID_ARG;
+    }
+    if (bytes_out) *bytes_out = bytes;
+    if (!dst) return REVO_OK;   // size query
+    if (dst_bytes < bytes) return REVO_ERR_BUFFER_TOO_SMALL;
+    if (bytes) REVO_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return REVO_OK;
+}
+
+int revo_pyr_upload_level(revo_ctx *ctx, revo_pyr *pyr, int lvl, const float *pts4, int n, const float *dt, const float *opt4)
+{
+    if (!ctx || !pyr) return REVO_ERR_INVALID_ARG;
+    if (lvl < 0 || lvl >= pyr->n_levels) return REVO_ERR_BAD_LEVEL;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    ImgLevel &L = pyr->lv[lvl];
+    const size_t px = (size_t)L.w * L.h;
+    if (pts4) {
+        if (n < 0 || n > L.pts_cap) return REVO_ERR_BUFFER_TOO_SMALL;
+        if (n) REVO_CUDA(ctx, cudaMemcpyAsync(L.pts, pts4, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+        REVO_CUDA(ctx, cudaMemcpyAsync(L.n_pts, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (dt || opt4) {
+        int rc = alloc_keyframe_mem(ctx, pyr);
+        if (rc) return rc;
+        if (dt) REVO_CUDA(ctx, cudaMemcpyAsync(L.dt, dt, px * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (opt4) {
+            REVO_CUDA(ctx, cudaMemcpyAsync(L.opt, opt4, px * 16, cudaMemcpyHostToDevice, ctx->stream));
+            pyr->is_keyframe = true;
+        }
+    }
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return REVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tracking
+// ---------------------------------------------------------------------------------------------------
+static int fill_pair(const revo_pyr *ref, const revo_pyr *cur, int min_lvl, int max_lvl, const float *R9, const float *t3,
+                     PairDesc *d)
+{
+    if (!ref || !cur) return REVO_ERR_INVALID_ARG;
+    if (!ref->is_keyframe) return REVO_ERR_NOT_KEYFRAME;
+    if (min_lvl < max_lvl || max_lvl < 0 || min_lvl >= cur->n_levels || min_lvl >= ref->n_levels) return REVO_ERR_BAD_LEVEL;
+    memset(d, 0, sizeof(*d));
+    for (int l = max_lvl; l <= min_lvl; ++l) {
+        const ImgLevel &c = cur->lv[l], &r = ref->lv[l];
+        if (c.w != r.w || c.h != r.h) return REVO_ERR_INVALID_ARG;
+        LevelIn &L = d->lvl[l];
+        L.pts = c.pts; L.n_pts = c.n_pts; L.opt = r.opt;
+        // calcErrorAndBuffers takes the camera from the reference frame (optimizer.cpp:80)
+        L.fx = r.fx; L.fy = r.fy; L.cx = r.cx; L.cy = r.cy; L.w = r.w; L.h = r.h;
+    }
+    d->ref_dt_min = ref->lv[min_lvl].dt;
+    memcpy(d->R, R9, sizeof(float) * 9);
+    memcpy(d->t, t3, sizeof(float) * 3);
+    return REVO_OK;
+}
+
+static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *refs, revo_pyr *const *curs, const float *R9s,
+                     const float *t3s, revo_track_result *results, double *records, revo_trace_entry *trace, int trace_cap,
+                     int *trace_counts)
+{
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int min_lvl = prm.mode == 0 ? prm.cfg.pyr_min_lvl : prm.level;
+    const int max_lvl = prm.mode == 0 ? prm.cfg.pyr_max_lvl : prm.level;
+    std::vector<PairDesc> host(n);
+    for (int i = 0; i < n; ++i) {
+        int rc = fill_pair(refs[i], curs[i], min_lvl, max_lvl, R9s + 9 * (size_t)i, t3s + 3 * (size_t)i, &host[i]);
+        if (rc) return rc;
+    }
+    if (!trace) trace_cap = 0;
+    prm.trace_cap = trace_cap;
+    // device workspace: pairs | results | records | trace | trace counts
+    const size_t b_pairs = align_up(sizeof(PairDesc) * (size_t)n, 256);
+    const size_t b_res = align_up(sizeof(revo_track_result) * (size_t)n, 256);
+    const size_t b_rec = align_up(sizeof(double) * 32 * (size_t)n, 256);
+    const size_t b_tr = align_up(sizeof(revo_trace_entry) * (size_t)trace_cap * n, 256);
+    const size_t b_tc = align_up(sizeof(int) * (size_t)n, 256);
+    uint8_t *ws = nullptr;
+    REVO_CUDA(ctx, cudaMallocAsync((void **)&ws, b_pairs + b_res + b_rec + b_tr + b_tc, ctx->stream));
+    PairDesc *d_pairs = (PairDesc *)ws;
+    revo_track_result *d_res = (revo_track_result *)(ws + b_pairs);
+    double *d_rec = (double *)(ws + b_pairs + b_res);
+    revo_trace_entry *d_tr = trace_cap ? (revo_trace_entry *)(ws + b_pairs + b_res + b_rec) : nullptr;
+    int *d_tc = (int *)(ws + b_pairs + b_res + b_rec + b_tr);
+    int rc = REVO_OK;
+    cudaError_t e = cudaMemcpyAsync(d_pairs, host.data(), sizeof(PairDesc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_res, 0, b_res + b_rec, ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "track upload");
+    if (!rc) rc = launch_track(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, nullptr);
+    if (!rc && results) {
+        e = cudaMemcpyAsync(results, d_res, sizeof(revo_track_result) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "results download");
+    }
+    if (!rc && records) {
+        e = cudaMemcpyAsync(records, d_rec, sizeof(double) * 32 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "records download");
+    }
+    if (!rc && trace && trace_cap) {
+        e = cudaMemcpyAsync(trace, d_tr, sizeof(revo_trace_entry) * (size_t)trace_cap * n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && trace_counts)
+            e = cudaMemcpyAsync(trace_counts, d_tc, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "trace download");
+    }
+    cudaFreeAsync(ws, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess && !rc) rc = cuda_fail(ctx, e, "track kernel");
+    return rc;
+}
+
+int revo_track_batch(revo_ctx *ctx, const revo_tracker_config *cfg, int n, revo_pyr *const *refs, revo_pyr *const *curs,
+                     const float *R9s, const float *t3s, revo_track_result *results, revo_trace_entry *trace, int trace_cap,
+                     int *trace_counts)
+{
+    if (!ctx || !cfg || !refs || !curs || !R9s || !t3s || !results || n < 0) return REVO_ERR_INVALID_ARG;
+    if (n == 0) return REVO_OK;
+    TrackParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.cfg = *cfg; prm.mode = 0; prm.split_world = 1;
+    return run_track(ctx, prm, n, refs, curs, R9s, t3s, results, nullptr, trace, trace_cap, trace_counts);
+}
+
+int revo_track(revo_ctx *ctx, const revo_tracker_config *cfg, const revo_pyr *ref, const revo_pyr *cur, float *R9, float *t3,
+               revo_track_result *result)
+{
+    if (!ctx || !cfg || !ref || !cur || !R9 || !t3) return REVO_ERR_INVALID_ARG;
+    revo_track_result res;
+    revo_pyr *r = const_cast<revo_pyr *>(ref), *c = const_cast<revo_pyr *>(cur);
+    int rc = revo_track_batch(ctx, cfg, 1, &r, &c, R9, t3, &res, nullptr, 0, nullptr);
+    if (rc) return rc;
+    if (result) *result = res;
+    if (res.rc) return res.rc;
+    memcpy(R9, res.R, sizeof(float) * 9);
+    memcpy(t3, res.t, sizeof(float) * 3);
+    return REVO_OK;
+}
+
+int revo_track_level(revo_ctx *ctx, const revo_opt_config *cfg, const revo_pyr *ref, const revo_pyr *cur, int lvl, float *R9,
+                     float *t3, revo_residual_info *res, float *err, int *n_evals)
+{
+    if (!ctx || !cfg || !ref || !cur || !R9 || !t3) return REVO_ERR_INVALID_ARG;
+    TrackParams prm;
+    memset(&prm, 0, sizeof(prm));
+    revo_tracker_config_default(&prm.cfg);
+    prm.cfg.opt = *cfg; prm.cfg.check_init_values = 0;
+    prm.mode = 1; prm.level = lvl; prm.split_world = 1;
+    revo_track_result out;
+    revo_pyr *r = const_cast<revo_pyr *>(ref), *c = const_cast<revo_pyr *>(cur);
+    int rc = run_track(ctx, prm, 1, &r, &c, R9, t3, &out, nullptr, nullptr, 0, nullptr);
+    if (rc) return rc;
+    if (out.rc) return out.rc;
+    memcpy(R9, out.R, sizeof(float) * 9);
+    memcpy(t3, out.t, sizeof(float) * 3);
+    if (res) *res = out.res;
+    if (err) *err = out.error;
+    if (n_evals) *n_evals = out.n_evals[lvl];
+    return REVO_OK;
+}
+
+int revo_eval(revo_ctx *ctx, const revo_opt_config *cfg, const revo_pyr *ref, const revo_pyr *cur, int lvl, const float *R9,
+              const float *t3, double *record32)
+{
+    if (!ctx || !cfg || !ref || !cur || !R9 || !t3 || !record32) return REVO_ERR_INVALID_ARG;
+    TrackParams prm;
+    memset(&prm, 0, sizeof(prm));
+    revo_tracker_config_default(&prm.cfg);
+    prm.cfg.opt = *cfg; prm.cfg.check_init_values = 0;
+    prm.mode = 2; prm.level = lvl; prm.split_world = 1;
+    revo_pyr *r = const_cast<revo_pyr *>(ref), *c = const_cast<revo_pyr *>(cur);
+    return run_track(ctx, prm, 1, &r, &c, R9, t3, nullptr, record32, nullptr, 0, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU split of one pair (one process per GPU; mailboxes exchanged as CUDA IPC handles)
+// ---------------------------------------------------------------------------------------------------
+struct SplitBlob {
+    cudaIpcMemHandle_t handle;   // 64 bytes
+    int32_t rank, world;
+    int32_t pid_lo, device;
+    char pad[REVO_SPLIT_HANDLE_BYTES - 64 - 16];
+};
+static_assert(sizeof(SplitBlob) == REVO_SPLIT_HANDLE_BYTES, "blob size");
+
+int revo_split_export(revo_ctx *ctx, int rank, int world, void *handle_out)
+{
+    if (!ctx || !handle_out || world < 1 || world > 16 || rank < 0 || rank >= world) return REVO_ERR_INVALID_ARG;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->split_local) {
+        REVO_CUDA(ctx, cudaMalloc(&ctx->split_local, 16384));
+        REVO_CUDA(ctx, cudaMemset(ctx->split_local, 0, 16384));
+    }
+    ctx->split_rank = rank; ctx->split_world = world;
+    SplitBlob b;
+    memset(&b, 0, sizeof(b));
+    REVO_CUDA(ctx, cudaIpcGetMemHandle(&b.handle, ctx->split_local));
+    b.rank = rank; b.world = world; b.device = ctx->device;
+    memcpy(handle_out, &b, sizeof(b));
+    return REVO_OK;
+}
+
+int revo_split_open(revo_ctx *ctx, const void *handles)
+{
+    if (!ctx || !handles || !ctx->split_local) return REVO_ERR_INVALID_ARG;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const SplitBlob *b = (const SplitBlob *)handles;
+    for (int r = 0; r < ctx->split_world; ++r) {
+        if (b[r].rank != r || b[r].world != ctx->split_world) return REVO_ERR_COMM;
+        if (r == ctx->split_rank) { ctx->split_peers[r] = ctx->split_local; continue; }
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, b[r].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaIpcOpenMemHandle"); return REVO_ERR_COMM; }
+        ctx->split_peers[r] = p;
+    }
+    ctx->split_seq = 0;
+    return REVO_OK;
+}
+
+int revo_track_split(revo_ctx *ctx, const revo_tracker_config *cfg, const revo_pyr *ref, const revo_pyr *cur, float *R9, float *t3,
+                     revo_track_result *result)
+{
+    if (!ctx || !cfg || !ref || !cur || !R9 || !t3) return REVO_ERR_INVALID_ARG;
+    if (ctx->split_world < 1 || !ctx->split_peers[ctx->split_rank]) return REVO_ERR_COMM;
+    TrackParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.cfg = *cfg; prm.mode = 0;
+    prm.split_rank = ctx->split_rank; prm.split_world = ctx->split_world;
+    prm.split_seq0 = ctx->split_seq;
+    ctx->split_seq += (1ull << 24);   // every launch owns a disjoint range of flag values
+    for (int r = 0; r < 16; ++r) prm.split_peers[r] = ctx->split_peers[r];
+    revo_track_result out;
+    revo_pyr *r = const_cast<revo_pyr *>(ref), *c = const_cast<revo_pyr *>(cur);
+    int rc = run_track(ctx, prm, 1, &r, &c, R9, t3, &out, nullptr, nullptr, 0, nullptr);
+    if (rc) return rc;
+    if (result) *result = out;
+    if (out.rc) return out.rc;
+    memcpy(R9, out.R, sizeof(float) * 9);
+    memcpy(t3, out.t, sizeof(float) * 3);
+    return REVO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+// internal.h -- shared declarations of the revo_b200 CUDA library (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/revo_b200.h"
+
+namespace revo {
+
+// One (frame, level) of an ImgPyramidRGBD as the kernels see it (device-visible POD).
+// Mirrors the per-level members of datastructures/imgpyramidrgbd.h:186-213.
+struct ImgLevel {
+    uint8_t *gray;        // grayPyr[l]       h*w
+    float *depth;         // depthPyr[l]      h*w
+    uint8_t *edges;       // edgesPyr[l]      h*w {0,255} (class map 0/1/2 while Canny runs)
+    uint8_t *edges_orig;  // edgesOrigPyr[l]  h*w
+    uint8_t *hist;        // histPyr[l]       (h/P)*(w/P)
+    float4 *pts;          // edges3DPyr[l]    tile-major order, capacity pts_cap
+    int *n_pts;           // number of valid entries of pts (device scalar)
+    int *nz_patches;      // countNonZero(hist) (device scalar)
+    int *tile_off;        // per-tile exclusive offsets of the compaction (n_tiles + 1)
+    int *labels;          // scratch h*w int32: union-find labels (Canny) / column distances (EDT)
+    uint8_t *flags;       // scratch h*w u8: "component holds a strong pixel"
+    float *dt;            // dtPyr[l]         h*w   (keyframes, else nullptr)
+    float4 *opt;          // optimizationStructure[l] h*w (keyframes, else nullptr)
+    int w, h;
+    int pts_cap;
+    int patch;            // distPatchSizes[l]
+    int hist_w, hist_h;
+    float fx, fy, cx, cy; // Camera at this level (camerapyr.h:98-103)
+};
+
+// Point-list tile: one warp <-> one 8x4 pixel tile (row-major inside, tiles row-major).
+constexpr int kTileW = 8;
+constexpr int kTileH = 4;
+
+struct Slab;  // one device allocation shared by the frames of a batch
+
+}  // namespace revo
+
+// The opaque handle types of the C ABI.
+struct revo_pyr {
+    revo::Slab *slab;
+    int index_in_slab;
+    int n_levels;
+    revo_pyr_config cfg;
+    revo_camera cam0;
+    double timestamp;
+    revo::ImgLevel lv[REVO_MAX_LEVELS];    // host copy of the device descriptors
+    void *kf_mem;                          // keyframe allocation (dt + opt of all levels)
+    bool is_keyframe;
+};
+
+struct revo_ctx {
+    int device;
+    cudaStream_t stream;
+    cudaDeviceProp prop;
+    std::string last_error;
+    uint64_t launches;
+    // scratch
+    void *scratch;        // generic device scratch (descriptor tables, staging of uploads)
+    size_t scratch_bytes;
+    void *pinned;         // pinned host staging for small results
+    size_t pinned_bytes;
+    int track_ctas_per_pair;
+    int track_threads;
+    // split mode (multi-GPU single pair)
+    int split_rank, split_world;
+    void *split_local;                 // this rank's mailbox (device memory, IPC-exported)
+    void *split_peers[16];             // mapped mailboxes of all ranks (own entry = split_local)
+    unsigned long long split_seq;
+};
+
+namespace revo {
+
+struct Slab {
+    void *mem;
+    size_t bytes;
+    int n_frames;
+    int live;             // pyramids still alive
+    ImgLevel *d_desc[REVO_MAX_LEVELS];  // device descriptor tables, n_frames entries each (inside mem)
+};
+
+// error helper: records the failure text in ctx and returns REVO_ERR_CUDA
+int cuda_fail(revo_ctx *ctx, cudaError_t e, const char *what);
+#define REVO_CUDA(ctx, call)                                            \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return revo::cuda_fail((ctx), e__, #call); \
+    } while (0)
+
+// ---- pyramid.cu ----------------------------------------------------------
+// All launchers are asynchronous on ctx->stream and batched over n frames (d_desc: device table).
+int launch_gray(revo_ctx *ctx, const uint8_t *d_bgr, size_t stride, int ch, size_t frame_bytes, const ImgLevel *d_desc,
+                int n, int w, int h);
+int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst,
+                         int w_src, int h_src);
+int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high);
+int launch_hist_fill(revo_ctx *ctx, const ImgLevel *d_desc, const ImgLevel *d_top, int n, int w, int h, int patch,
+                     int patch_low, bool do_fill, float n_percentage);
+int launch_compact(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, float dmin, float dmax);
+int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h);
+// reference-order (column-major scan) 3-D edge list into d_out (capacity w*h float4); *d_n receives the count
+int launch_edges3d_reference_order(revo_ctx *ctx, const ImgLevel *d_desc_one, int w, int h, float dmin, float dmax,
+                                   float4 *d_out, int *d_n, int *d_col_off);
+
+// ---- track.cu --------------------------------------------------------------
+struct LevelIn {
+    const float4 *pts;
+    const int *n_pts;
+    const float4 *opt;
+    float fx, fy, cx, cy;
+    int w, h;
+};
+struct PairDesc {
+    LevelIn lvl[REVO_MAX_LEVELS];
+    const float *ref_dt_min;  // returnDistTransform(min_lvl) of the reference frame
+    float R[9];
+    float t[3];
+};
+struct TrackParams {
+    revo_tracker_config cfg;
+    int mode;            // 0 = full trackFrames, 1 = single level (Optimizer::trackFrames), 2 = one evaluation
+    int level;           // for modes 1,2
+    int trace_cap;
+    // split mode
+    int split_rank, split_world;
+    unsigned long long split_seq0;
+    void *split_peers[16];
+};
+int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm,
+                 revo_track_result *d_results, double *d_records, revo_trace_entry *d_trace, int *d_trace_counts,
+                 int *d_work_counter);
+
+}  // namespace revo

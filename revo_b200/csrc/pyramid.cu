@@ -1,0 +1,611 @@
+// pyramid.cu -- ImgPyramidRGBD construction and keyframe promotion on the GPU.
+//
+// Replaces (reference file:line, fabianschenk/REVO):
+//   K1 gray            cv::cvtColor(BGRA2GRAY)            datastructures/imgpyramidrgbd.cpp:53
+//   K2 Canny           cv::Canny(g, e, 150, 100, 3, true) datastructures/imgpyramidrgbd.cpp:184
+//   K3 pyrDown         cv::pyrDown                        datastructures/imgpyramidrgbd.cpp:82
+//   K4 depth /2        FilterSubsampleWithHoles           datastructures/imgpyramidrgbd.h:218-249
+//   K5 hist + fill-in  generateDistHistogram/fillInEdges  datastructures/imgpyramidrgbd.cpp:146-172,111-145
+//   K6 3-D edge list   loop in addLevelEdge               datastructures/imgpyramidrgbd.cpp:199-226
+//   K7 exact L2 EDT    cv::distanceTransform(L2,PRECISE)  datastructures/imgpyramidrgbd.cpp:241
+//   K8 lookup struct   buildOptimizationStructure         datastructures/imgpyramidrgbd.cpp:255-276
+//
+// All kernels are batched over frames (blockIdx.z = frame) and integer/byte
+// exact against OpenCV 4.13 (see oracle/revo_oracle.c for the CPU restatement
+// these are tested against).  HBM-bound byte work: no tensor cores.
+#include "internal.h"
+
+namespace revo {
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+#define LAUNCH_CHECK(ctx)                                   \
+    do {                                                    \
+        (ctx)->launches++;                                  \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return cuda_fail((ctx), e__, __func__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// K1: BGR(A) -> gray, Y = (3735 B + 19235 G + 9798 R + 16384) >> 15  (OpenCV 4.x)
+// 4 pixels per thread: 3 x 32-bit loads (BGR) / 1 x 128-bit load (BGRA), one 32-bit store.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r)
+{
+    return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
+}
+
+__global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ bgr, size_t stride, int ch, size_t frame_bytes,
+                                              const ImgLevel *__restrict__ desc, int w, int h)
+{
+    const int f = blockIdx.z;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= h || x0 >= w) return;
+    const uint8_t *row = bgr + (size_t)f * frame_bytes + (size_t)y * stride;
+    uint8_t *out = desc[f].gray + (size_t)y * w;
+    const uint8_t *p = row + (size_t)x0 * ch;
+    if (x0 + 4 <= w && (((uintptr_t)p) & 3) == 0 && (((uintptr_t)(out + x0)) & 3) == 0) {
+        uint32_t y0, y1, y2, y3;
+        if (ch == 3) {
+            const uint32_t a = __ldg((const uint32_t *)p), b = __ldg((const uint32_t *)p + 1), c = __ldg((const uint32_t *)p + 2);
+            // a = B0 G0 R0 B1 | b = G1 R1 B2 G2 | c = R2 B3 G3 R3   (little endian)
+            y0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255);
+            y1 = gray_of(a >> 24, b & 255, (b >> 8) & 255);
+            y2 = gray_of((b >> 16) & 255, b >> 24, c & 255);
+            y3 = gray_of((c >> 8) & 255, (c >> 16) & 255, c >> 24);
+        } else {
+            const uint32_t *q = (const uint32_t *)p;
+            const uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+            y0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255);
+            y1 = gray_of(b & 255, (b >> 8) & 255, (b >> 16) & 255);
+            y2 = gray_of(c & 255, (c >> 8) & 255, (c >> 16) & 255);
+            y3 = gray_of(d & 255, (d >> 8) & 255, (d >> 16) & 255);
+        }
+        *(uint32_t *)(out + x0) = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+    } else {
+        for (int k = 0; k < 4 && x0 + k < w; ++k) {
+            const uint8_t *q = p + k * ch;
+            out[x0 + k] = (uint8_t)gray_of(q[0], q[1], q[2]);
+        }
+    }
+}
+
+int launch_gray(revo_ctx *ctx, const uint8_t *d_bgr, size_t stride, int ch, size_t frame_bytes, const ImgLevel *d_desc,
+                int n, int w, int h)
+{
+    dim3 block(32, 8), grid(cdiv(cdiv(w, 4), 32), cdiv(h, 8), n);
+    k_gray<<<grid, block, 0, ctx->stream>>>(d_bgr, stride, ch, frame_bytes, d_desc, w, h);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K3: pyrDown 8U: separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8.
+// 32x8 outputs per CTA; input tile 67x19 staged in shared memory.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+constexpr int PD_TW = 32, PD_TH = 8;
+__global__ void __launch_bounds__(256) k_pyrdown(const ImgLevel *__restrict__ src, const ImgLevel *__restrict__ dst, int ws,
+                                                 int hs, int wd, int hd)
+{
+    __shared__ uint8_t tile[2 * PD_TH + 3][2 * PD_TW + 4];
+    __shared__ uint16_t hb[2 * PD_TH + 3][PD_TW];
+    const int f = blockIdx.z;
+    const uint8_t *__restrict__ in = src[f].gray;
+    uint8_t *__restrict__ out = dst[f].gray;
+    const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH;
+    const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    constexpr int IW = 2 * PD_TW + 3, IH = 2 * PD_TH + 3;
+    for (int i = tid; i < IW * IH; i += 256) {
+        const int r = i / IW, c = i - r * IW;
+        tile[r][c] = in[(size_t)reflect101(iy0 + r, hs) * ws + reflect101(ix0 + c, ws)];
+    }
+    __syncthreads();
+    for (int i = tid; i < IH * PD_TW; i += 256) {
+        const int r = i / PD_TW, c = i - r * PD_TW;
+        const uint8_t *t = &tile[r][2 * c];
+        hb[r][c] = (uint16_t)(t[0] + 4 * t[1] + 6 * t[2] + 4 * t[3] + t[4]);
+    }
+    __syncthreads();
+    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
+    if (ox < wd && oy < hd) {
+        const int r = 2 * threadIdx.y, c = threadIdx.x;
+        const int s = hb[r][c] + 4 * hb[r + 1][c] + 6 * hb[r + 2][c] + 4 * hb[r + 3][c] + hb[r + 4][c];
+        out[(size_t)oy * wd + ox] = (uint8_t)((s + 128) >> 8);
+    }
+}
+
+// K4: FilterSubsampleWithHoles: mean of the >0 entries of each 2x2 block (NaN excluded by the compare).
+__global__ void __launch_bounds__(256) k_depth_half(const ImgLevel *__restrict__ src, const ImgLevel *__restrict__ dst, int ws,
+                                                    int wd, int hd)
+{
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= wd || y >= hd) return;
+    const float *__restrict__ in = src[f].depth;
+    const float2 a = *(const float2 *)(in + (size_t)(2 * y) * ws + 2 * x);
+    const float2 b = *(const float2 *)(in + (size_t)(2 * y + 1) * ws + 2 * x);
+    float acc = 0.f, n = 0.f;
+    if (a.x > 0.0f) { acc = __fadd_rn(acc, a.x); n += 1.f; }
+    if (a.y > 0.0f) { acc = __fadd_rn(acc, a.y); n += 1.f; }
+    if (b.x > 0.0f) { acc = __fadd_rn(acc, b.x); n += 1.f; }
+    if (b.y > 0.0f) { acc = __fadd_rn(acc, b.y); n += 1.f; }
+    if (n > 0.f) acc = __fdiv_rn(acc, n);
+    dst[f].depth[(size_t)y * wd + x] = acc;
+}
+
+int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst,
+                         int w_src, int h_src)
+{
+    {
+        dim3 block(PD_TW, PD_TH), grid(cdiv(w_dst, PD_TW), cdiv(h_dst, PD_TH), n);
+        k_pyrdown<<<grid, block, 0, ctx->stream>>>(d_src, d_dst, w_src, h_src, w_dst, h_dst);
+        LAUNCH_CHECK(ctx);
+    }
+    {
+        dim3 block(32, 8), grid(cdiv(w_dst, 32), cdiv(h_dst, 8), n);
+        k_depth_half<<<grid, block, 0, ctx->stream>>>(d_src, d_dst, w_src, w_dst, h_dst);
+        LAUNCH_CHECK(ctx);
+    }
+    return REVO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K2: Canny (aperture 3, L2 gradient).
+//  (a) k_canny_nms: 3x3 Sobel with BORDER_REPLICATE, mag = dx^2+dy^2 (zero outside the image),
+//      non-maximum suppression with OpenCV's TG22 fixed-point sector test -> class map
+//      0 = no edge, 1 = weak candidate (> low), 2 = strong (> high); candidates get a
+//      union-find label (their own index).
+//  (b) k_canny_link: union every candidate with its W, NW, N, NE candidate neighbours
+//      (8-connectivity) -- lock-free atomicMin union-find, root = smallest index.
+//  (c) k_canny_mark: every strong pixel flags its root.
+//  (d) k_canny_out: 255 for candidates whose root is flagged, else 0 (edges and edges_orig).
+// The result is the unique fixed point of OpenCV's hysteresis, independent of thread order.
+// ---------------------------------------------------------------------------
+constexpr int CN_TW = 32, CN_TH = 8;
+
+__global__ void __launch_bounds__(256) k_canny_nms(const ImgLevel *__restrict__ desc, int w, int h, int low, int high)
+{
+    __shared__ uint8_t g[CN_TH + 4][CN_TW + 4];
+    __shared__ int mag[CN_TH + 2][CN_TW + 2];
+    const int f = blockIdx.z;
+    const ImgLevel L = desc[f];
+    const int x0 = blockIdx.x * CN_TW, y0 = blockIdx.y * CN_TH;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int i = tid; i < (CN_TH + 4) * (CN_TW + 4); i += 256) {
+        const int r = i / (CN_TW + 4), c = i - r * (CN_TW + 4);
+        const int yy = min(max(y0 + r - 2, 0), h - 1), xx = min(max(x0 + c - 2, 0), w - 1);
+        g[r][c] = L.gray[(size_t)yy * w + xx];
+    }
+    __syncthreads();
+    for (int i = tid; i < (CN_TH + 2) * (CN_TW + 2); i += 256) {
+        const int r = i / (CN_TW + 2), c = i - r * (CN_TW + 2);
+        const int yy = y0 + r - 1, xx = x0 + c - 1;
+        int m = 0;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+            // g index of (yy,xx) is [r+1][c+1]
+            const int gx = (g[r][c + 2] - g[r][c]) + 2 * (g[r + 1][c + 2] - g[r + 1][c]) + (g[r + 2][c + 2] - g[r + 2][c]);
+            const int gy = (g[r + 2][c] - g[r][c]) + 2 * (g[r + 2][c + 1] - g[r][c + 1]) + (g[r + 2][c + 2] - g[r][c + 2]);
+            m = gx * gx + gy * gy;
+        }
+        mag[r][c] = m;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int r = threadIdx.y + 1, c = threadIdx.x + 1;   // position in mag
+    const int m = mag[r][c];
+    uint8_t cls = 0;
+    if (m > low) {
+        const int gr = threadIdx.y + 1, gc = threadIdx.x + 1;  // top-left of the 3x3 window in g is [gr][gc]
+        const int xs = (g[gr][gc + 2] - g[gr][gc]) + 2 * (g[gr + 1][gc + 2] - g[gr + 1][gc]) + (g[gr + 2][gc + 2] - g[gr + 2][gc]);
+        const int ys = (g[gr + 2][gc] - g[gr][gc]) + 2 * (g[gr + 2][gc + 1] - g[gr][gc + 1]) + (g[gr + 2][gc + 2] - g[gr][gc + 2]);
+        const int ax = abs(xs), ay = abs(ys) << 15;
+        const int tg22x = ax * 13573;
+        bool cand;
+        if (ay < tg22x) {
+            cand = (m > mag[r][c - 1]) && (m >= mag[r][c + 1]);
+        } else {
+            const int tg67x = tg22x + (ax << 16);
+            if (ay > tg67x) cand = (m > mag[r - 1][c]) && (m >= mag[r + 1][c]);
+            else {
+                const int s = ((xs ^ ys) < 0) ? -1 : 1;
+                cand = (m > mag[r - 1][c - s]) && (m > mag[r + 1][c + s]);
+            }
+        }
+        if (cand) cls = (m > high) ? 2 : 1;
+    }
+    const int p = y * w + x;
+    L.edges[p] = cls;
+    if (cls) {
+        L.labels[p] = p;
+        L.flags[p] = 0;
+    }
+}
+
+__device__ __forceinline__ int uf_find(const int *L, int a)
+{
+    int p = __ldcg(L + a);
+    while (p != a) {
+        a = p;
+        p = __ldcg(L + a);
+    }
+    return a;
+}
+
+__device__ __forceinline__ void uf_union(int *L, int a, int b)
+{
+    while (true) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(L + a, b);   // attach the larger root under the smaller
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_canny_link(const ImgLevel *__restrict__ desc, int w, int h)
+{
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t *__restrict__ cls = desc[f].edges;
+    int *lab = desc[f].labels;
+    const int p = y * w + x;
+    if (!cls[p]) return;
+    if (x > 0 && cls[p - 1]) uf_union(lab, p, p - 1);
+    if (y > 0) {
+        const int q = p - w;
+        if (x > 0 && cls[q - 1]) uf_union(lab, p, q - 1);
+        if (cls[q]) uf_union(lab, p, q);
+        if (x < w - 1 && cls[q + 1]) uf_union(lab, p, q + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_canny_mark(const ImgLevel *__restrict__ desc, int w, int h)
+{
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int p = y * w + x;
+    if (desc[f].edges[p] == 2) desc[f].flags[uf_find(desc[f].labels, p)] = 1;
+}
+
+__global__ void __launch_bounds__(256) k_canny_out(const ImgLevel *__restrict__ desc, int w, int h)
+{
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int p = y * w + x;
+    uint8_t o = 0;
+    if (desc[f].edges[p]) o = desc[f].flags[uf_find(desc[f].labels, p)] ? 255 : 0;
+    desc[f].edges[p] = o;
+    desc[f].edges_orig[p] = o;
+}
+
+int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high)
+{
+    dim3 block(CN_TW, CN_TH), grid(cdiv(w, CN_TW), cdiv(h, CN_TH), n);
+    k_canny_nms<<<grid, block, 0, ctx->stream>>>(d_desc, w, h, low, high);
+    LAUNCH_CHECK(ctx);
+    k_canny_link<<<grid, block, 0, ctx->stream>>>(d_desc, w, h);
+    LAUNCH_CHECK(ctx);
+    k_canny_mark<<<grid, block, 0, ctx->stream>>>(d_desc, w, h);
+    LAUNCH_CHECK(ctx);
+    k_canny_out<<<grid, block, 0, ctx->stream>>>(d_desc, w, h);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K5: patch histogram (u8 counts wrap like cv::Mat_<uchar>::operator++) + count of
+// non-empty patches; fill-in from the level above.  One CTA per patch row.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hist(const ImgLevel *__restrict__ desc, int w, int h, int P)
+{
+    extern __shared__ int cnt[];
+    const int f = blockIdx.z;
+    const ImgLevel L = desc[f];
+    const int py = blockIdx.x;
+    for (int i = threadIdx.x; i < L.hist_w; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    const int band_w = L.hist_w * P;
+    for (int i = threadIdx.x; i < band_w * P; i += blockDim.x) {
+        const int r = i / band_w, c = i - r * band_w;
+        if (L.edges[(size_t)(py * P + r) * w + c]) atomicAdd(&cnt[c / P], 1);
+    }
+    __syncthreads();
+    int nz = 0;
+    for (int i = threadIdx.x; i < L.hist_w; i += blockDim.x) {
+        const uint8_t v = (uint8_t)(cnt[i] & 255);
+        L.hist[(size_t)py * L.hist_w + i] = v;
+        nz += v != 0;
+    }
+    nz = __reduce_add_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0 && nz) atomicAdd(L.nz_patches, nz);
+}
+
+// fillInEdges: this-level pixel (ox,oy) <- top pixel (2ox+1, 2oy+1) when the patch of the top pixel has
+// fewer than 0.05 P^2 edge pixels AT THIS LEVEL and the whole level has < n_percentage non-empty patches.
+__global__ void __launch_bounds__(256) k_fill_in(const ImgLevel *__restrict__ desc, const ImgLevel *__restrict__ top, int w, int h,
+                                                 int P, int P_low, float n_percentage)
+{
+    const int f = blockIdx.z;
+    const ImgLevel L = desc[f];
+    const float frac = __fdiv_rn((float)(*L.nz_patches), (float)(L.hist_w * L.hist_h));
+    if (!(frac < n_percentage)) return;
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox >= w || oy >= h) return;
+    const int xx = 2 * ox + 1, yy = 2 * oy + 1;
+    const int wt = top[f].w, ht = top[f].h;
+    if (xx >= wt || yy >= ht) return;
+    const int py = yy / P_low, px = xx / P_low;
+    if (py >= L.hist_h || px >= L.hist_w) return;
+    if ((double)L.hist[(size_t)py * L.hist_w + px] < (double)(P * P) * 0.05) {
+        if (top[f].edges[(size_t)yy * wt + xx]) L.edges[(size_t)oy * w + ox] = 255;
+    }
+}
+
+int launch_hist_fill(revo_ctx *ctx, const ImgLevel *d_desc, const ImgLevel *d_top, int n, int w, int h, int patch,
+                     int patch_low, bool do_fill, float n_percentage)
+{
+    const int hist_w = w / patch, hist_h = h / patch;
+    if (hist_w > 0 && hist_h > 0) {
+        dim3 grid(hist_h, 1, n);
+        k_hist<<<grid, 256, hist_w * sizeof(int), ctx->stream>>>(d_desc, w, h, patch);
+        LAUNCH_CHECK(ctx);
+        if (do_fill) {
+            dim3 block(32, 8), g2(cdiv(w, 32), cdiv(h, 8), n);
+            k_fill_in<<<g2, block, 0, ctx->stream>>>(d_desc, d_top, w, h, patch, patch_low, n_percentage);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    return REVO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K6: 3-D edge list.  One warp per 8x4 tile; deterministic tile-major order
+// (count -> exclusive scan -> scatter).  X = Z (x - cx) / fx exactly as the reference.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool edge_point_ok(const ImgLevel &L, int x, int y, int w, int h, float dmin, float dmax, float &Z)
+{
+    if (x >= w || y >= h) return false;
+    Z = L.depth[(size_t)y * w + x];
+    return isfinite(Z) && Z > dmin && Z < dmax && L.edges[(size_t)y * w + x] > 0;
+}
+
+__global__ void __launch_bounds__(256) k_tile_count(const ImgLevel *__restrict__ desc, int w, int h, int tiles_x, int n_tiles,
+                                                    float dmin, float dmax)
+{
+    const int f = blockIdx.z;
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    float Z;
+    const bool ok = edge_point_ok(desc[f], tx * kTileW + (lane & 7), ty * kTileH + (lane >> 3), w, h, dmin, dmax, Z);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) desc[f].tile_off[tile] = __popc(m);
+}
+
+// in-place exclusive scan of tile_off[0..n_tiles) ; tile_off[n_tiles] = total ; n_pts = min(total, cap)
+__global__ void __launch_bounds__(1024) k_tile_scan(const ImgLevel *__restrict__ desc, int n_tiles)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    const int f = blockIdx.x;
+    int *off = desc[f].tile_off;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_tiles ? off[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += t;
+        }
+        if (lane == 31) warp_sums[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, ws, d);
+                if (lane >= d) ws += t;
+            }
+            warp_sums[lane] = ws;   // inclusive
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + (wid ? warp_sums[wid - 1] : 0) + s - v;
+        if (i < n_tiles) off[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        off[n_tiles] = carry_s;
+        *desc[f].n_pts = min(carry_s, desc[f].pts_cap);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tile_scatter(const ImgLevel *__restrict__ desc, int w, int h, int tiles_x, int n_tiles,
+                                                      float dmin, float dmax)
+{
+    const int f = blockIdx.z;
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const ImgLevel &L = desc[f];
+    const int x = tx * kTileW + (lane & 7), y = ty * kTileH + (lane >> 3);
+    float Z;
+    const bool ok = edge_point_ok(L, x, y, w, h, dmin, dmax, Z);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (!ok) return;
+    const int o = L.tile_off[tile] + __popc(m & ((1u << lane) - 1u));
+    if (o >= L.pts_cap) return;
+    const float X = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)x, L.cx)), L.fx);
+    const float Y = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)y, L.cy)), L.fy);
+    L.pts[o] = make_float4(X, Y, Z, 1.0f);
+}
+
+int launch_compact(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, float dmin, float dmax)
+{
+    const int tiles_x = cdiv(w, kTileW), tiles_y = cdiv(h, kTileH), n_tiles = tiles_x * tiles_y;
+    dim3 grid(cdiv(n_tiles, 8), 1, n);
+    k_tile_count<<<grid, 256, 0, ctx->stream>>>(d_desc, w, h, tiles_x, n_tiles, dmin, dmax);
+    LAUNCH_CHECK(ctx);
+    k_tile_scan<<<n, 1024, 0, ctx->stream>>>(d_desc, n_tiles);
+    LAUNCH_CHECK(ctx);
+    k_tile_scatter<<<grid, 256, 0, ctx->stream>>>(d_desc, w, h, tiles_x, n_tiles, dmin, dmax);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
+// Reference order (xx outer, yy inner -- imgpyramidrgbd.cpp:203-205) for the return3DEdges accessor.
+__global__ void k_col_count(const ImgLevel *__restrict__ desc, int w, int h, float dmin, float dmax, int *col_off)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    int c = 0;
+    float Z;
+    for (int y = 0; y < h; ++y) c += edge_point_ok(desc[0], x, y, w, h, dmin, dmax, Z);
+    col_off[x] = c;
+}
+__global__ void k_col_scan(int *col_off, int w, int *n_out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int s = 0;
+        for (int x = 0; x < w; ++x) { const int c = col_off[x]; col_off[x] = s; s += c; }
+        *n_out = s;
+    }
+}
+__global__ void k_col_scatter(const ImgLevel *__restrict__ desc, int w, int h, float dmin, float dmax, const int *col_off,
+                              float4 *out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const ImgLevel &L = desc[0];
+    int o = col_off[x];
+    float Z;
+    for (int y = 0; y < h; ++y)
+        if (edge_point_ok(L, x, y, w, h, dmin, dmax, Z)) {
+            const float X = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)x, L.cx)), L.fx);
+            const float Y = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)y, L.cy)), L.fy);
+            out[o++] = make_float4(X, Y, Z, 1.0f);
+        }
+}
+
+int launch_edges3d_reference_order(revo_ctx *ctx, const ImgLevel *d_desc_one, int w, int h, float dmin, float dmax,
+                                   float4 *d_out, int *d_n, int *d_col_off)
+{
+    k_col_count<<<cdiv(w, 128), 128, 0, ctx->stream>>>(d_desc_one, w, h, dmin, dmax, d_col_off);
+    LAUNCH_CHECK(ctx);
+    k_col_scan<<<1, 32, 0, ctx->stream>>>(d_col_off, w, d_n);
+    LAUNCH_CHECK(ctx);
+    k_col_scatter<<<cdiv(w, 128), 128, 0, ctx->stream>>>(d_desc_one, w, h, dmin, dmax, d_col_off, d_out);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K7: exact Euclidean distance transform to the nearest edge pixel, out = sqrtf(d2).
+//  (a) column pass: vertical distance g(x,y) to the nearest edge in the column (int, kEdtInf if none)
+//  (b) row pass: d2(x,y) = min_j (x-j)^2 + g(j,y)^2 by an outward search that stops once r^2 >= best
+//      (exact; typical DT values are small so the search is short).
+// K8: {0.5(dt[i-1]-dt[i+1]), 0.5(dt[i-w]-dt[i+w]), dt[i], 0} for rows 1..h-2, zeros elsewhere.
+// ---------------------------------------------------------------------------
+constexpr int kEdtInf = 1 << 14;
+
+__global__ void k_edt_cols(const ImgLevel *__restrict__ desc, int w, int h)
+{
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const uint8_t *__restrict__ e = desc[f].edges;
+    int *__restrict__ g = desc[f].labels;
+    int d = kEdtInf;
+    for (int y = 0; y < h; ++y) {
+        d = e[(size_t)y * w + x] ? 0 : min(d + 1, kEdtInf);
+        g[(size_t)y * w + x] = d;
+    }
+    d = kEdtInf;
+    for (int y = h - 1; y >= 0; --y) {
+        const int cur = g[(size_t)y * w + x];
+        d = min(cur, min(d + 1, kEdtInf));
+        if (d < cur) g[(size_t)y * w + x] = d;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_edt_rows(const ImgLevel *__restrict__ desc, int w, int h)
+{
+    extern __shared__ int grow[];
+    const int f = blockIdx.z, y = blockIdx.x;
+    const int *__restrict__ g = desc[f].labels + (size_t)y * w;
+    for (int i = threadIdx.x; i < w; i += blockDim.x) grow[i] = g[i];
+    __syncthreads();
+    float *__restrict__ out = desc[f].dt + (size_t)y * w;
+    for (int x = threadIdx.x; x < w; x += blockDim.x) {
+        const int g0 = grow[x];
+        int best = g0 * g0;
+        const int rmax = max(x, w - 1 - x);
+        for (int r = 1; r <= rmax && r * r < best; ++r) {
+            const int r2 = r * r;
+            if (x - r >= 0) { const int gl = grow[x - r]; best = min(best, r2 + gl * gl); }
+            if (x + r < w) { const int gr = grow[x + r]; best = min(best, r2 + gr * gr); }
+        }
+        out[x] = best >= kEdtInf * kEdtInf ? 18446744073709551616.0f : sqrtf((float)best);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_opt_struct(const ImgLevel *__restrict__ desc, int w, int h)
+{
+    const int f = blockIdx.z;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)w * h;
+    if (i >= n) return;
+    const float *__restrict__ dt = desc[f].dt;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= (size_t)w && i < (size_t)w * (h - 1)) {
+        o.x = __fmul_rn(0.5f, __fsub_rn(dt[i - 1], dt[i + 1]));
+        o.y = __fmul_rn(0.5f, __fsub_rn(dt[i - w], dt[i + w]));
+        o.z = dt[i];
+    }
+    desc[f].opt[i] = o;
+}
+
+int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h)
+{
+    {
+        dim3 grid(cdiv(w, 64), 1, n);
+        k_edt_cols<<<grid, 64, 0, ctx->stream>>>(d_desc, w, h);
+        LAUNCH_CHECK(ctx);
+    }
+    {
+        dim3 grid(h, 1, n);
+        k_edt_rows<<<grid, 256, w * sizeof(int), ctx->stream>>>(d_desc, w, h);
+        LAUNCH_CHECK(ctx);
+    }
+    {
+        dim3 grid(cdiv(w * h, 256), 1, n);
+        k_opt_struct<<<grid, 256, 0, ctx->stream>>>(d_desc, w, h);
+        LAUNCH_CHECK(ctx);
+    }
+    return REVO_OK;
+}
+
+}  // namespace revo

@@ -1,0 +1,135 @@
+"""GPU parity: ImgPyramidRGBD construction + makeKeyframe through the C ABI vs the oracle
+(cv2 4.13 + C restatement of the reference loops). Byte/integer work: bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import synth_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _settings(cam, n_levels):
+    from revo_b200 import api
+
+    fx, fy, cx, cy, w, h = cam
+    return api.ImgPyramidSettings(PYR_MIN_LVL=n_levels - 1, PYR_MAX_LVL=0, width=w, height=h, fx=fx, fy=fy, cx=cx, cy=cy)
+
+
+def _oracle_pyr(orc, cam, n_levels, bgr, depth, keyframe=True, n_percentage=0.3):
+    from oracle import oracle as O
+
+    cfg = O.PyrCfg(n_levels=n_levels, n_percentage=n_percentage)
+    p = O.build_pyramid(orc, cfg, cam, bgr, depth, backend="cv2")
+    if keyframe:
+        O.make_keyframe(orc, p, backend="cv2")
+    return p
+
+
+def _compare(pg, po, n_levels, keyframe=True):
+    for l in range(n_levels):
+        assert np.array_equal(pg.returnGray(l), po.gray[l]), f"gray L{l}"
+        assert np.array_equal(pg.returnDepth(l), po.depth[l], equal_nan=True), f"depth L{l}"
+        assert np.array_equal(pg._download(l, 3, np.uint8, lambda c: (c.height, c.width)), po.edges_orig[l]), f"canny L{l}"
+        assert np.array_equal(pg.returnEdges(l), po.edges[l]), f"edges L{l}"
+        assert np.array_equal(pg.returnHist(l), po.hist[l]), f"hist L{l}"
+        e3 = pg.return3DEdges(l)
+        assert e3.shape == po.edges3d[l].shape, f"edge count L{l}: {e3.shape} vs {po.edges3d[l].shape}"
+        assert np.array_equal(e3, po.edges3d[l]), f"edges3d L{l}"
+        assert pg.returnNumEdges(l) == len(po.edges3d[l])
+        # the tracker's tile-major list is a permutation of the reference list
+        dev = pg.return3DEdgesDeviceOrder(l)
+        a = dev[np.lexsort(dev.T[::-1])]
+        b = po.edges3d[l][np.lexsort(po.edges3d[l].T[::-1])]
+        assert np.array_equal(a, b), f"device-order list L{l}"
+        if keyframe:
+            assert np.array_equal(pg.returnDistTransform(l), po.dt[l]), f"dt L{l}"
+            assert np.array_equal(pg.returnOptimizationStructure(l), po.opt[l]), f"opt L{l}"
+
+
+@pytest.mark.parametrize("seed,w,h,n_levels", [(1, 640, 480, 3), (2, 640, 480, 4), (3, 320, 240, 3), (5, 1920, 1080, 3)])
+def test_pyramid_bit_exact(ctx, orc32, seed, w, h, n_levels):
+    from revo_b200 import api
+
+    p = synth_pair(seed, w, h)
+    bgr, depth = p["key"]
+    st = _settings(p["cam"], n_levels)
+    pg = api.ImgPyramidRGBD(ctx, st, None, bgr, depth, 1.5)
+    pg.makeKeyframe()
+    po = _oracle_pyr(orc32, p["cam"], n_levels, bgr, depth)
+    _compare(pg, po, n_levels)
+    assert pg.returnTimestamp() == 1.5
+
+
+def test_pyramid_fill_in_path(ctx, orc32):
+    """Sparse texture -> fraction of non-empty patches < nPercentage -> fillInEdges runs (imgpyramidrgbd.cpp:188-196)."""
+    from revo_b200 import api
+
+    rng = np.random.default_rng(7)
+    h, w = 480, 640
+    bgr = np.full((h, w, 3), 90, np.uint8)
+    # a few strong thin structures only: most 20x20 patches stay empty
+    for k in range(6):
+        x0, y0 = int(rng.integers(20, w - 120)), int(rng.integers(20, h - 120))
+        bgr[y0:y0 + int(rng.integers(31, 99)), x0:x0 + int(rng.integers(31, 99))] = int(rng.integers(150, 255))
+    bgr = np.clip(bgr.astype(np.int16) + rng.integers(-2, 3, bgr.shape), 0, 255).astype(np.uint8)
+    depth = (1.0 + 0.5 * rng.random((h, w))).astype(np.float32)
+    depth[rng.random((h, w)) < 0.05] = 0.0
+    depth[rng.random((h, w)) < 0.01] = np.nan
+    cam = (525.0, 525.0, 319.5, 239.5, w, h)
+    st = _settings(cam, 3)
+    pg = api.ImgPyramidRGBD(ctx, st, None, bgr, depth)
+    pg.makeKeyframe()
+    po = _oracle_pyr(orc32, cam, 3, bgr, depth)
+    assert any(po.filled), "test scene must trigger the fill-in path"
+    _compare(pg, po, 3)
+
+
+def test_pyramid_noise_and_empty(ctx, orc32):
+    """Pure noise (max edge density, many tiny components) and a constant image (no edges: DT = 2^64 like cv2)."""
+    from revo_b200 import api
+
+    rng = np.random.default_rng(3)
+    h, w = 240, 320
+    cam = (260.0, 260.0, 159.5, 119.5, w, h)
+    st = _settings(cam, 3)
+    noise = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    depth = np.full((h, w), 2.0, np.float32)
+    for bgr in (noise, np.full((h, w, 3), 77, np.uint8)):
+        pg = api.ImgPyramidRGBD(ctx, st, None, bgr, depth)
+        pg.makeKeyframe()
+        po = _oracle_pyr(orc32, cam, 3, bgr, depth)
+        _compare(pg, po, 3)
+
+
+def test_pyramid_batch_matches_single(ctx, orc32):
+    from revo_b200 import api
+
+    ps = [synth_pair(s, 320, 240) for s in (11, 12, 13)]
+    st = _settings(ps[0]["cam"], 3)
+    bgr = np.stack([p["cur"][0] for p in ps])
+    depth = np.stack([p["cur"][1] for p in ps])
+    pyrs = api.ImgPyramidRGBD.create_batch(ctx, st, bgr, depth, timestamps=[0.1, 0.2, 0.3])
+    api.ImgPyramidRGBD.makeKeyframes(ctx, pyrs)
+    for i, pg in enumerate(pyrs):
+        po = _oracle_pyr(orc32, ps[i]["cam"], 3, bgr[i], depth[i])
+        _compare(pg, po, 3)
+        assert abs(pg.returnTimestamp() - 0.1 * (i + 1)) < 1e-12
+
+
+def test_bgra_input_and_errors(ctx, orc32):
+    from revo_b200 import api
+
+    p = synth_pair(3, 320, 240)
+    bgr, depth = p["key"]
+    bgra = np.concatenate([bgr, np.full(bgr.shape[:2] + (1,), 255, np.uint8)], axis=2)
+    st = _settings(p["cam"], 3)
+    pg = api.ImgPyramidRGBD(ctx, st, None, bgra, depth)
+    po = _oracle_pyr(orc32, p["cam"], 3, bgr, depth, keyframe=False)
+    _compare(pg, po, 3, keyframe=False)
+    # returnOptimizationStructure before makeKeyframe: error code instead of the reference's exit(0)
+    with pytest.raises(api.RevoError) as ei:
+        pg.returnOptimizationStructure(0)
+    assert ei.value.code == 4
+    with pytest.raises(api.RevoError) as ei:
+        pg.returnGray(5)
+    assert ei.value.code == 6
