@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s and GN-iterations/s of the edge-based RGB-D tracking hot path on B200.
+
+Workload (BASELINE.json configs[1]): TUM-fr1-style synthetic VGA streams, 4-level pyramid, Canny edges.
+One STEP = every one of the B independent streams on a GPU advances by one frame: ImgPyramidRGBD
+construction (gray, Canny, depth pyramid, 3-D edge lists) for B frames, coarse-to-fine GN/LM tracking of the
+B frames against their keyframes in one persistent kernel, and -- every `kf_interval` steps -- keyframe
+promotion (exact EDT + lookup structure).  Streams shard over GPUs with no collective (weak scaling).
+
+  value  : frames/s, inputs already resident in HBM when the timed region starts
+  e2e    : frames/s through the same public API with pinned HOST buffers (H2D of every frame and D2H of
+           every pose inside the timed region)
+  roofline: the persistent residual/Jacobian/normal-equation kernel (k_track), algorithmic 60 B per edge
+           point per evaluation / its CUDA-event time, against the measured HBM copy bandwidth
+  cpu_baseline / --impl reference: the CPU oracle (port of the reference's OpenCV/Eigen path; the reference
+           itself cannot be built in this image) on the box's host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=128, help="independent streams (frames per step) per GPU")
+    ap.add_argument("--ref-streams", type=int, default=32, help="streams per step of the CPU reference arm / cpu_baseline")
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--levels", type=int, default=4)
+    ap.add_argument("--kf-interval", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ctas-per-pair", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU oracle backend (reference arm / cpu_baseline ONLY -- never on the product path)
+# ---------------------------------------------------------------------------------------------
+class OracleBackend:
+    """The reference's CPU path restated (oracle/): OpenCV kernels through cv2 (all cores), the hand-written
+    loops and the tracker through the C port (tracker: OpenMP over independent pairs)."""
+
+    def __init__(self, cam, n_levels):
+        from oracle import oracle as O
+
+        self.O = O
+        self.orc = O.Oracle("f32")
+        self.cfg = O.PyrCfg(n_levels=n_levels)
+        self.cam = cam
+        self.n_levels = n_levels
+        self.ocfg = self.orc.default_cfg()
+
+    def create(self, bgr, depth, n):
+        return [self.O.build_pyramid(self.orc, self.cfg, self.cam, bgr[i], depth[i]) for i in range(n)]
+
+    def make_keyframes(self, handles):
+        for p in handles:
+            if not p.dt:
+                self.O.make_keyframe(self.orc, p)
+
+    def track(self, Rs, Ts, refs, curs):
+        r = self.orc.track_frames_batch(refs, curs, list(Rs), list(Ts), self.ocfg, self.n_levels - 1, 0, True)
+        n_pts = np.zeros((len(refs), 6), np.int64)
+        for i, c in enumerate(curs):
+            for l in range(self.n_levels):
+                n_pts[i, l] = len(c.edges3d[l])
+        return dict(R=r["R"].astype(np.float32), T=r["T"].astype(np.float32), status=r["status"], n_evals=r["evals"], n_pts=n_pts)
+
+    def destroy(self, handles):
+        pass
+
+
+def run_cpu(args, bgr_h, depth_h, cam, n_streams, steps, warmup):
+    """Times `steps` steps of `n_streams` streams on the host cores. bgr_h/depth_h: numpy (F, S, ...)."""
+    from revo_b200.stream import StreamTracker
+
+    be = OracleBackend(cam, args.levels)
+    st = StreamTracker(be, n_streams, args.kf_interval)
+    st.start(bgr_h[0, :n_streams], depth_h[0, :n_streams])
+    for i in range(1, warmup + 1):
+        st.step(bgr_h[i, :n_streams], depth_h[i, :n_streams])
+    ev0 = st.total_evals
+    t0 = time.perf_counter()
+    for i in range(warmup + 1, warmup + 1 + steps):
+        st.step(bgr_h[i, :n_streams], depth_h[i, :n_streams])
+    dt = time.perf_counter() - t0
+    return dict(seconds=dt, frames=steps * n_streams, evals=st.total_evals - ev0, T_w_c=st.T_w_c.copy())
+
+
+def pose_errors(T_est, poses_gt, frame):
+    """Mean rotation (rad) / translation (m) error of the estimated world poses against the renderer's ground truth
+    (both relative to each stream's first frame)."""
+    from revo_b200 import synth
+
+    er, et = [], []
+    for s in range(T_est.shape[0]):
+        T_gt = np.linalg.inv(poses_gt[s][0]) @ poses_gt[s][frame]
+        D = np.linalg.inv(T_gt) @ T_est[s].astype(np.float64)
+        er.append(synth.rot_angle(D[:3, :3]))
+        et.append(float(np.linalg.norm(D[:3, 3])))
+    return float(np.mean(er)), float(np.mean(et))
+
+
+def main():
+    args = parse_args()
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+    n_frames = 1 + W + K
+    w, h = args.width, args.height
+
+    # ------------------------------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from revo_b200 import synth_torch
+
+        S = args.ref_streams
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        bgr = torch.empty((n_frames, S, h, w, 3), dtype=torch.uint8)
+        depth = torch.empty((n_frames, S, h, w), dtype=torch.float32)
+        cam, poses = synth_torch.render_streams([2000 + s for s in range(S)], n_frames, w, h, dev, bgr, depth)
+        from oracle import oracle as O
+
+        O.build()
+        import cv2
+
+        r = run_cpu(args, bgr.numpy(), depth.numpy(), cam, S, K, W)
+        er, et = pose_errors(r["T_w_c"], poses, W + K)
+        fps = r["frames"] / r["seconds"]
+        cores = os.cpu_count()
+        line = {
+            "impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * r["seconds"] / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gn_iters_per_sec": r["evals"] / r["seconds"],
+            "config": {"workload": f"TUM-fr1-style synthetic {w}x{h} RGB-D streams, {args.levels}-level pyramid, Canny 150/100, "
+                                   f"keyframe every {args.kf_interval} frames; bounded sample: {S} streams x {K} frames per run",
+                       "streams_per_step": S},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{S} streams x {K} timed frames ({r['frames']} frames); OpenCV kernels via cv2 "
+                                       f"{cv2.__version__} ({cv2.getNumThreads()} threads), loops + tracker = C port of the "
+                                       f"reference (OpenMP over independent pairs)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "pose_error_vs_ground_truth": {"rot_rad": er, "trans_m": et},
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------- our arm
+    from revo_b200 import api, synth_torch
+    from revo_b200.stream import CudaBackend, StreamTracker
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.streams
+    ctx = api.Context(local_rank)
+    if args.ctas_per_pair or args.threads:
+        ctx.set_track_shape(args.ctas_per_pair, args.threads)
+    ext_stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    # ---- synthetic inputs: B distinct streams per rank, rendered on the GPU into pinned host memory ----
+    bgr_h = torch.empty((n_frames, B, h, w, 3), dtype=torch.uint8).pin_memory()
+    depth_h = torch.empty((n_frames, B, h, w), dtype=torch.float32).pin_memory()
+    seeds = [2000 + rank * B + s for s in range(B)]
+    cam, poses = synth_torch.render_streams(seeds, n_frames, w, h, torch.device("cuda", local_rank), bgr_h, depth_h)
+    bgr_d = bgr_h.to(torch.device("cuda", local_rank))
+    depth_d = depth_h.to(torch.device("cuda", local_rank))
+    torch.cuda.synchronize()
+
+    fx, fy, cx, cy, _, _ = cam
+    settings = api.ImgPyramidSettings(PYR_MIN_LVL=args.levels - 1, PYR_MAX_LVL=0, width=w, height=h, fx=fx, fy=fy, cx=cx, cy=cy)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_run(src_bgr, src_depth, sample_clocks):
+        be = CudaBackend(ctx, settings)
+        st = StreamTracker(be, B, args.kf_interval)
+        st.start(src_bgr[0], src_depth[0])
+        for i in range(1, W + 1):
+            st.step(src_bgr[i], src_depth[i])
+        ctx.synchronize()
+        ev0, pe0, l0 = st.total_evals, st.total_point_evals, ctx.launch_count
+        k9_ms = pyr_ms = kf_ms = 0.0
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(ext_stream)
+        for i in range(W + 1, W + 1 + K):
+            st.step(src_bgr[i], src_depth[i])
+            p, kf, k9 = ctx.last_timings()
+            pyr_ms += p
+            k9_ms += k9
+            if st.frame % args.kf_interval == 0:
+                kf_ms += kf
+        e1.record(ext_stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        res = dict(ms=ms, wall=wall, evals=st.total_evals - ev0, point_evals=st.total_point_evals - pe0,
+                   launches=ctx.launch_count - l0, k9_ms=k9_ms, pyr_ms=pyr_ms, kf_ms=kf_ms, T_w_c=st.T_w_c.copy(), clocks=clocks,
+                   n_pts=st.last["n_pts"].mean(axis=0).tolist(), n_evals=st.last["n_evals"].mean(axis=0).tolist())
+        st.close()
+        return res
+
+    dev_run = timed_run(bgr_d, depth_d, sample_clocks=True)       # inputs resident in HBM
+    host_run = timed_run(bgr_h, depth_h, sample_clocks=False)     # pinned host inputs, H2D inside the timed region
+
+    frames_rank = K * B
+    tot = torch.tensor([float(dev_run["evals"]), float(dev_run["point_evals"]), float(dev_run["launches"])], device="cuda",
+                       dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tot)
+    evals_all, point_evals_all, launches_all = [float(x) for x in tot.tolist()]
+    frames_all = frames_rank * world
+    value = frames_all / (dev_run["ms"] * 1e-3)
+    e2e = frames_all / (host_run["ms"] * 1e-3)
+    er, et = pose_errors(dev_run["T_w_c"], poses, W + K)
+
+    # roofline of the dominant kernel (rank 0's launches): algorithmic 60 B / point / evaluation
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    k9_s = dev_run["k9_ms"] * 1e-3
+    achieved = 60.0 * dev_run["point_evals"] / k9_s / 1e9 if k9_s > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k_track_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_run["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"TUM-fr1-style synthetic {w}x{h} RGB-D streams, {args.levels}-level pyramid, Canny 150/100, "
+                               f"keyframe every {args.kf_interval} frames (BASELINE.json configs[1])",
+                   "streams_per_gpu": B, "frames_per_step": B * world, "parallelism": f"stream-shard x{world}, no collective",
+                   "l2_policy": f"inputs larger than L2: every step touches {B} new frames "
+                                f"({B * w * h * 7 / 1e6:.0f} MB of bgr+depth) plus {B} keyframe structures"},
+        "gn_iters_per_sec": evals_all / (dev_run["ms"] * 1e-3),
+        "gn_iters_per_sec_tracking_kernel": dev_run["evals"] / k9_s if k9_s > 0 else None,
+        "gpu_launches": int(launches_all),
+        "phase_ms_per_step": {"pyramid": dev_run["pyr_ms"] / K, "keyframe": dev_run["kf_ms"] / K, "track_kernel": dev_run["k9_ms"] / K,
+                              "whole_step": dev_run["ms"] / K},
+        "mean_edge_points_per_level": dev_run["n_pts"], "mean_evals_per_level": dev_run["n_evals"],
+        "pose_error_vs_ground_truth": {"rot_rad": er, "trans_m": et},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * w * h * 7), "d2h_bytes_per_step": int(B * 128),
+                "ms_per_step": host_run["ms"] / K},
+        "roofline": {"kernel": "k_track (persistent residual/Jacobian/6x6 reduce + LM)", "bound": "hbm", "achieved": achieved,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                     "traffic": traffic, "algorithmic_bytes": 60.0 * dev_run["point_evals"] / K,
+                     "note": "algorithmic bytes = 60 B x sum(n_pts x n_evals); keyframe structures of a pair stay L2-resident "
+                             "across its LM iterations, so achieved may exceed DRAM traffic"},
+        "clocks": dev_run["clocks"],
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+
+        O.build()
+        import cv2
+
+        S = min(args.ref_streams, B)
+        r = run_cpu(args, bgr_h.numpy(), depth_h.numpy(), cam, S, min(K, 4), 1)
+        line["cpu_baseline"] = {"value": r["frames"] / r["seconds"], "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                "gn_iters_per_sec": r["evals"] / r["seconds"],
+                                "sample": f"{S} of the {B} streams x {min(K, 4)} frames ({r['frames']} frames, {r['seconds']:.1f} s); "
+                                          f"cv2 {cv2.__version__} ({cv2.getNumThreads()} threads) + C port of the reference loops/tracker"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

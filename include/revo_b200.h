@@ -125,6 +125,7 @@ typedef struct revo_track_result {
     int32_t rc;                       /* REVO_OK or REVO_ERR_NOT_ORTHOGONAL for this pair */
     revo_residual_info res;           /* of the last evaluation (tracker.cpp:351 uses good/bad) */
     int32_t n_evals[REVO_MAX_LEVELS]; /* fused evaluations ("GN iterations") per level */
+    int32_t n_pts[REVO_MAX_LEVELS];   /* 3-D edge points of the current frame per level (return3DEdges(l).cols()) */
     int32_t used_identity_init;       /* 1 if checkInitializationValues reset (R,t) to identity */
 } revo_track_result;
 
@@ -165,6 +166,9 @@ REVO_API const char *revo_last_error(revo_ctx *ctx); /* text of the last CUDA fa
 REVO_API uint64_t revo_ctx_stream(revo_ctx *ctx);
 /* number of kernels this library has launched on the context so far */
 REVO_API uint64_t revo_ctx_launch_count(revo_ctx *ctx);
+/* Device time (CUDA events on the context stream) of the most recent completed pyramid-construction,
+ * keyframe-promotion and tracking-kernel launches, in milliseconds (0 if none yet). Synchronises. */
+REVO_API int revo_ctx_last_timings(revo_ctx *ctx, float *pyramid_ms, float *keyframe_ms, float *track_kernel_ms);
 
 /* ---- ImgPyramidRGBD ------------------------------------------------------ */
 /* ImgPyramidRGBD(settings, camPyr, rgb, depth, ts) -- imgpyramidrgbd.cpp:43-96.

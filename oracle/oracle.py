@@ -413,6 +413,23 @@ def _add_level_edge(orc, cfg, pyr, gray, depth, cam, lvl, backend):
     pyr.edges3d.append(orc.edges3d(edges, depth, cam, cfg.depth_min, cfg.depth_max))  # :199-226
 
 
+def cv2_distance_transform(edges: np.ndarray) -> np.ndarray:
+    """``cv::distanceTransform(255-edges, CV_DIST_L2, CV_DIST_MASK_PRECISE)`` through OpenCV's OWN
+    implementation (trueDistTrans).  cv2 4.13 routes images with fewer than 2^14 pixels (or any image when
+    it runs single-threaded) to Intel IPP instead (distransform.cpp, IPP_DISABLE_PERF_TRUE_DIST_MT), whose
+    square root is 1 ulp off the correctly rounded value on some inputs; every VGA-or-larger level goes
+    through trueDistTrans = exactly sqrtf(d^2).  The parity target is that exact definition, so the IPP
+    branch is switched off around this one call."""
+    import cv2
+
+    had = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        return cv2.distanceTransform(255 - edges, cv2.DIST_L2, cv2.DIST_MASK_PRECISE)
+    finally:
+        cv2.ipp.setUseIPP(had)
+
+
 def make_keyframe(orc: Oracle, pyr: Pyramid, backend: str = "cv2") -> None:
     """``ImgPyramidRGBD::makeKeyframe`` (imgpyramidrgbd.cpp:231-252)."""
     pyr.dt, pyr.opt = [], []
@@ -420,7 +437,7 @@ def make_keyframe(orc: Oracle, pyr: Pyramid, backend: str = "cv2") -> None:
         if backend == "cv2":
             import cv2
 
-            dt = cv2.distanceTransform(255 - pyr.edges[lvl], cv2.DIST_L2, cv2.DIST_MASK_PRECISE)  # :241
+            dt = cv2_distance_transform(pyr.edges[lvl])  # :241
         else:
             dt = orc.edt(pyr.edges[lvl])
         pyr.dt.append(dt)

@@ -65,7 +65,7 @@ class revo_residual_info(C.Structure):
 class revo_track_result(C.Structure):
     _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("error", C.c_float), ("status", C.c_int32),
                 ("rc", C.c_int32), ("res", revo_residual_info), ("n_evals", C.c_int32 * MAX_LEVELS),
-                ("used_identity_init", C.c_int32)]
+                ("n_pts", C.c_int32 * MAX_LEVELS), ("used_identity_init", C.c_int32)]
 
 
 class revo_trace_entry(C.Structure):
@@ -76,7 +76,7 @@ class revo_trace_entry(C.Structure):
 TRACK_RESULT_DTYPE = np.dtype([("R", np.float32, (9,)), ("t", np.float32, (3,)), ("error", np.float32),
                                ("status", np.int32), ("rc", np.int32), ("good", np.int32), ("bad", np.int32),
                                ("sum_unw", np.float32), ("sum_w", np.float32), ("n_evals", np.int32, (MAX_LEVELS,)),
-                               ("used_identity_init", np.int32)])
+                               ("n_pts", np.int32, (MAX_LEVELS,)), ("used_identity_init", np.int32)])
 assert TRACK_RESULT_DTYPE.itemsize == C.sizeof(revo_track_result)
 
 # revo_pyr_download selectors
@@ -88,7 +88,7 @@ SPLIT_HANDLE_BYTES = 128
 EXPORTED_SYMBOLS = [
     "revo_pyr_config_default", "revo_opt_config_default", "revo_tracker_config_default", "revo_ctx_create",
     "revo_ctx_destroy", "revo_ctx_synchronize", "revo_strerror", "revo_last_error", "revo_ctx_stream",
-    "revo_ctx_launch_count", "revo_pyr_create", "revo_pyr_create_batch", "revo_pyr_make_keyframe",
+    "revo_ctx_launch_count", "revo_ctx_last_timings", "revo_pyr_create", "revo_pyr_create_batch", "revo_pyr_make_keyframe",
     "revo_pyr_make_keyframe_batch", "revo_pyr_destroy", "revo_pyr_is_keyframe", "revo_pyr_level_camera",
     "revo_pyr_timestamp", "revo_pyr_num_edges", "revo_pyr_download", "revo_pyr_upload_level", "revo_eval",
     "revo_track_level", "revo_track", "revo_track_batch", "revo_ctx_set_track_shape", "revo_split_export",
@@ -113,6 +113,7 @@ def load_library():
     lib.revo_ctx_stream.argtypes = [vp]
     lib.revo_ctx_launch_count.restype = C.c_uint64
     lib.revo_ctx_launch_count.argtypes = [vp]
+    lib.revo_ctx_last_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.revo_pyr_timestamp.restype = C.c_double
     lib.revo_pyr_timestamp.argtypes = [vp]
     lib.revo_ctx_create.argtypes = [i32, C.POINTER(vp)]
@@ -291,6 +292,12 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.revo_ctx_launch_count(self.h))
+
+    def last_timings(self):
+        """(pyramid_ms, keyframe_ms, track_kernel_ms) of the most recent launches (CUDA events on the context stream)."""
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        self.check(self.lib.revo_ctx_last_timings(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def set_track_shape(self, ctas_per_pair: int = 0, threads_per_cta: int = 0):
         self.check(self.lib.revo_ctx_set_track_shape(self.h, ctas_per_pair, threads_per_cta))

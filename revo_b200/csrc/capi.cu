@@ -143,6 +143,7 @@ int revo_ctx_create(int device, revo_ctx **out)
     ctx->launches = 0;
     ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0;
     ctx->track_ctas_per_pair = 0; ctx->track_threads = 0;
+    for (auto &v : ctx->ev_valid) v = false;
     ctx->split_rank = 0; ctx->split_world = 1; ctx->split_local = nullptr; ctx->split_seq = 0;
     for (auto &p : ctx->split_peers) p = nullptr;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
@@ -157,6 +158,7 @@ int revo_ctx_create(int device, revo_ctx **out)
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
     (void)cudaGetLastError();
     *out = ctx;
     return REVO_OK;
@@ -172,6 +174,7 @@ int revo_ctx_destroy(revo_ctx *ctx)
     if (ctx->split_local) cudaFree(ctx->split_local);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto &e : ctx->ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     (void)cudaGetLastError();
     delete ctx;
@@ -188,6 +191,20 @@ int revo_ctx_synchronize(revo_ctx *ctx)
 const char *revo_last_error(revo_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 uint64_t revo_ctx_stream(revo_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
 uint64_t revo_ctx_launch_count(revo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int revo_ctx_last_timings(revo_ctx *ctx, float *pyramid_ms, float *keyframe_ms, float *track_kernel_ms)
+{
+    if (!ctx) return REVO_ERR_INVALID_ARG;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float *out[3] = {pyramid_ms, keyframe_ms, track_kernel_ms};
+    for (int i = 0; i < 3; ++i) {
+        if (!out[i]) continue;
+        *out[i] = 0.f;
+        if (ctx->ev_valid[i]) REVO_CUDA(ctx, cudaEventElapsedTime(out[i], ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+    }
+    return REVO_OK;
+}
 
 int revo_ctx_set_track_shape(revo_ctx *ctx, int ctas_per_pair, int threads_per_cta)
 {
@@ -335,6 +352,7 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
     if (hi > 0) hi *= hi;
     const int low = (int)floor(lo), high = (int)floor(hi);
 
+    cudaEventRecord(ctx->ev[0], ctx->stream);
     rc = launch_gray(ctx, d_bgr, (size_t)w0 * channels, channels, bgr_frame, slab->d_desc[0], n, w0, h0);
     for (int l = 0; l < NL && !rc; ++l) {
         if (l > 0) rc = launch_pyrdown_depth(ctx, slab->d_desc[l - 1], slab->d_desc[l], n, g[l].w, g[l].h, g[l - 1].w, g[l - 1].h);
@@ -346,6 +364,8 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
         if (!rc) rc = launch_compact(ctx, slab->d_desc[l], n, g[l].w, g[l].h, cfg->depth_min, cfg->depth_max);
     }
     if (rc) return fail(rc);
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->ev_valid[0] = true;
     for (int f = 0; f < n; ++f) pyr_out[f] = pyrs[f];
     return REVO_OK;
 }
@@ -414,7 +434,10 @@ int revo_pyr_make_keyframe_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs)
     REVO_CUDA(ctx, cudaMallocAsync((void **)&d_tab, sizeof(ImgLevel) * host.size(), ctx->stream));
     REVO_CUDA(ctx, cudaMemcpyAsync(d_tab, host.data(), sizeof(ImgLevel) * host.size(), cudaMemcpyHostToDevice, ctx->stream));
     int rc = REVO_OK;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
     for (int l = 0; l < NL && !rc; ++l) rc = launch_keyframe(ctx, d_tab + (size_t)l * m, m, todo[0]->lv[l].w, todo[0]->lv[l].h);
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    ctx->ev_valid[1] = true;
     cudaFreeAsync(d_tab, ctx->stream);
     if (rc) return rc;
     for (auto *p : todo) p->is_keyframe = true;
@@ -596,7 +619,10 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     cudaError_t e = cudaMemcpyAsync(d_pairs, host.data(), sizeof(PairDesc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_res, 0, b_res + b_rec, ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "track upload");
+    cudaEventRecord(ctx->ev[4], ctx->stream);
     if (!rc) rc = launch_track(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, nullptr);
+    cudaEventRecord(ctx->ev[5], ctx->stream);
+    ctx->ev_valid[2] = true;
     if (!rc && results) {
         e = cudaMemcpyAsync(results, d_res, sizeof(revo_track_result) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
         if (e != cudaSuccess) rc = cuda_fail(ctx, e, "results download");

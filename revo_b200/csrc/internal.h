@@ -68,6 +68,8 @@ struct revo_ctx {
     size_t pinned_bytes;
     int track_ctas_per_pair;
     int track_threads;
+    cudaEvent_t ev[6];      // pyramid begin/end, keyframe begin/end, track kernel begin/end
+    bool ev_valid[3];
     // split mode (multi-GPU single pair)
     int split_rank, split_world;
     void *split_local;                 // this rank's mailbox (device memory, IPC-exported)

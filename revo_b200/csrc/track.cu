@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kThreads) k_track(const PairDesc *__restrict__
                 o.rc = REVO_ERR_NOT_ORTHOGONAL;
                 o.res.good_pts_edges = o.res.bad_pts_edges = 0;
                 o.res.sum_error_unweighted = o.res.sum_error_weighted = 0.f;
-                for (int l = 0; l < REVO_MAX_LEVELS; ++l) o.n_evals[l] = 0;
+                for (int l = 0; l < REVO_MAX_LEVELS; ++l) { o.n_evals[l] = 0; o.n_pts[l] = 0; }
                 o.used_identity_init = 0;
                 if (trace_counts) trace_counts[pair] = 0;
             }
@@ -598,7 +598,10 @@ __global__ void __launch_bounds__(kThreads) k_track(const PairDesc *__restrict__
             // tracker.cpp:351: good/bad < 4 -> NEW_KF (double division; bad == 0 -> inf -> OK)
             o.status = ((double)last_good / (double)last_bad < 4.0) ? REVO_TRACKER_STATE_NEW_KF : REVO_TRACKER_STATE_OK;
             o.rc = REVO_OK;
-            for (int l = 0; l < REVO_MAX_LEVELS; ++l) o.n_evals[l] = evals_lvl[l];
+            for (int l = 0; l < REVO_MAX_LEVELS; ++l) {
+                o.n_evals[l] = evals_lvl[l];
+                o.n_pts[l] = (l >= max_lvl && l <= min_lvl) ? *P.lvl[l].n_pts : 0;
+            }
             o.used_identity_init = used_identity;
             if (trace_counts) trace_counts[pair] = ntrace < prm.trace_cap ? ntrace : prm.trace_cap;
         }

@@ -1,0 +1,123 @@
+"""Minimal multi-stream driver of the hot path: B independent RGB-D streams advance one frame per step.
+
+This is the slice of ``REVO::start`` (system/system.cpp:128-283) the tracker needs to run on a stream:
+the motion-model initialisation ``T_init = T_kf_N * T_NM1_N`` (system.cpp:262-271), world-pose
+composition, and promotion of a frame to keyframe (``makeKeyframe`` + re-initialisation with
+``T_NM1_N``, system.cpp:203-216).  The tracking-quality vote that decides WHEN to switch keyframes
+(``assessTrackingQuality``) is a "next" row; here a keyframe is promoted every
+``kf_interval`` frames.
+
+The backend object does the actual work (the CUDA library in production; bench.py plugs the CPU oracle
+in for the reference arm) and must provide::
+
+    create(bgr, depth, n) -> list of frame handles        (ImgPyramidRGBD construction)
+    make_keyframes(handles)                                (makeKeyframe)
+    track(Rs, Ts, refs, curs) -> dict(R (n,3,3), T (n,3), status (n,), n_evals (n,6), n_pts (n,6))
+    destroy(handles)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _inv(T: np.ndarray) -> np.ndarray:
+    """Batched inverse of rigid 4x4 transforms."""
+    R = T[:, :3, :3]
+    t = T[:, :3, 3]
+    Ti = np.tile(np.eye(4, dtype=T.dtype), (T.shape[0], 1, 1))
+    Rt = R.transpose(0, 2, 1)
+    Ti[:, :3, :3] = Rt
+    Ti[:, :3, 3] = -np.einsum("nij,nj->ni", Rt, t)
+    return Ti
+
+
+class StreamTracker:
+    def __init__(self, backend, n_streams: int, kf_interval: int = 10):
+        self.be = backend
+        self.B = n_streams
+        self.kf_interval = kf_interval
+        self.kf = None                      # keyframe handles (one per stream)
+        self.prev = None                    # previous-frame handles
+        eye = np.tile(np.eye(4, dtype=np.float32), (n_streams, 1, 1))
+        self.T_w_kf = eye.copy()            # keyframe pose in the world
+        self.T_kf_prev = eye.copy()         # previous frame relative to its keyframe (T_kf_N)
+        self.T_nm1_n = eye.copy()           # last inter-frame motion (T_NM1_N)
+        self.T_w_c = eye.copy()             # current world pose of every stream
+        self.frame = 0
+        self.total_evals = 0
+        self.total_point_evals = 0          # sum over pairs/levels of n_pts * n_evals (roofline numerator / 60 B)
+        self.last = None
+
+    def start(self, bgr, depth):
+        """First frame of every stream: becomes the keyframe (system.cpp:151-175)."""
+        self.kf = self.be.create(bgr, depth, self.B)
+        self.be.make_keyframes(self.kf)
+        self.prev = None
+        self.frame = 0
+
+    def step(self, bgr, depth):
+        """Track the next frame of every stream against its keyframe."""
+        cur = self.be.create(bgr, depth, self.B)
+        T_init = self.T_kf_prev @ self.T_nm1_n                     # system.cpp:268
+        out = self.be.track(T_init[:, :3, :3], T_init[:, :3, 3], self.kf, cur)
+        T_kf_n = np.tile(np.eye(4, dtype=np.float32), (self.B, 1, 1))
+        T_kf_n[:, :3, :3] = out["R"]
+        T_kf_n[:, :3, 3] = out["T"]
+        self.T_nm1_n = _inv(self.T_kf_prev) @ T_kf_n               # system.cpp:266
+        self.T_w_c = self.T_w_kf @ T_kf_n                          # system.cpp:192
+        self.frame += 1
+        self.total_evals += int(out["n_evals"].sum())
+        self.total_point_evals += int((out["n_evals"].astype(np.int64) * out["n_pts"].astype(np.int64)).sum())
+        self.last = out
+        if self.prev is not None:
+            self.be.destroy(self.prev)
+        if self.frame % self.kf_interval == 0:
+            # promote the frame just tracked (the reference promotes prevPyr and re-tracks; with a fixed
+            # interval the promoted frame's pose is already known): system.cpp:203-216
+            self.be.make_keyframes(cur)
+            self.be.destroy(self.kf)
+            self.kf = cur
+            self.prev = None
+            self.T_w_kf = self.T_w_c.copy()
+            self.T_kf_prev = np.tile(np.eye(4, dtype=np.float32), (self.B, 1, 1))
+        else:
+            self.prev = cur
+            self.T_kf_prev = T_kf_n
+        return out
+
+    def close(self):
+        if self.prev is not None:
+            self.be.destroy(self.prev)
+        if self.kf is not None:
+            self.be.destroy(self.kf)
+        self.prev = self.kf = None
+
+
+class CudaBackend:
+    """The product path: everything through the C ABI (revo_b200/api.py)."""
+
+    def __init__(self, ctx, settings, tracker_settings=None):
+        from . import api
+
+        self.api = api
+        self.ctx = ctx
+        self.settings = settings
+        self.tracker = api.TrackerNew(ctx, tracker_settings or api.TrackerSettings(), settings)
+        self.campyr = api.CameraPyr(settings)
+
+    def create(self, bgr, depth, n):
+        return self.api.ImgPyramidRGBD.create_batch(self.ctx, self.settings, bgr, depth, n=n, channels=3, cameraPyr=self.campyr,
+                                                    synchronize=False)
+
+    def make_keyframes(self, handles):
+        self.api.ImgPyramidRGBD.makeKeyframes(self.ctx, handles)
+
+    def track(self, Rs, Ts, refs, curs):
+        out = self.tracker.trackFramesBatch(Rs, Ts, refs, curs)
+        n = len(refs)
+        R = out["R"].reshape(n, 3, 3).transpose(0, 2, 1)
+        return dict(R=R, T=out["t"], status=out["status"], n_evals=out["n_evals"], n_pts=out["n_pts"], error=out["error"])
+
+    def destroy(self, handles):
+        for h in handles:
+            h.destroy()

@@ -56,7 +56,10 @@ def se3_exp(xi):
 
 
 def rot_angle(R):
-    return float(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1)))
+    """Rotation angle from the skew part (well conditioned for small angles, unlike arccos(trace))."""
+    R = np.asarray(R, np.float64)
+    s = 0.5 * np.linalg.norm([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return float(np.arctan2(s, 0.5 * (np.trace(R) - 1.0)))
 
 
 # ---------------------------------------------------------------------------

@@ -67,5 +67,8 @@ def synth_pair(seed, w=640, h=480, xi=None):
 
 
 def rot_angle(Ra, Rb):
+    """Angle of Ra^T Rb, from the skew part (well conditioned for small angles, unlike arccos(trace))."""
     R = np.asarray(Ra, np.float64).T @ np.asarray(Rb, np.float64)
-    return float(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1)))
+    s = 0.5 * np.linalg.norm([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    c = 0.5 * (np.trace(R) - 1.0)
+    return float(np.arctan2(s, c))
