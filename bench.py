@@ -36,7 +36,7 @@ if ROOT not in sys.path:
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=128, help="independent streams (frames per step) per GPU")
@@ -139,7 +139,7 @@ class OracleBackend:
         pass
 
 
-def run_cpu(args, bgr_h, depth_h, cam, n_streams, steps, warmup):
+def run_cpu(args, bgr_h, depth_h, cam, n_streams, steps, warmup, fidx=lambda i: i):
     """Times `steps` steps of `n_streams` streams on the host cores. bgr_h/depth_h: numpy (F, S, ...)."""
     from revo_b200.stream import StreamTracker
 
@@ -147,11 +147,11 @@ def run_cpu(args, bgr_h, depth_h, cam, n_streams, steps, warmup):
     st = StreamTracker(be, n_streams, args.kf_interval)
     st.start(bgr_h[0, :n_streams], depth_h[0, :n_streams])
     for i in range(1, warmup + 1):
-        st.step(bgr_h[i, :n_streams], depth_h[i, :n_streams])
+        st.step(bgr_h[fidx(i), :n_streams], depth_h[fidx(i), :n_streams])
     ev0 = st.total_evals
     t0 = time.perf_counter()
     for i in range(warmup + 1, warmup + 1 + steps):
-        st.step(bgr_h[i, :n_streams], depth_h[i, :n_streams])
+        st.step(bgr_h[fidx(i), :n_streams], depth_h[fidx(i), :n_streams])
     dt = time.perf_counter() - t0
     return dict(seconds=dt, frames=steps * n_streams, evals=st.total_evals - ev0, T_w_c=st.T_w_c.copy())
 
@@ -178,7 +178,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     W, K = max(args.warmup, 0), max(args.steps, 1)
-    n_frames = 1 + W + K
+    # frames rendered per stream; longer runs walk the stream back and forth (camera reverses), which bounds host memory
+    n_frames = min(1 + W + K, 16)
+
+    def fidx(i):
+        """frame index of step i on the ping-pong path 0,1,..,n-1,n-2,..,1,0,1,.."""
+        period = 2 * (n_frames - 1)
+        j = i % period
+        return j if j < n_frames else period - j
     w, h = args.width, args.height
 
     # ------------------------------------------------------------------------------------- reference arm
@@ -197,8 +204,8 @@ def main():
         O.build()
         import cv2
 
-        r = run_cpu(args, bgr.numpy(), depth.numpy(), cam, S, K, W)
-        er, et = pose_errors(r["T_w_c"], poses, W + K)
+        r = run_cpu(args, bgr.numpy(), depth.numpy(), cam, S, K, W, fidx)
+        er, et = pose_errors(r["T_w_c"], poses, fidx(W + K))
         fps = r["frames"] / r["seconds"]
         cores = os.cpu_count()
         line = {
@@ -255,21 +262,21 @@ def main():
     def timed_run(src_bgr, src_depth, sample_clocks):
         be = CudaBackend(ctx, settings)
         st = StreamTracker(be, B, args.kf_interval)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()     # sampled from the warm-up on: the GPU is under the same load throughout
         st.start(src_bgr[0], src_depth[0])
         for i in range(1, W + 1):
-            st.step(src_bgr[i], src_depth[i])
+            st.step(src_bgr[fidx(i)], src_depth[fidx(i)])
         ctx.synchronize()
         ev0, pe0, l0 = st.total_evals, st.total_point_evals, ctx.launch_count
         k9_ms = pyr_ms = kf_ms = 0.0
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        if sampler:
-            sampler.start()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(ext_stream)
         for i in range(W + 1, W + 1 + K):
-            st.step(src_bgr[i], src_depth[i])
+            st.step(src_bgr[fidx(i)], src_depth[fidx(i)])
             p, kf, k9 = ctx.last_timings()
             pyr_ms += p
             k9_ms += k9
@@ -302,7 +309,7 @@ def main():
     frames_all = frames_rank * world
     value = frames_all / (dev_run["ms"] * 1e-3)
     e2e = frames_all / (host_run["ms"] * 1e-3)
-    er, et = pose_errors(dev_run["T_w_c"], poses, W + K)
+    er, et = pose_errors(dev_run["T_w_c"], poses, fidx(W + K))
 
     # roofline of the dominant kernel (rank 0's launches): algorithmic 60 B / point / evaluation
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -358,12 +365,15 @@ def main():
         import cv2
 
         S = min(args.ref_streams, B)
-        r = run_cpu(args, bgr_h.numpy(), depth_h.numpy(), cam, S, min(K, 4), 1)
+        r = run_cpu(args, bgr_h.numpy(), depth_h.numpy(), cam, S, min(K, 10), 1, fidx)
         line["cpu_baseline"] = {"value": r["frames"] / r["seconds"], "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                 "gn_iters_per_sec": r["evals"] / r["seconds"],
-                                "sample": f"{S} of the {B} streams x {min(K, 4)} frames ({r['frames']} frames, {r['seconds']:.1f} s); "
+                                "sample": f"{S} of the {B} streams x {min(K, 10)} frames ({r['frames']} frames, {r['seconds']:.1f} s); "
                                           f"cv2 {cv2.__version__} ({cv2.getNumThreads()} threads) + C port of the reference loops/tracker"}
     print(json.dumps(line))
+    sys.stderr.write(f"[bench] {value:.0f} frames/s (e2e {e2e:.0f}), {line['gn_iters_per_sec']:.0f} GN-iters/s, step {dev_run['ms'] / K:.2f} ms = "
+                     f"pyr {dev_run['pyr_ms'] / K:.2f} + kf {dev_run['kf_ms'] / K:.2f} + track {dev_run['k9_ms'] / K:.2f} ms, "
+                     f"k_track {achieved:.0f} GB/s algorithmic = {achieved / peak:.3f} of HBM peak\n")
     if dist is not None:
         dist.destroy_process_group()
 

@@ -845,7 +845,8 @@ ORC_API void orc_canny(const uint8_t *gray, int w, int h, double t1, double t2, 
  * (imgpyramidrgbd.cpp:241): exact Euclidean DT, out = sqrtf((float)d2) with d2
  * the integer squared distance to the nearest edge pixel (edges > 0).
  * Meijster's two-scan algorithm in exact integer arithmetic.  An image with
- * no edge pixel yields 2^64 (1.8446744e19f), the constant cv2 4.13 returns. */
+ * no edge pixel yields 65536.0f, the constant cv2 4.13's own trueDistTrans returns
+ * (its IPP branch, used only for images < 2^14 px, returns 2^64 instead -- see oracle.py). */
 ORC_API void orc_edt_l2(const uint8_t *edges, int w, int h, float *dt)
 {
     const int INF = w + h + 1;   /* > any real 1-D distance */
@@ -884,7 +885,7 @@ ORC_API void orc_edt_l2(const uint8_t *edges, int w, int h, float *dt)
             }
         }
         if (q < 0) {
-            for (int x = 0; x < w; ++x) dt[(size_t)y * w + x] = 18446744073709551616.0f;
+            for (int x = 0; x < w; ++x) dt[(size_t)y * w + x] = 65536.0f;
             continue;
         }
         for (int x = w - 1; x >= 0; --x) {

@@ -609,18 +609,20 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     const size_t b_tr = align_up(sizeof(revo_trace_entry) * (size_t)trace_cap * n, 256);
     const size_t b_tc = align_up(sizeof(int) * (size_t)n, 256);
     uint8_t *ws = nullptr;
-    REVO_CUDA(ctx, cudaMallocAsync((void **)&ws, b_pairs + b_res + b_rec + b_tr + b_tc, ctx->stream));
+    REVO_CUDA(ctx, cudaMallocAsync((void **)&ws, b_pairs + b_res + b_rec + b_tr + b_tc + 256, ctx->stream));
     PairDesc *d_pairs = (PairDesc *)ws;
     revo_track_result *d_res = (revo_track_result *)(ws + b_pairs);
     double *d_rec = (double *)(ws + b_pairs + b_res);
     revo_trace_entry *d_tr = trace_cap ? (revo_trace_entry *)(ws + b_pairs + b_res + b_rec) : nullptr;
     int *d_tc = (int *)(ws + b_pairs + b_res + b_rec + b_tr);
+    int *d_wc = (int *)(ws + b_pairs + b_res + b_rec + b_tr + b_tc);
     int rc = REVO_OK;
     cudaError_t e = cudaMemcpyAsync(d_pairs, host.data(), sizeof(PairDesc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_res, 0, b_res + b_rec, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_wc, 0, 256, ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "track upload");
     cudaEventRecord(ctx->ev[4], ctx->stream);
-    if (!rc) rc = launch_track(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, nullptr);
+    if (!rc) rc = launch_track(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);
     cudaEventRecord(ctx->ev[5], ctx->stream);
     ctx->ev_valid[2] = true;
     if (!rc && results) {

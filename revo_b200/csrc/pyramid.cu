@@ -530,6 +530,8 @@ int launch_edges3d_reference_order(revo_ctx *ctx, const ImgLevel *d_desc_one, in
 // K8: {0.5(dt[i-1]-dt[i+1]), 0.5(dt[i-w]-dt[i+w]), dt[i], 0} for rows 1..h-2, zeros elsewhere.
 // ---------------------------------------------------------------------------
 constexpr int kEdtInf = 1 << 14;
+// value of every pixel when the edge map is empty: what OpenCV's own trueDistTrans returns (cv2 4.13, IPP off)
+constexpr float kEdtEmpty = 65536.0f;
 
 __global__ void k_edt_cols(const ImgLevel *__restrict__ desc, int w, int h)
 {
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(256) k_edt_rows(const ImgLevel *__restrict__ d
             if (x - r >= 0) { const int gl = grow[x - r]; best = min(best, r2 + gl * gl); }
             if (x + r < w) { const int gr = grow[x + r]; best = min(best, r2 + gr * gr); }
         }
-        out[x] = best >= kEdtInf * kEdtInf ? 18446744073709551616.0f : sqrtf((float)best);
+        out[x] = best >= kEdtInf * kEdtInf ? kEdtEmpty : sqrtf((float)best);
     }
 }
 

@@ -8,16 +8,17 @@
 //   Optimizer::calculateWarpUpdate (PASS B) + LGS6::update/finish             system/optimizer.cpp:192-234, utils/LGSX.h:320-326,392-398
 //   Eigen LDLT 6x6 solve, Sophus::SE3f exp / product                          system/optimizer.cpp:258-266
 //
-// Design (B200): a frame pair is owned by one thread-block CLUSTER (1..16 CTAs).  PASS A and PASS B are
-// fused: every evaluation at a pose warps each 3-D edge point, fetches the 4 {gx,gy,dt} texels, forms the
-// residual, Huber weight and 1x6 Jacobian and accumulates the 21+6 normal-equation terms + 4 statistics in
-// registers -- the 7 SoA buffers of the reference never exist.  The 32-value record is reduced with a
-// transposing warp-shuffle tree, across warps through shared memory, across the CTAs of the cluster through
-// distributed shared memory (one cluster barrier per evaluation), and -- when one pair is split over several
-// GPUs -- across GPUs through peer-mapped mailboxes over NVLink inside the same kernel.  Every CTA then runs
-// the identical 6x6 LDLT solve, SE3 update and accept/reject test redundantly (bitwise-equal inputs, so no
-// broadcast is needed), so all levels and all LM iterations of a pair run without a host round trip.
-// No tensor cores: there is no dense contraction on this path.
+// Design (B200): a frame pair is owned by one thread-block CLUSTER (1..16 CTAs); clusters pull pairs from a
+// global work counter (persistent kernel).  PASS A and PASS B are fused: every evaluation at a pose warps each
+// 3-D edge point, fetches the 4 {gx,gy,dt} texels, forms the residual, Huber weight and 1x6 Jacobian and
+// accumulates the 21+6 normal-equation terms + 4 statistics in registers -- the 7 SoA buffers of the reference
+// never exist.  Two points are in flight per thread (their 8 texel gathers are issued back to back) to cover the
+// dependent pts -> texel latency.  The 32-value record is reduced with a transposing warp-shuffle tree, across
+// warps through shared memory, across the CTAs of the cluster through distributed shared memory (one cluster
+// barrier per evaluation), and -- when one pair is split over several GPUs -- across GPUs through peer-mapped
+// mailboxes over NVLink inside the same kernel.  Every CTA then runs the identical 6x6 LDL^T solve, SE3 update
+// and accept/reject test redundantly (bitwise-equal inputs, so no broadcast is needed): all levels and all LM
+// iterations of a pair run without a host round trip.  No tensor cores: there is no dense contraction here.
 #include <cooperative_groups.h>
 #include <math.h>
 
@@ -40,6 +41,7 @@ struct Ctrl {
     float t[3];
     int level_done;
     int pair_skip;
+    int next_pair;
 };
 
 struct LMState {
@@ -48,11 +50,11 @@ struct LMState {
     double A[21], b[6], n;
     double inc[6];
     float lastErr, last_residual, lambda;
-    int iteration, incTry, tries, evals;
+    int iteration, incTry, tries;
 };
 
-// ---- small double-precision SE3 / LDLT helpers (thread 0 only) --------------
-__device__ void quat_to_R(const double *q, double *R /* col-major */)
+// ---- small double-precision SE3 / solver helpers (thread 0 only) --------------
+__device__ __forceinline__ void quat_to_R(const double *q, double *R /* col-major */)
 {
     const double x = q[0], y = q[1], z = q[2], w = q[3];
     const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
@@ -109,44 +111,42 @@ __device__ bool rotation_ok(const float *Rf)
     return (sqrt(n2) < 1e-5) && (det > 0);
 }
 
-__device__ void se3_exp(const double *xi, double *q, double *t)
+// Sophus::SE3::exp (se3.hpp:723-748, so3.hpp:531-564) in double; one sincos: sin t = 2 s c, 1 - cos t = 2 s^2.
+__device__ __forceinline__ void se3_exp(const double *xi, double *q, double *t)
 {
     const double ox = xi[3], oy = xi[4], oz = xi[5];
     const double theta_sq = ox * ox + oy * oy + oz * oz;
     const double theta = sqrt(theta_sq);
-    double imag, re;
-    const bool small_angle = theta < 1e-5;   // Sophus::Constants<float>::epsilon()
-    if (small_angle) {
+    double imag, re, c1, c2;
+    if (theta < 1e-5) {   // Sophus::Constants<float>::epsilon()
         const double t4 = theta_sq * theta_sq;
         imag = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * t4;
         re = 1.0 - (1.0 / 8.0) * theta_sq + (1.0 / 384.0) * t4;
+        // V = R(q) there (se3.hpp:735-737) = I + 2 re imag Om + 2 imag^2 Om^2
+        c1 = 2.0 * re * imag;
+        c2 = 2.0 * imag * imag;
     } else {
         double s, c;
         sincos(0.5 * theta, &s, &c);
-        imag = s / theta;
+        const double inv_t = 1.0 / theta, inv_t2 = inv_t * inv_t;
+        imag = s * inv_t;
         re = c;
+        c1 = 2.0 * s * s * inv_t2;                       // (1 - cos t) / t^2
+        c2 = (theta - 2.0 * s * c) * inv_t2 * inv_t;     // (t - sin t) / t^3
     }
     q[0] = imag * ox; q[1] = imag * oy; q[2] = imag * oz; q[3] = re;
-    // V = I + c1 Om + c2 Om^2 ; small angle: V = R(q) (se3.hpp:735-737)
-    double V[9];
-    if (small_angle) {
-        quat_to_R(q, V);
-    } else {
-        double s, c;
-        sincos(theta, &s, &c);
-        const double c1 = (1.0 - c) / theta_sq, c2 = (theta - s) / (theta_sq * theta);
-        // Om = hat(omega); Om^2 = omega omega^T - |omega|^2 I
-        V[0] = 1 + c2 * (ox * ox - theta_sq); V[3] = -c1 * oz + c2 * ox * oy;       V[6] = c1 * oy + c2 * ox * oz;
-        V[1] = c1 * oz + c2 * ox * oy;        V[4] = 1 + c2 * (oy * oy - theta_sq); V[7] = -c1 * ox + c2 * oy * oz;
-        V[2] = -c1 * oy + c2 * ox * oz;       V[5] = c1 * ox + c2 * oy * oz;        V[8] = 1 + c2 * (oz * oz - theta_sq);
-    }
-    for (int i = 0; i < 3; ++i) t[i] = V[i] * xi[0] + V[3 + i] * xi[1] + V[6 + i] * xi[2];
+    // V = I + c1 Om + c2 Om^2 ; Om = hat(omega), Om^2 = omega omega^T - |omega|^2 I
+    const double v00 = 1 + c2 * (ox * ox - theta_sq), v01 = -c1 * oz + c2 * ox * oy, v02 = c1 * oy + c2 * ox * oz;
+    const double v10 = c1 * oz + c2 * ox * oy, v11 = 1 + c2 * (oy * oy - theta_sq), v12 = -c1 * ox + c2 * oy * oz;
+    const double v20 = -c1 * oy + c2 * ox * oz, v21 = c1 * ox + c2 * oy * oz, v22 = 1 + c2 * (oz * oz - theta_sq);
+    t[0] = v00 * xi[0] + v01 * xi[1] + v02 * xi[2];
+    t[1] = v10 * xi[0] + v11 * xi[1] + v12 * xi[2];
+    t[2] = v20 * xi[0] + v21 * xi[1] + v22 * xi[2];
 }
 
 // (qa,ta) * (qb,tb) with Sophus' renormalisation (se3.hpp:317-321, so3.hpp:335-352)
-__device__ void se3_mul(const double *qa, const double *ta, const double *qb, const double *tb, double *q, double *t)
+__device__ __forceinline__ void se3_mul(const double *qa, const double *ta, const double *qb, const double *tb, double *q, double *t)
 {
-    // rotate tb by qa
     double ux = qa[1] * tb[2] - qa[2] * tb[1], uy = qa[2] * tb[0] - qa[0] * tb[2], uz = qa[0] * tb[1] - qa[1] * tb[0];
     ux += ux; uy += uy; uz += uz;
     const double cx = qa[1] * uz - qa[2] * uy, cy = qa[2] * ux - qa[0] * uz, cz = qa[0] * uy - qa[1] * ux;
@@ -166,78 +166,86 @@ __device__ void se3_mul(const double *qa, const double *ta, const double *qb, co
     q[0] = x; q[1] = y; q[2] = z; q[3] = w;
 }
 
-// Pivoted LDL^T solve of a symmetric 6x6 system (Eigen::LDLT semantics, system/optimizer.cpp:262), double.
-// M: full column-major 6x6 (lower triangle used).
-__device__ void ldlt_solve6(double *M, const double *b, double *x)
+// Solve (A/n with diag * lam1) x = b/n for the symmetric positive (semi-)definite 6x6 normal equations
+// (system/optimizer.cpp:258-262, "A.ldlt().solve(b)").  LDL^T in double, fully unrolled so that everything
+// stays in registers; no pivoting (the matrix is a damped sum of outer products; Eigen's diagonal pivoting
+// only changes rounding, which double precision makes irrelevant at the float tolerance of this path).
+// Non-positive / non-finite pivots are treated like Eigen's pseudo-inverse of D: that component becomes 0.
+__device__ __forceinline__ void solve6(const double *Au /* 21 upper slots */, const double *b, double inv_n, double lam1, double *x)
 {
-    constexpr int N = 6;
-    int tr[N];
-#define AM(i, j) M[(j) * N + (i)]
-    for (int k = 0; k < N; ++k) {
-        int p = k;
-        double big = fabs(AM(k, k));
-        for (int i = k + 1; i < N; ++i)
-            if (fabs(AM(i, i)) > big) { big = fabs(AM(i, i)); p = i; }
-        tr[k] = p;
-        if (p != k) {
-            for (int j = 0; j < k; ++j) { const double tmp = AM(k, j); AM(k, j) = AM(p, j); AM(p, j) = tmp; }
-            for (int i = p + 1; i < N; ++i) { const double tmp = AM(i, k); AM(i, k) = AM(i, p); AM(i, p) = tmp; }
-            for (int i = k + 1; i < p; ++i) { const double tmp = AM(i, k); AM(i, k) = AM(p, i); AM(p, i) = tmp; }
-            { const double tmp = AM(k, k); AM(k, k) = AM(p, p); AM(p, p) = tmp; }
-        }
-        if (k > 0) {
-            double temp[N];
-            for (int j = 0; j < k; ++j) temp[j] = AM(j, j) * AM(k, j);
-            double s = 0;
-            for (int j = 0; j < k; ++j) s += AM(k, j) * temp[j];
-            AM(k, k) -= s;
-            for (int i = k + 1; i < N; ++i) {
-                double s2 = 0;
-                for (int j = 0; j < k; ++j) s2 += AM(i, j) * temp[j];
-                AM(i, k) -= s2;
-            }
-        }
-        const double piv = AM(k, k);
-        if (fabs(piv) > 0)
-            for (int i = k + 1; i < N; ++i) AM(i, k) /= piv;
+    double a[6][6];
+    {
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) a[j][i] = Au[s++] * inv_n;   // lower triangle
     }
-    double y[N];
-    for (int i = 0; i < N; ++i) y[i] = b[i];
-    for (int k = 0; k < N; ++k)
-        if (tr[k] != k) { const double tmp = y[k]; y[k] = y[tr[k]]; y[tr[k]] = tmp; }
-    for (int i = 0; i < N; ++i)
-        for (int j = 0; j < i; ++j) y[i] -= AM(i, j) * y[j];
-    for (int i = 0; i < N; ++i) y[i] = (fabs(AM(i, i)) > 1e-300) ? y[i] / AM(i, i) : 0.0;
-    for (int i = N - 1; i >= 0; --i)
-        for (int j = i + 1; j < N; ++j) y[i] -= AM(j, i) * y[j];
-    for (int k = N - 1; k >= 0; --k)
-        if (tr[k] != k) { const double tmp = y[k]; y[k] = y[tr[k]]; y[tr[k]] = tmp; }
-    for (int i = 0; i < N; ++i) x[i] = y[i];
-#undef AM
+    double y[6], invd[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { a[i][i] *= lam1; y[i] = b[i] * inv_n; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double dk = a[k][k];
+        const double id = (dk > 0.0 && dk < 1e300) ? 1.0 / dk : 0.0;
+        invd[k] = id;
+#pragma unroll
+        for (int j = k + 1; j < 6; ++j) {
+            const double ljk = a[j][k] * id;
+#pragma unroll
+            for (int i = j; i < 6; ++i) a[i][j] -= a[i][k] * ljk;
+        }
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) a[i][k] *= id;   // L
+    }
+#pragma unroll
+    for (int i = 1; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) y[i] -= a[i][j] * y[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] *= invd[i];
+#pragma unroll
+    for (int i = 4; i >= 0; --i)
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) y[i] -= a[j][i] * y[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = y[i];
 }
 
-// ---- per-thread accumulation ------------------------------------------------
-// PASS A + PASS B fused for one point.
-__device__ __forceinline__ void accumulate_point(const float4 p, const LevelIn &L, const float *__restrict__ R,
-                                                 const float *__restrict__ t, float edge_dist, bool use_filter, float huber,
-                                                 float (&acc)[32])
+// ---- per-point work: PASS A + PASS B fused ---------------------------------------
+struct Proj {
+    float Wx, Wy, Wz, dx, dy;
+    const float4 *bp;
+    int state;   // 0 = no point, 1 = in bounds (texels wanted), 2 = out of bounds
+};
+
+// optimizer.cpp:93-100: warp, project, bounds test
+__device__ __forceinline__ Proj project(bool exists, const float4 p, const LevelIn &L, const float *__restrict__ R,
+                                        const float *__restrict__ t)
 {
-    // optimizer.cpp:93-95
-    const float Wx = R[0] * p.x + R[3] * p.y + R[6] * p.z + t[0];
-    const float Wy = R[1] * p.x + R[4] * p.y + R[7] * p.z + t[1];
-    const float Wz = R[2] * p.x + R[5] * p.y + R[8] * p.z + t[2];
-    const float u = Wx / Wz * L.fx + L.cx;
-    const float v = Wy / Wz * L.fy + L.cy;
-    if (!(u > 1.f && v > 1.f && u < (float)(L.w - 2) && v < (float)(L.h - 2))) {   // optimizer.cpp:100 (NaN-safe)
-        acc[kRecBad] += 1.f;
-        return;
-    }
+    Proj o;
+    o.Wx = R[0] * p.x + R[3] * p.y + R[6] * p.z + t[0];
+    o.Wy = R[1] * p.x + R[4] * p.y + R[7] * p.z + t[1];
+    o.Wz = R[2] * p.x + R[5] * p.y + R[8] * p.z + t[2];
+    const float u = o.Wx / o.Wz * L.fx + L.cx;
+    const float v = o.Wy / o.Wz * L.fy + L.cy;
+    const bool inb = (u > 1.f && v > 1.f && u < (float)(L.w - 2) && v < (float)(L.h - 2));   // NaN-safe (:100)
+    const int ix = inb ? (int)u : 0, iy = inb ? (int)v : 0;
+    o.dx = u - (float)ix;
+    o.dy = v - (float)iy;
+    o.bp = L.opt + (size_t)iy * L.w + ix;
+    o.state = exists ? (inb ? 1 : 2) : 0;
+    return o;
+}
+
+__device__ __forceinline__ void finish_point(const Proj &P, const float4 t00, const float4 t10, const float4 t01, const float4 t11,
+                                             const LevelIn &L, float edge_dist, bool use_filter, float huber, float (&acc)[32])
+{
+    if (P.state == 0) return;
+    if (P.state == 2) { acc[kRecBad] += 1.f; return; }
     // getInterpolatedElement43, optimizer.h:173-185
-    const int ix = (int)u, iy = (int)v;
-    const float dx = u - (float)ix, dy = v - (float)iy, dxdy = dx * dy;
-    const float4 *bp = L.opt + (size_t)iy * L.w + ix;
-    const float4 t00 = __ldg(bp), t10 = __ldg(bp + 1), t01 = __ldg(bp + L.w), t11 = __ldg(bp + L.w + 1);
-    const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1.f - dx - dy + dxdy;
+    const float dxdy = P.dx * P.dy;
+    const float w11 = dxdy, w01 = P.dy - dxdy, w10 = P.dx - dxdy, w00 = 1.f - P.dx - P.dy + dxdy;
     const float gxi = w11 * t11.x + w01 * t01.x + w10 * t10.x + w00 * t00.x;
     const float gyi = w11 * t11.y + w01 * t01.y + w10 * t10.y + w00 * t00.y;
     const float r = w11 * t11.z + w01 * t01.z + w10 * t10.z + w00 * t00.z;
@@ -248,6 +256,7 @@ __device__ __forceinline__ void accumulate_point(const float4 p, const LevelIn &
     const float wr = (r <= huber) ? 1.f : huber / r;                               // optimizer.h:159
     const float gx = L.fx * gxi, gy = L.fy * gyi;                                  // optimizer.cpp:119-120
     // calculateWarpUpdate, optimizer.cpp:204-228
+    const float Wx = P.Wx, Wy = P.Wy, Wz = P.Wz;
     const float z = 1.0f / Wz, z_sqr = 1.0f / (Wz * Wz);
     float J[6];
     J[0] = z * gx;
@@ -272,7 +281,7 @@ __device__ __forceinline__ void accumulate_point(const float4 p, const LevelIn &
     acc[kRecGood] += 1.f;
 }
 
-// evalCostFunction (tracker.cpp:357-393) for two poses at once: acc[0] = cost(I,0), acc[1] = cost(R,t)
+// evalCostFunction (tracker.cpp:357-393) for one pose
 __device__ __forceinline__ float cost_point(float X, float Y, float Z, const LevelIn &L, const float *__restrict__ dt, float edge_dist,
                                             bool use_filter)
 {
@@ -319,11 +328,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+template <int kThreads>
+struct MinBlocks {
+    static constexpr int value = kThreads <= 128 ? 4 : (kThreads <= 256 ? 2 : 1);
+};
+
 // ---- the kernel ---------------------------------------------------------------
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads) k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm,
-                                                    revo_track_result *__restrict__ results, double *__restrict__ records,
-                                                    revo_trace_entry *__restrict__ trace, int *__restrict__ trace_counts)
+__global__ void __launch_bounds__(kThreads, MinBlocks<kThreads>::value)
+k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, revo_track_result *__restrict__ results,
+        double *__restrict__ records, revo_trace_entry *__restrict__ trace, int *__restrict__ trace_counts,
+        int *__restrict__ work_counter)
 {
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
@@ -354,15 +369,18 @@ __global__ void __launch_bounds__(kThreads) k_track(const PairDesc *__restrict__
         const int par = seq & 1;
         if (tid < 32) {
             double s = 0;
-#pragma unroll 4
+#pragma unroll
             for (int w = 0; w < kWarps; ++w) s += (double)warp_part[w][tid];
             cta_part[par][tid] = s;
         }
-        cluster.sync();
+        if (C > 1 || world > 1) cluster.sync(); else __syncthreads();
         if (world == 1) {
             if (tid < 32) {
-                double s = 0;
-                for (int r = 0; r < C; ++r) s += *cluster.map_shared_rank(&cta_part[par][tid], r);
+                double s = cta_part[par][tid];
+                if (C > 1) {
+                    s = 0;
+                    for (int r = 0; r < C; ++r) s += *cluster.map_shared_rank(&cta_part[par][tid], r);
+                }
                 rec[tid] = s;
             }
         } else {
@@ -395,7 +413,8 @@ __global__ void __launch_bounds__(kThreads) k_track(const PairDesc *__restrict__
         __syncthreads();
     };
 
-    for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+    int pair = cluster_id;
+    while (pair < n_pairs) {
         const PairDesc &P = pairs[pair];
         const int min_lvl = prm.mode == 0 ? prm.cfg.pyr_min_lvl : prm.level;
         const int max_lvl = prm.mode == 0 ? prm.cfg.pyr_max_lvl : prm.level;
@@ -410,8 +429,9 @@ __global__ void __launch_bounds__(kThreads) k_track(const PairDesc *__restrict__
             ctrl.level_done = 0;
         }
         __syncthreads();
-        if (ctrl.pair_skip) {
-            if (crank == 0 && tid == 0 && (world == 1 || true)) {
+        const bool skip = ctrl.pair_skip != 0;
+        if (skip) {
+            if (crank == 0 && tid == 0) {
                 revo_track_result &o = results[pair];
                 for (int i = 0; i < 9; ++i) o.R[i] = P.R[i];
                 for (int i = 0; i < 3; ++i) o.t[i] = P.t[i];
@@ -424,196 +444,201 @@ __global__ void __launch_bounds__(kThreads) k_track(const PairDesc *__restrict__
                 o.used_identity_init = 0;
                 if (trace_counts) trace_counts[pair] = 0;
             }
-            __syncthreads();
-            continue;
-        }
-
-        // ---- checkInitializationValues (tracker.cpp:265-283): cost at identity vs cost at (R,t), coarsest level
-        if (prm.mode == 0 && prm.cfg.check_init_values) {
-            const LevelIn L = P.lvl[min_lvl];
-            const int n = *L.n_pts;
-            const int lo = (int)((long long)n * member / n_members), hi = (int)((long long)n * (member + 1) / n_members);
-            float acc[32];
+        } else {
+            // ---- checkInitializationValues (tracker.cpp:265-283): cost at identity vs cost at (R,t), coarsest level
+            if (prm.mode == 0 && prm.cfg.check_init_values) {
+                const LevelIn L = P.lvl[min_lvl];
+                const int n = *L.n_pts;
+                const int lo = (int)((long long)n * member / n_members), hi = (int)((long long)n * (member + 1) / n_members);
+                float acc[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-            const float ed = oc.edge_distance_lvl[min_lvl];
-            float R[9], t[3];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) R[i] = ctrl.R[i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) t[i] = ctrl.t[i];
-            for (int i = lo + tid; i < hi; i += kThreads) {
-                const float4 p = __ldg(L.pts + i);
-                acc[0] += cost_point(p.x, p.y, p.z, L, P.ref_dt_min, ed, use_filter);
-                const float X = R[0] * p.x + R[3] * p.y + R[6] * p.z + t[0];
-                const float Y = R[1] * p.x + R[4] * p.y + R[7] * p.z + t[1];
-                const float Z = R[2] * p.x + R[5] * p.y + R[8] * p.z + t[2];
-                acc[1] += cost_point(X, Y, Z, L, P.ref_dt_min, ed, use_filter);
-            }
-            reduce_record(acc);
-            if (tid == 0) {
-                if ((float)rec[0] < (float)rec[1]) {   // tracker.cpp:277
-                    for (int i = 0; i < 9; ++i) ctrl.R[i] = (i % 4 == 0) ? 1.f : 0.f;
-                    for (int i = 0; i < 3; ++i) ctrl.t[i] = 0.f;
-                    ctrl.pair_skip = 2;   // marker: identity init used
-                }
-            }
-            __syncthreads();
-            used_identity = ctrl.pair_skip == 2;
-            __syncthreads();
-        }
-
-        if (tid == 0) {
-            quat_from_R(ctrl.R, lm.q);
-            for (int i = 0; i < 3; ++i) lm.t[i] = ctrl.t[i];
-            lm.last_residual = INFINITY;
-        }
-        float last_good = 0.f, last_bad = 0.f, last_sw = 0.f, last_su = 0.f;
-
-        for (int lvl = min_lvl; lvl >= max_lvl; --lvl) {
-            const LevelIn L = P.lvl[lvl];
-            const int n = *L.n_pts;
-            const int lo = (int)((long long)n * member / n_members), hi = (int)((long long)n * (member + 1) / n_members);
-            const float ed = oc.edge_distance_lvl[lvl];
-            const float huber = oc.huber_edge;
-            bool first = true;
-            __syncthreads();
-            while (true) {
+                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                const float ed = oc.edge_distance_lvl[min_lvl];
                 float R[9], t[3];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) R[i] = ctrl.R[i];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) t[i] = ctrl.t[i];
-                float acc[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
                 for (int i = lo + tid; i < hi; i += kThreads) {
                     const float4 p = __ldg(L.pts + i);
-                    accumulate_point(p, L, R, t, ed, use_filter, huber, acc);
+                    acc[0] += cost_point(p.x, p.y, p.z, L, P.ref_dt_min, ed, use_filter);
+                    const float X = R[0] * p.x + R[3] * p.y + R[6] * p.z + t[0];
+                    const float Y = R[1] * p.x + R[4] * p.y + R[7] * p.z + t[1];
+                    const float Z = R[2] * p.x + R[5] * p.y + R[8] * p.z + t[2];
+                    acc[1] += cost_point(X, Y, Z, L, P.ref_dt_min, ed, use_filter);
                 }
                 reduce_record(acc);
-                evals_lvl[lvl]++;
-                last_good = (float)rec[kRecGood]; last_bad = (float)rec[kRecBad];
-                last_sw = (float)rec[kRecSW]; last_su = (float)rec[kRecSU];
-
-                if (prm.mode == 2) {   // single evaluation: export the record
-                    if (crank == 0 && tid < 32 && records) records[(size_t)pair * 32 + tid] = rec[tid];
-                    break;
-                }
-
                 if (tid == 0) {
-                    // ---------------- Optimizer::trackFrames LM logic, optimizer.cpp:243-306 ----------------
-                    const float err = (float)(rec[kRecSW] / rec[kRecGood]);    // :190
-                    bool propose = false, done = false;
-                    if (first) {
-                        lm.lastErr = err;
-                        lm.last_residual = err;
-                        lm.lambda = oc.lambda_initial[lvl];
-                        lm.iteration = 0; lm.incTry = 0; lm.tries = 0;
-                        for (int i = 0; i < 21; ++i) lm.A[i] = rec[kRecA + i];
-                        for (int i = 0; i < 6; ++i) lm.b[i] = rec[kRecB + i];
-                        lm.n = rec[kRecGood];
-                        propose = true;
-                    } else {
-                        const bool accepted = err < lm.lastErr;                // :273
-                        if (trace && crank == 0 && ntrace < prm.trace_cap) {
-                            revo_trace_entry &e = trace[(size_t)pair * prm.trace_cap + ntrace];
-                            e.error = err; e.lambda = lm.lambda; e.accepted = accepted ? 1 : 0;
-                            e.good = (int)rec[kRecGood]; e.bad = (int)rec[kRecBad]; e.level = lvl;
-                        }
-                        ntrace++;
-                        if (accepted) {
-                            for (int i = 0; i < 4; ++i) lm.q[i] = lm.qn[i];
-                            for (int i = 0; i < 3; ++i) lm.t[i] = lm.tn[i];
+                    if ((float)rec[0] < (float)rec[1]) {   // tracker.cpp:277
+                        for (int i = 0; i < 9; ++i) ctrl.R[i] = (i % 4 == 0) ? 1.f : 0.f;
+                        for (int i = 0; i < 3; ++i) ctrl.t[i] = 0.f;
+                        ctrl.pair_skip = 2;   // marker: identity init used
+                    }
+                }
+                __syncthreads();
+                used_identity = ctrl.pair_skip == 2;
+                __syncthreads();
+            }
+
+            if (tid == 0) {
+                quat_from_R(ctrl.R, lm.q);
+                for (int i = 0; i < 3; ++i) lm.t[i] = ctrl.t[i];
+                lm.last_residual = INFINITY;
+            }
+            float last_good = 0.f, last_bad = 0.f, last_sw = 0.f, last_su = 0.f;
+
+            for (int lvl = min_lvl; lvl >= max_lvl; --lvl) {
+                const LevelIn L = P.lvl[lvl];
+                const int n = *L.n_pts;
+                const int lo = (int)((long long)n * member / n_members), hi = (int)((long long)n * (member + 1) / n_members);
+                const float ed = oc.edge_distance_lvl[lvl];
+                const float huber = oc.huber_edge;
+                bool first = true;
+                __syncthreads();
+                while (true) {
+                    float R[9], t[3];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) R[i] = ctrl.R[i];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) t[i] = ctrl.t[i];
+                    float acc[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                    // two points per thread in flight: project both, issue all 8 texel loads, then finish both
+                    for (int i = lo + tid; i < hi; i += 2 * kThreads) {
+                        const int i1 = i + kThreads;
+                        const bool e1 = i1 < hi;
+                        const float4 p0 = __ldg(L.pts + i);
+                        const float4 p1 = __ldg(L.pts + (e1 ? i1 : i));
+                        const Proj a = project(true, p0, L, R, t);
+                        const Proj b = project(e1, p1, L, R, t);
+                        const float4 a00 = __ldg(a.bp), a10 = __ldg(a.bp + 1), a01 = __ldg(a.bp + L.w), a11 = __ldg(a.bp + L.w + 1);
+                        const float4 b00 = __ldg(b.bp), b10 = __ldg(b.bp + 1), b01 = __ldg(b.bp + L.w), b11 = __ldg(b.bp + L.w + 1);
+                        finish_point(a, a00, a10, a01, a11, L, ed, use_filter, huber, acc);
+                        finish_point(b, b00, b10, b01, b11, L, ed, use_filter, huber, acc);
+                    }
+                    reduce_record(acc);
+                    evals_lvl[lvl]++;
+                    last_good = (float)rec[kRecGood]; last_bad = (float)rec[kRecBad];
+                    last_sw = (float)rec[kRecSW]; last_su = (float)rec[kRecSU];
+
+                    if (prm.mode == 2) {   // single evaluation: export the record
+                        if (crank == 0 && tid < 32 && records) records[(size_t)pair * 32 + tid] = rec[tid];
+                        break;
+                    }
+
+                    if (tid == 0) {
+                        // ---------------- Optimizer::trackFrames LM logic, optimizer.cpp:243-306 ----------------
+                        const float err = (float)(rec[kRecSW] / rec[kRecGood]);    // :190
+                        bool propose = false, done = false;
+                        if (first) {
+                            lm.lastErr = err;
+                            lm.last_residual = err;
+                            lm.lambda = oc.lambda_initial[lvl];
+                            lm.iteration = 0; lm.incTry = 0; lm.tries = 0;
                             for (int i = 0; i < 21; ++i) lm.A[i] = rec[kRecA + i];
                             for (int i = 0; i < 6; ++i) lm.b[i] = rec[kRecB + i];
                             lm.n = rec[kRecGood];
-                            if (err / lm.lastErr > oc.convergence_eps[lvl]) lm.iteration = oc.max_its_per_lvl[lvl];   // :279-283
-                            lm.last_residual = lm.lastErr = err;
-                            if (lm.lambda <= 0.2f) lm.lambda = 0.f; else lm.lambda *= oc.lambda_success_fac;          // :286-289
-                            lm.iteration++;     // for-loop increment after the break (:291)
-                            lm.incTry = 0;
                             propose = true;
                         } else {
-                            double dot = 0;
-                            for (int i = 0; i < 6; ++i) dot += lm.inc[i] * lm.inc[i];
-                            if (!((float)dot > oc.step_size_min[lvl])) {                                               // :294
-                                done = true;
-                            } else {
-                                if (lm.lambda == 0.f) lm.lambda = 0.2f;                                                // :300-303
-                                else lm.lambda *= powf(oc.lambda_fail_fac, (float)lm.incTry);
+                            const bool accepted = err < lm.lastErr;                // :273
+                            if (trace && crank == 0 && ntrace < prm.trace_cap) {
+                                revo_trace_entry &e = trace[(size_t)pair * prm.trace_cap + ntrace];
+                                e.error = err; e.lambda = lm.lambda; e.accepted = accepted ? 1 : 0;
+                                e.good = (int)rec[kRecGood]; e.bad = (int)rec[kRecBad]; e.level = lvl;
+                            }
+                            ntrace++;
+                            if (accepted) {
+                                for (int i = 0; i < 4; ++i) lm.q[i] = lm.qn[i];
+                                for (int i = 0; i < 3; ++i) lm.t[i] = lm.tn[i];
+                                for (int i = 0; i < 21; ++i) lm.A[i] = rec[kRecA + i];
+                                for (int i = 0; i < 6; ++i) lm.b[i] = rec[kRecB + i];
+                                lm.n = rec[kRecGood];
+                                if (err / lm.lastErr > oc.convergence_eps[lvl]) lm.iteration = oc.max_its_per_lvl[lvl];   // :279-283
+                                lm.last_residual = lm.lastErr = err;
+                                if (lm.lambda <= 0.2f) lm.lambda = 0.f; else lm.lambda *= oc.lambda_success_fac;          // :286-289
+                                lm.iteration++;     // for-loop increment after the break (:291)
+                                lm.incTry = 0;
                                 propose = true;
+                            } else {
+                                double dot = 0;
+                                for (int i = 0; i < 6; ++i) dot += lm.inc[i] * lm.inc[i];
+                                if (!((float)dot > oc.step_size_min[lvl])) {                                               // :294
+                                    done = true;
+                                } else {
+                                    if (lm.lambda == 0.f) lm.lambda = 0.2f;                                                // :300-303
+                                    else lm.lambda *= powf(oc.lambda_fail_fac, (float)lm.incTry);
+                                    propose = true;
+                                }
                             }
                         }
+                        if (propose && !done) {
+                            if (lm.iteration >= oc.max_its_per_lvl[lvl]) done = true;
+                            else if (oc.max_lm_tries > 0 && lm.tries >= oc.max_lm_tries) done = true;
+                        }
+                        if (propose && !done) {
+                            // solve (A/n with diag *(1+lambda)) inc = (sum w r v)/n     :258-262
+                            solve6(lm.A, lm.b, 1.0 / lm.n, (double)(1.f + lm.lambda), lm.inc);
+                            lm.incTry++; lm.tries++;
+                            double qe[4], te[3];
+                            se3_exp(lm.inc, qe, te);
+                            se3_mul(qe, te, lm.q, lm.t, lm.qn, lm.tn);              // :266 exp(inc) * referenceToFrame
+                            double Rn[9];
+                            quat_to_R(lm.qn, Rn);
+                            for (int i = 0; i < 9; ++i) ctrl.R[i] = (float)Rn[i];
+                            for (int i = 0; i < 3; ++i) ctrl.t[i] = (float)lm.tn[i];
+                        }
+                        if (done) {
+                            // next level (or the result) starts from the accepted pose      :308-309
+                            double Ra[9];
+                            quat_to_R(lm.q, Ra);
+                            for (int i = 0; i < 9; ++i) ctrl.R[i] = (float)Ra[i];
+                            for (int i = 0; i < 3; ++i) ctrl.t[i] = (float)lm.t[i];
+                        }
+                        ctrl.level_done = done ? 1 : 0;
                     }
-                    if (propose && !done) {
-                        if (lm.iteration >= oc.max_its_per_lvl[lvl]) done = true;
-                        else if (oc.max_lm_tries > 0 && lm.tries >= oc.max_lm_tries) done = true;
-                    }
-                    if (propose && !done) {
-                        // solve (A/n with diag *(1+lambda)) inc = (sum w r v)/n     :258-262
-                        double M[36], rhs[6];
-                        int s = 0;
-                        for (int i = 0; i < 6; ++i)
-                            for (int j = i; j < 6; ++j) {
-                                const double a = lm.A[s++] / lm.n;
-                                M[j * 6 + i] = a; M[i * 6 + j] = a;
-                            }
-                        for (int i = 0; i < 6; ++i) { M[i * 6 + i] *= (double)(1.f + lm.lambda); rhs[i] = lm.b[i] / lm.n; }
-                        ldlt_solve6(M, rhs, lm.inc);
-                        lm.incTry++; lm.tries++;
-                        double qe[4], te[3];
-                        se3_exp(lm.inc, qe, te);
-                        se3_mul(qe, te, lm.q, lm.t, lm.qn, lm.tn);              // :266 exp(inc) * referenceToFrame
-                        double Rn[9];
-                        quat_to_R(lm.qn, Rn);
-                        for (int i = 0; i < 9; ++i) ctrl.R[i] = (float)Rn[i];
-                        for (int i = 0; i < 3; ++i) ctrl.t[i] = (float)lm.tn[i];
-                    }
-                    if (done) {
-                        // next level (or the result) starts from the accepted pose      :308-309
-                        double Ra[9];
-                        quat_to_R(lm.q, Ra);
-                        for (int i = 0; i < 9; ++i) ctrl.R[i] = (float)Ra[i];
-                        for (int i = 0; i < 3; ++i) ctrl.t[i] = (float)lm.t[i];
-                    }
-                    ctrl.level_done = done ? 1 : 0;
+                    first = false;
+                    __syncthreads();
+                    if (ctrl.level_done) break;
                 }
-                first = false;
                 __syncthreads();
-                if (ctrl.level_done) break;
             }
-            __syncthreads();
-        }
 
-        if (crank == 0 && tid == 0 && prm.mode != 2) {
-            revo_track_result &o = results[pair];
-            for (int i = 0; i < 9; ++i) o.R[i] = ctrl.R[i];
-            for (int i = 0; i < 3; ++i) o.t[i] = ctrl.t[i];
-            o.error = lm.last_residual;
-            o.res.good_pts_edges = (int)last_good;
-            o.res.bad_pts_edges = (int)last_bad;
-            o.res.sum_error_weighted = last_sw;
-            o.res.sum_error_unweighted = last_su;
-            // tracker.cpp:351: good/bad < 4 -> NEW_KF (double division; bad == 0 -> inf -> OK)
-            o.status = ((double)last_good / (double)last_bad < 4.0) ? REVO_TRACKER_STATE_NEW_KF : REVO_TRACKER_STATE_OK;
-            o.rc = REVO_OK;
-            for (int l = 0; l < REVO_MAX_LEVELS; ++l) {
-                o.n_evals[l] = evals_lvl[l];
-                o.n_pts[l] = (l >= max_lvl && l <= min_lvl) ? *P.lvl[l].n_pts : 0;
+            if (crank == 0 && tid == 0 && prm.mode != 2) {
+                revo_track_result &o = results[pair];
+                for (int i = 0; i < 9; ++i) o.R[i] = ctrl.R[i];
+                for (int i = 0; i < 3; ++i) o.t[i] = ctrl.t[i];
+                o.error = lm.last_residual;
+                o.res.good_pts_edges = (int)last_good;
+                o.res.bad_pts_edges = (int)last_bad;
+                o.res.sum_error_weighted = last_sw;
+                o.res.sum_error_unweighted = last_su;
+                // tracker.cpp:351: good/bad < 4 -> NEW_KF (double division; bad == 0 -> inf -> OK)
+                o.status = ((double)last_good / (double)last_bad < 4.0) ? REVO_TRACKER_STATE_NEW_KF : REVO_TRACKER_STATE_OK;
+                o.rc = REVO_OK;
+                for (int l = 0; l < REVO_MAX_LEVELS; ++l) {
+                    o.n_evals[l] = evals_lvl[l];
+                    o.n_pts[l] = (l >= max_lvl && l <= min_lvl) ? *P.lvl[l].n_pts : 0;
+                }
+                o.used_identity_init = used_identity;
+                if (trace_counts) trace_counts[pair] = ntrace < prm.trace_cap ? ntrace : prm.trace_cap;
             }
-            o.used_identity_init = used_identity;
-            if (trace_counts) trace_counts[pair] = ntrace < prm.trace_cap ? ntrace : prm.trace_cap;
         }
+        // ---- next pair from the global work counter (cluster rank 0 fetches, everybody reads it over DSMEM)
         __syncthreads();
+        if (crank == 0 && tid == 0) ctrl.next_pair = n_clusters + atomicAdd(work_counter, 1);
+        if (C > 1) cluster.sync(); else __syncthreads();
+        pair = *cluster.map_shared_rank(&ctrl.next_pair, 0);
+        if (C > 1) cluster.sync(); else __syncthreads();
     }
-    cluster.sync();   // nobody may exit while a peer can still read its shared memory
+    if (C > 1 || world > 1) cluster.sync();   // nobody may exit while a peer can still read its shared memory
 }
 
 // ---- launcher -------------------------------------------------------------------
 template <int kThreads>
 static int launch_track_t(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, int ctas_per_pair,
-                          revo_track_result *d_results, double *d_records, revo_trace_entry *d_trace, int *d_trace_counts)
+                          revo_track_result *d_results, double *d_records, revo_trace_entry *d_trace, int *d_trace_counts,
+                          int *d_work_counter)
 {
     auto kern = k_track<kThreads>;
     if (ctas_per_pair > 8) REVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -639,7 +664,8 @@ static int launch_track_t(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, c
     }
     const int n_clusters = n_pairs < max_clusters ? n_pairs : max_clusters;
     cfg.gridDim = dim3(n_clusters * ctas_per_pair);
-    REVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, d_pairs, n_pairs, prm, d_results, d_records, d_trace, d_trace_counts));
+    REVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, d_pairs, n_pairs, prm, d_results, d_records, d_trace, d_trace_counts,
+                                      d_work_counter));
     ctx->launches++;
     return REVO_OK;
 }
@@ -647,21 +673,22 @@ static int launch_track_t(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, c
 int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, revo_track_result *d_results,
                  double *d_records, revo_trace_entry *d_trace, int *d_trace_counts, int *d_work_counter)
 {
-    (void)d_work_counter;
     if (n_pairs <= 0) return REVO_OK;
+    const int T = ctx->track_threads > 0 ? ctx->track_threads : 256;
     int C = ctx->track_ctas_per_pair;
-    const int sms = ctx->prop.multiProcessorCount;
     if (C <= 0) {
-        // automatic: spread the chip over the pairs; one pair alone gets the largest portable cluster
+        // automatic: fill the CTA slots of the chip (SMs x resident CTAs of this shape); a pair alone gets a
+        // full portable cluster
+        const int per_sm = T <= 128 ? 4 : (T <= 256 ? 2 : 1);
+        const int slots = ctx->prop.multiProcessorCount * per_sm;
         C = 1;
-        while (C < 8 && n_pairs * (C * 2) <= sms) C *= 2;
+        while (C < 8 && n_pairs * (C * 2) <= slots) C *= 2;
     }
-    int T = ctx->track_threads > 0 ? ctx->track_threads : 512;
     switch (T) {
-        case 128: return launch_track_t<128>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts);
-        case 256: return launch_track_t<256>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts);
-        case 1024: return launch_track_t<1024>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts);
-        default: return launch_track_t<512>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts);
+        case 128: return launch_track_t<128>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter);
+        case 512: return launch_track_t<512>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter);
+        case 1024: return launch_track_t<1024>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter);
+        default: return launch_track_t<256>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter);
     }
 }
 

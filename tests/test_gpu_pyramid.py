@@ -42,12 +42,6 @@ def _compare(pg, po, n_levels, keyframe=True):
         b = po.edges3d[l][np.lexsort(po.edges3d[l].T[::-1])]
         assert np.array_equal(a, b), f"device-order list L{l}"
         if keyframe:
-            if not po.edges[l].any():
-                # no edge pixel at all: cv2 returns a build-dependent "infinity" (IPP vs trueDistTrans);
-                # the product defines it as 2^64 (what cv2's IPP branch yields) -- see DESIGN.md
-                assert (pg.returnDistTransform(l) == np.float32(2.0 ** 64)).all(), f"empty dt L{l}"
-                assert (po.dt[l] > 1e15).all()
-                continue
             assert np.array_equal(pg.returnDistTransform(l), po.dt[l]), f"dt L{l}"
             assert np.array_equal(pg.returnOptimizationStructure(l), po.opt[l]), f"opt L{l}"
 
@@ -91,7 +85,7 @@ def test_pyramid_fill_in_path(ctx, orc32):
 
 
 def test_pyramid_noise_and_empty(ctx, orc32):
-    """Pure noise (max edge density, many tiny components) and a constant image (no edges: DT = 2^64 like cv2)."""
+    """Pure noise (max edge density, many tiny components) and a constant image (no edges: DT = 65536 like cv2's own trueDistTrans)."""
     from revo_b200 import api
 
     rng = np.random.default_rng(3)

@@ -42,7 +42,7 @@ def _build(ctx, orc, p, n_levels):
     return ok, oc, gk, gc, st
 
 
-def _rec_close(g, o, tol=2e-5, max_flips=0):
+def _rec_close(g, o, tol=2e-5, max_flips=0, unw_tol=None):
     """Record parity.  Counts must agree exactly unless max_flips > 0 (poses that put points exactly on the
     u>1 / v>1 / u<w-2 / v<h-2 bounds, e.g. the identity, classify border pixels on float rounding)."""
     flips = abs(g[29] - o[29])
@@ -54,7 +54,7 @@ def _rec_close(g, o, tol=2e-5, max_flips=0):
     assert np.abs(g[:21] - o[:21]).max() <= tol * sA, (g[:21], o[:21])
     assert np.abs(g[21:27] - o[21:27]).max() <= tol * sb, (g[21:27], o[21:27])
     assert abs(g[27] - o[27]) <= tol * abs(o[27]) + 1e-12
-    assert abs(g[28] - o[28]) <= tol * abs(o[28]) + 1e-12
+    assert abs(g[28] - o[28]) <= (unw_tol or tol) * abs(o[28]) + 1e-12
 
 
 @pytest.mark.parametrize("seed", [1, 21])
@@ -76,7 +76,7 @@ def test_eval_record_matches_oracle(ctx, orc32, orc64, seed):
             _rec_close(g, o, max_flips=1)
             # and the float32 sequential reference-as-is agrees with both at its own precision
             o32 = orc32.eval_record(oc.edges3d[lvl], ok.opt[lvl], oc.cams[lvl], R32, T32, ocfg, lvl)
-            _rec_close(o32, o, tol=3e-4, max_flips=1)
+            _rec_close(o32, o, tol=2e-3, max_flips=1, unw_tol=0.06)
     # identity pose: every point projects onto an integer pixel, so border pixels sit exactly on the bounds
     # test and classify on rounding (the f32 and f64 oracles disagree with each other there, too)
     I, Z = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
@@ -84,7 +84,7 @@ def test_eval_record_matches_oracle(ctx, orc32, orc64, seed):
     o = orc64.eval_record(oc.edges3d[0], ok.opt[0], oc.cams[0], I, Z, ocfg, 0)
     o32 = orc32.eval_record(oc.edges3d[0], ok.opt[0], oc.cams[0], I, Z, ocfg, 0)
     _rec_close(g, o, max_flips=200)
-    _rec_close(o32, o, max_flips=200)
+    _rec_close(o32, o, tol=2e-3, max_flips=200, unw_tol=0.06)
     # edge filter off
     opt2 = api.Optimizer(ctx, api.OptimizerSettings(USE_EDGE_FILTER=False))
     ocfg.use_edge_filter = 0
