@@ -1,0 +1,378 @@
+// canny.cu -- K2: cv::Canny(gray, edges, t1, t2, 3, true)  (datastructures/imgpyramidrgbd.cpp:184), bit-exact.
+//
+// Three kernels per pyramid level, batched over frames:
+//  (A) k_canny_tile: one CTA per 128x16 pixel tile.  The gray tile (+2 halo) is fetched with ONE TMA bulk-tensor
+//      copy (cp.async.bulk.tensor.3d, zero fill outside the image; BORDER_REPLICATE is patched in shared
+//      memory), 3x3 Sobel -> mag = dx^2 + dy^2 (zero outside the image) -> non-maximum suppression with OpenCV's
+//      TG22 fixed-point sector test -> class map (0 none / 1 weak / 2 strong).  The hysteresis inside the tile
+//      is resolved right there: union-find over the tile's candidates in shared memory (8-connectivity), with
+//      the "strong" flag folded into the key (strong keys are smaller, roots are minima) so a component's root
+//      tells whether it holds a strong pixel.  Writes the class map and one global label per candidate
+//      (= key of its tile-local root in global coordinates).
+//  (B) k_canny_merge: only candidates on tile borders: union with candidate neighbours in adjacent tiles
+//      (lock-free atomicMin union-find in global memory; trees are at most a few tiles deep).
+//  (C) k_canny_final: 16 pixels per thread: 255 where the candidate's root key is strong, else 0, into both
+//      edges and edges_orig.
+// The result is the unique fixed point of OpenCV's hysteresis (every 8-connected component of candidates that
+// contains a strong pixel), independent of thread order.
+#include <cuda.h>
+#include <string.h>
+
+#include "internal.h"
+
+namespace revo {
+
+#define LAUNCH_CHECK(ctx)                                   \
+    do {                                                    \
+        (ctx)->launches++;                                  \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return cuda_fail((ctx), e__, __func__); \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+constexpr int CT_W = 128, CT_H = 16;                 // output tile
+constexpr int CT_BW = CT_W + 16, CT_BH = CT_H + 4;   // TMA box (inner extent a multiple of 16 bytes), origin (x0-2, y0-2)
+constexpr int kWeakBit = 0x40000000;
+constexpr int kIdxMask = 0x3fffffff;
+constexpr int kNoLabel = 0x7fffffff;
+
+// ---- TMA / mbarrier PTX ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- union-find on keys ----------------------------------------------------------------------------
+// key = (weak ? kWeakBit : 0) | index of the pixel; a pixel's label is the key of its parent; roots point
+// to themselves.  Linking always attaches the larger key under the smaller, so a root is the minimum key of
+// its component and is "strong" (bit clear) iff the component contains a strong pixel.
+template <typename LoadFn>
+__device__ __forceinline__ int uf_find_key(LoadFn load, int key)
+{
+    int p = load(key & kIdxMask);
+    while (p != key) {
+        key = p;
+        p = load(key & kIdxMask);
+    }
+    return key;
+}
+
+__device__ __forceinline__ void uf_union_smem(int *lab, int ka, int kb)
+{
+    auto ld = [&](int i) { return ((volatile int *)lab)[i]; };
+    while (true) {
+        ka = uf_find_key(ld, ka);
+        kb = uf_find_key(ld, kb);
+        if (ka == kb) return;
+        if (ka < kb) { const int t = ka; ka = kb; kb = t; }
+        const int old = atomicMin(lab + (ka & kIdxMask), kb);
+        if (old == ka) return;
+        ka = old;
+    }
+}
+
+__device__ __forceinline__ void uf_union_gmem(int *lab, int ka, int kb)
+{
+    auto ld = [&](int i) { return __ldcg(lab + i); };
+    while (true) {
+        ka = uf_find_key(ld, ka);
+        kb = uf_find_key(ld, kb);
+        if (ka == kb) return;
+        if (ka < kb) { const int t = ka; ka = kb; kb = t; }
+        const int old = atomicMin(lab + (ka & kIdxMask), kb);
+        if (old == ka) return;
+        ka = old;
+    }
+}
+
+// ---- (A) ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_canny_tile(const __grid_constant__ CUtensorMap tm_gray, const int use_tma,
+                                                    const ImgLevel *__restrict__ desc, int w, int h, int low, int high)
+{
+    __shared__ alignas(128) uint8_t g[CT_BH][CT_BW];
+    __shared__ int mag[CT_H + 2][CT_W + 2];
+    __shared__ int lab[CT_H * CT_W];
+    __shared__ uint8_t cls[CT_H][CT_W];
+    __shared__ alignas(8) uint64_t bar;
+
+    const int f = blockIdx.z;
+    const ImgLevel L = desc[f];
+    const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    const int tid = threadIdx.x;
+
+    // ---- gray tile with halo 2
+    if (use_tma) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, CT_BW * CT_BH);
+            tma_load_3d(&g[0][0], &tm_gray, x0 - 2, y0 - 2, f, &bar);
+        }
+        mbar_wait(&bar, 0);
+        // BORDER_REPLICATE: cells outside the image take the value of the clamped cell (always inside this box)
+        const bool edge_tile = (x0 == 0) || (y0 == 0) || (x0 + CT_BW - 2 > w) || (y0 + CT_BH - 2 > h);
+        if (edge_tile) {
+            for (int i = tid; i < CT_BH * CT_BW; i += 256) {
+                const int r = i / CT_BW, c = i - r * CT_BW;
+                const int gy = y0 - 2 + r, gx = x0 - 2 + c;
+                if (gx < 0 || gx >= w || gy < 0 || gy >= h) {
+                    const int sy = min(max(gy, 0), h - 1) - (y0 - 2), sx = min(max(gx, 0), w - 1) - (x0 - 2);
+                    g[r][c] = g[sy][sx];
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < CT_BH * CT_BW; i += 256) {
+            const int r = i / CT_BW, c = i - r * CT_BW;
+            const int yy = min(max(y0 + r - 2, 0), h - 1), xx = min(max(x0 + c - 2, 0), w - 1);
+            g[r][c] = L.gray[(size_t)yy * w + xx];
+        }
+    }
+    __syncthreads();
+
+    // ---- squared gradient magnitude on tile + halo 1 (zero outside the image)
+    for (int i = tid; i < (CT_H + 2) * (CT_W + 2); i += 256) {
+        const int r = i / (CT_W + 2), c = i - r * (CT_W + 2);
+        const int yy = y0 + r - 1, xx = x0 + c - 1;
+        int m = 0;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+            const int gx = (g[r][c + 2] - g[r][c]) + 2 * (g[r + 1][c + 2] - g[r + 1][c]) + (g[r + 2][c + 2] - g[r + 2][c]);
+            const int gy = (g[r + 2][c] - g[r][c]) + 2 * (g[r + 2][c + 1] - g[r][c + 1]) + (g[r + 2][c + 2] - g[r][c + 2]);
+            m = gx * gx + gy * gy;
+        }
+        mag[r][c] = m;
+    }
+    __syncthreads();
+
+    // ---- non-maximum suppression: thread -> 8 consecutive pixels of one row
+    const int ty = tid >> 4, tx0 = (tid & 15) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int tx = tx0 + k;
+        const int x = x0 + tx, y = y0 + ty;
+        uint8_t c8 = 0;
+        if (x < w && y < h) {
+            const int r = ty + 1, c = tx + 1;
+            const int m = mag[r][c];
+            if (m > low) {
+                const int xs = (g[r][c + 2] - g[r][c]) + 2 * (g[r + 1][c + 2] - g[r + 1][c]) + (g[r + 2][c + 2] - g[r + 2][c]);
+                const int ys = (g[r + 2][c] - g[r][c]) + 2 * (g[r + 2][c + 1] - g[r][c + 1]) + (g[r + 2][c + 2] - g[r][c + 2]);
+                const int ax = abs(xs), ay = abs(ys) << 15;
+                const int tg22x = ax * 13573;
+                bool cand;
+                if (ay < tg22x) {
+                    cand = (m > mag[r][c - 1]) && (m >= mag[r][c + 1]);
+                } else {
+                    const int tg67x = tg22x + (ax << 16);
+                    if (ay > tg67x) cand = (m > mag[r - 1][c]) && (m >= mag[r + 1][c]);
+                    else {
+                        const int s = ((xs ^ ys) < 0) ? -1 : 1;
+                        cand = (m > mag[r - 1][c - s]) && (m > mag[r + 1][c + s]);
+                    }
+                }
+                if (cand) c8 = (m > high) ? 2 : 1;
+            }
+        }
+        cls[ty][tx] = c8;
+        const int li = ty * CT_W + tx;
+        lab[li] = c8 ? ((c8 == 2 ? 0 : kWeakBit) | li) : kNoLabel;
+    }
+    __syncthreads();
+
+    // ---- hysteresis inside the tile: union with W, NW, N, NE candidates
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int tx = tx0 + k;
+        const int c8 = cls[ty][tx];
+        if (!c8) continue;
+        const int li = ty * CT_W + tx;
+        const int key = (c8 == 2 ? 0 : kWeakBit) | li;
+        if (tx > 0 && cls[ty][tx - 1]) uf_union_smem(lab, key, (cls[ty][tx - 1] == 2 ? 0 : kWeakBit) | (li - 1));
+        if (ty > 0) {
+            if (tx > 0 && cls[ty - 1][tx - 1]) uf_union_smem(lab, key, (cls[ty - 1][tx - 1] == 2 ? 0 : kWeakBit) | (li - CT_W - 1));
+            if (cls[ty - 1][tx]) uf_union_smem(lab, key, (cls[ty - 1][tx] == 2 ? 0 : kWeakBit) | (li - CT_W));
+            if (tx < CT_W - 1 && cls[ty - 1][tx + 1]) uf_union_smem(lab, key, (cls[ty - 1][tx + 1] == 2 ? 0 : kWeakBit) | (li - CT_W + 1));
+        }
+    }
+    __syncthreads();
+
+    // ---- write the class map (8 bytes per thread) and the global labels of the candidates
+    const int y = y0 + ty;
+    if (y < h && x0 + tx0 < w) {
+        uint8_t *erow = L.edges + (size_t)y * w + x0 + tx0;
+        if (x0 + tx0 + 8 <= w && ((((uintptr_t)erow) & 7) == 0)) {
+            *(uint2 *)erow = *(const uint2 *)&cls[ty][tx0];
+        } else {
+            for (int k = 0; k < 8 && x0 + tx0 + k < w; ++k) erow[k] = cls[ty][tx0 + k];
+        }
+        auto ld = [&](int i) { return lab[i]; };
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int tx = tx0 + k;
+            const int c8 = cls[ty][tx];
+            if (!c8 || x0 + tx >= w) continue;
+            const int li = ty * CT_W + tx;
+            const int root = uf_find_key(ld, (c8 == 2 ? 0 : kWeakBit) | li);
+            const int ri = root & kIdxMask;
+            const int gidx = (y0 + ri / CT_W) * w + (x0 + (ri % CT_W));
+            L.labels[(size_t)y * w + x0 + tx] = (root & kWeakBit) | gidx;
+        }
+    }
+}
+
+// ---- (B): candidates on the top row / left column / right column of every tile ----------------------------
+__global__ void __launch_bounds__(192) k_canny_merge(const ImgLevel *__restrict__ desc, int w, int h)
+{
+    const int f = blockIdx.z;
+    const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    const int t = threadIdx.x;
+    int lx, ly;
+    if (t < CT_W) { lx = t; ly = 0; }                                   // top row
+    else if (t < CT_W + CT_H - 1) { lx = 0; ly = t - CT_W + 1; }         // left column (below the corner)
+    else if (t < CT_W + 2 * (CT_H - 1)) { lx = CT_W - 1; ly = t - (CT_W + CT_H - 1) + 1; }   // right column
+    else return;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x >= w || y >= h) return;
+    const uint8_t *__restrict__ cls = desc[f].edges;
+    int *lab = desc[f].labels;
+    const int p = y * w + x;
+    const int cp = cls[p];
+    if (!cp) return;
+    const int key = (cp == 2 ? 0 : kWeakBit) | p;
+    auto other_tile = [&](int qx, int qy) { return (qx / CT_W != x / CT_W) || (qy / CT_H != y / CT_H); };
+    auto try_union = [&](int qx, int qy) {
+        if (qx < 0 || qx >= w || qy < 0 || qy >= h || !other_tile(qx, qy)) return;
+        const int q = qy * w + qx;
+        const int cq = cls[q];
+        if (cq) uf_union_gmem(lab, key, (cq == 2 ? 0 : kWeakBit) | q);
+    };
+    try_union(x - 1, y);
+    try_union(x - 1, y - 1);
+    try_union(x, y - 1);
+    try_union(x + 1, y - 1);
+}
+
+// ---- (C) ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_canny_final(const ImgLevel *__restrict__ desc, int w, int h)
+{
+    const int f = blockIdx.z;
+    const size_t n = (size_t)w * h;
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    uint8_t *e = desc[f].edges, *eo = desc[f].edges_orig;
+    const int *lab = desc[f].labels;
+    auto ld = [&](int i) { return __ldcg(lab + i); };
+    if (i0 + 16 <= n && ((((uintptr_t)(e + i0)) & 15) == 0) && ((((uintptr_t)(eo + i0)) & 15) == 0)) {
+        uint4 v = *(const uint4 *)(e + i0);
+        uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        if (v.x | v.y | v.z | v.w) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!wv[q]) continue;
+                uint32_t o = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t c = (wv[q] >> (8 * b)) & 255u;
+                    if (c) {
+                        const int p = (int)i0 + q * 4 + b;
+                        const int root = uf_find_key(ld, (c == 2 ? 0 : kWeakBit) | p);
+                        if (!(root & kWeakBit)) o |= 255u << (8 * b);
+                    }
+                }
+                wv[q] = o;
+            }
+            v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            *(uint4 *)(e + i0) = v;
+        }
+        *(uint4 *)(eo + i0) = v;
+    } else {
+        for (size_t i = i0; i < i0 + 16 && i < n; ++i) {
+            const int c = e[i];
+            uint8_t o = 0;
+            if (c) {
+                const int root = uf_find_key(ld, (c == 2 ? 0 : kWeakBit) | (int)i);
+                o = (root & kWeakBit) ? 0 : 255;
+            }
+            e[i] = o;
+            eo[i] = o;
+        }
+    }
+}
+
+// ---- host: tensor map for the gray images of one level of a slab ---------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn()
+{
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+bool make_gray_tensor_map(void *tmap_out, const uint8_t *base, int w, int h, int n_frames, size_t frame_stride)
+{
+    PFN_tmapEncodeTiled fn = get_encode_fn();
+    if (!fn || (w % 16) != 0 || (frame_stride % 16) != 0 || (((uintptr_t)base) & 15)) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_frames};
+    cuuint64_t strides[2] = {(cuuint64_t)w, (cuuint64_t)frame_stride};
+    cuuint32_t box[3] = {CT_BW, CT_BH, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn((CUtensorMap *)tmap_out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high, const void *gray_tmap)
+{
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    const int use_tma = gray_tmap != nullptr;
+    if (use_tma) memcpy(&tm, gray_tmap, sizeof(tm));
+    dim3 grid(cdiv(w, CT_W), cdiv(h, CT_H), n);
+    k_canny_tile<<<grid, 256, 0, ctx->stream>>>(tm, use_tma, d_desc, w, h, low, high);
+    LAUNCH_CHECK(ctx);
+    k_canny_merge<<<grid, 192, 0, ctx->stream>>>(d_desc, w, h);
+    LAUNCH_CHECK(ctx);
+    dim3 g3(cdiv(cdiv(w * h, 16), 256), 1, n);
+    k_canny_final<<<g3, 256, 0, ctx->stream>>>(d_desc, w, h);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
+}  // namespace revo

@@ -356,7 +356,11 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
     rc = launch_gray(ctx, d_bgr, (size_t)w0 * channels, channels, bgr_frame, slab->d_desc[0], n, w0, h0);
     for (int l = 0; l < NL && !rc; ++l) {
         if (l > 0) rc = launch_pyrdown_depth(ctx, slab->d_desc[l - 1], slab->d_desc[l], n, g[l].w, g[l].h, g[l - 1].w, g[l - 1].h);
-        if (!rc) rc = launch_canny(ctx, slab->d_desc[l], n, g[l].w, g[l].h, low, high);
+        if (!rc) {
+            alignas(64) unsigned char tmap[128];
+            const bool tma = make_gray_tensor_map(tmap, base + o_gray[l], g[l].w, g[l].h, n, align_up((size_t)g[l].w * g[l].h, 256));
+            rc = launch_canny(ctx, slab->d_desc[l], n, g[l].w, g[l].h, low, high, tma ? tmap : nullptr);
+        }
         // fill-in is only defined for the reference's 3 patch sizes (levels 1,2); see SURVEY D5
         const bool fill = cfg->use_edge_hist && l >= 1 && l <= 2;
         if (!rc) rc = launch_hist_fill(ctx, slab->d_desc[l], l > 0 ? slab->d_desc[l - 1] : nullptr, n, g[l].w, g[l].h,

@@ -101,7 +101,11 @@ int launch_gray(revo_ctx *ctx, const uint8_t *d_bgr, size_t stride, int ch, size
                 int n, int w, int h);
 int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst,
                          int w_src, int h_src);
-int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high);
+// gray_tmap: host pointer to a CUtensorMap made by make_gray_tensor_map (nullptr = plain loads)
+int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high, const void *gray_tmap);
+// 3-D (x, y, frame) tensor map over the u8 gray images of one level of a slab; false if TMA cannot be used
+bool make_gray_tensor_map(void *tmap_out /* 128 bytes, 64-aligned */, const uint8_t *base, int w, int h, int n_frames,
+                          size_t frame_stride);
 int launch_hist_fill(revo_ctx *ctx, const ImgLevel *d_desc, const ImgLevel *d_top, int n, int w, int h, int patch,
                      int patch_low, bool do_fill, float n_percentage);
 int launch_compact(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, float dmin, float dmax);

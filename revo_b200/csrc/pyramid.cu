@@ -158,154 +158,7 @@ int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d
     return REVO_OK;
 }
 
-// ---------------------------------------------------------------------------
-// K2: Canny (aperture 3, L2 gradient).
-//  (a) k_canny_nms: 3x3 Sobel with BORDER_REPLICATE, mag = dx^2+dy^2 (zero outside the image),
-//      non-maximum suppression with OpenCV's TG22 fixed-point sector test -> class map
-//      0 = no edge, 1 = weak candidate (> low), 2 = strong (> high); candidates get a
-//      union-find label (their own index).
-//  (b) k_canny_link: union every candidate with its W, NW, N, NE candidate neighbours
-//      (8-connectivity) -- lock-free atomicMin union-find, root = smallest index.
-//  (c) k_canny_mark: every strong pixel flags its root.
-//  (d) k_canny_out: 255 for candidates whose root is flagged, else 0 (edges and edges_orig).
-// The result is the unique fixed point of OpenCV's hysteresis, independent of thread order.
-// ---------------------------------------------------------------------------
-constexpr int CN_TW = 32, CN_TH = 8;
-
-__global__ void __launch_bounds__(256) k_canny_nms(const ImgLevel *__restrict__ desc, int w, int h, int low, int high)
-{
-    __shared__ uint8_t g[CN_TH + 4][CN_TW + 4];
-    __shared__ int mag[CN_TH + 2][CN_TW + 2];
-    const int f = blockIdx.z;
-    const ImgLevel L = desc[f];
-    const int x0 = blockIdx.x * CN_TW, y0 = blockIdx.y * CN_TH;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (int i = tid; i < (CN_TH + 4) * (CN_TW + 4); i += 256) {
-        const int r = i / (CN_TW + 4), c = i - r * (CN_TW + 4);
-        const int yy = min(max(y0 + r - 2, 0), h - 1), xx = min(max(x0 + c - 2, 0), w - 1);
-        g[r][c] = L.gray[(size_t)yy * w + xx];
-    }
-    __syncthreads();
-    for (int i = tid; i < (CN_TH + 2) * (CN_TW + 2); i += 256) {
-        const int r = i / (CN_TW + 2), c = i - r * (CN_TW + 2);
-        const int yy = y0 + r - 1, xx = x0 + c - 1;
-        int m = 0;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-            // g index of (yy,xx) is [r+1][c+1]
-            const int gx = (g[r][c + 2] - g[r][c]) + 2 * (g[r + 1][c + 2] - g[r + 1][c]) + (g[r + 2][c + 2] - g[r + 2][c]);
-            const int gy = (g[r + 2][c] - g[r][c]) + 2 * (g[r + 2][c + 1] - g[r][c + 1]) + (g[r + 2][c + 2] - g[r][c + 2]);
-            m = gx * gx + gy * gy;
-        }
-        mag[r][c] = m;
-    }
-    __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const int r = threadIdx.y + 1, c = threadIdx.x + 1;   // position in mag
-    const int m = mag[r][c];
-    uint8_t cls = 0;
-    if (m > low) {
-        const int gr = threadIdx.y + 1, gc = threadIdx.x + 1;  // top-left of the 3x3 window in g is [gr][gc]
-        const int xs = (g[gr][gc + 2] - g[gr][gc]) + 2 * (g[gr + 1][gc + 2] - g[gr + 1][gc]) + (g[gr + 2][gc + 2] - g[gr + 2][gc]);
-        const int ys = (g[gr + 2][gc] - g[gr][gc]) + 2 * (g[gr + 2][gc + 1] - g[gr][gc + 1]) + (g[gr + 2][gc + 2] - g[gr][gc + 2]);
-        const int ax = abs(xs), ay = abs(ys) << 15;
-        const int tg22x = ax * 13573;
-        bool cand;
-        if (ay < tg22x) {
-            cand = (m > mag[r][c - 1]) && (m >= mag[r][c + 1]);
-        } else {
-            const int tg67x = tg22x + (ax << 16);
-            if (ay > tg67x) cand = (m > mag[r - 1][c]) && (m >= mag[r + 1][c]);
-            else {
-                const int s = ((xs ^ ys) < 0) ? -1 : 1;
-                cand = (m > mag[r - 1][c - s]) && (m > mag[r + 1][c + s]);
-            }
-        }
-        if (cand) cls = (m > high) ? 2 : 1;
-    }
-    const int p = y * w + x;
-    L.edges[p] = cls;
-    if (cls) {
-        L.labels[p] = p;
-        L.flags[p] = 0;
-    }
-}
-
-__device__ __forceinline__ int uf_find(const int *L, int a)
-{
-    int p = __ldcg(L + a);
-    while (p != a) {
-        a = p;
-        p = __ldcg(L + a);
-    }
-    return a;
-}
-
-__device__ __forceinline__ void uf_union(int *L, int a, int b)
-{
-    while (true) {
-        a = uf_find(L, a);
-        b = uf_find(L, b);
-        if (a == b) return;
-        if (a < b) { const int t = a; a = b; b = t; }
-        const int old = atomicMin(L + a, b);   // attach the larger root under the smaller
-        if (old == a) return;
-        a = old;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_canny_link(const ImgLevel *__restrict__ desc, int w, int h)
-{
-    const int f = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const uint8_t *__restrict__ cls = desc[f].edges;
-    int *lab = desc[f].labels;
-    const int p = y * w + x;
-    if (!cls[p]) return;
-    if (x > 0 && cls[p - 1]) uf_union(lab, p, p - 1);
-    if (y > 0) {
-        const int q = p - w;
-        if (x > 0 && cls[q - 1]) uf_union(lab, p, q - 1);
-        if (cls[q]) uf_union(lab, p, q);
-        if (x < w - 1 && cls[q + 1]) uf_union(lab, p, q + 1);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_canny_mark(const ImgLevel *__restrict__ desc, int w, int h)
-{
-    const int f = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const int p = y * w + x;
-    if (desc[f].edges[p] == 2) desc[f].flags[uf_find(desc[f].labels, p)] = 1;
-}
-
-__global__ void __launch_bounds__(256) k_canny_out(const ImgLevel *__restrict__ desc, int w, int h)
-{
-    const int f = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const int p = y * w + x;
-    uint8_t o = 0;
-    if (desc[f].edges[p]) o = desc[f].flags[uf_find(desc[f].labels, p)] ? 255 : 0;
-    desc[f].edges[p] = o;
-    desc[f].edges_orig[p] = o;
-}
-
-int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high)
-{
-    dim3 block(CN_TW, CN_TH), grid(cdiv(w, CN_TW), cdiv(h, CN_TH), n);
-    k_canny_nms<<<grid, block, 0, ctx->stream>>>(d_desc, w, h, low, high);
-    LAUNCH_CHECK(ctx);
-    k_canny_link<<<grid, block, 0, ctx->stream>>>(d_desc, w, h);
-    LAUNCH_CHECK(ctx);
-    k_canny_mark<<<grid, block, 0, ctx->stream>>>(d_desc, w, h);
-    LAUNCH_CHECK(ctx);
-    k_canny_out<<<grid, block, 0, ctx->stream>>>(d_desc, w, h);
-    LAUNCH_CHECK(ctx);
-    return REVO_OK;
-}
+// K2 (Canny) lives in canny.cu.
 
 // ---------------------------------------------------------------------------
 // K5: patch histogram (u8 counts wrap like cv::Mat_<uchar>::operator++) + count of
