@@ -32,7 +32,12 @@ namespace revo {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 constexpr int CT_W = 128, CT_H = 16;                 // output tile
-constexpr int CT_BW = CT_W + 16, CT_BH = CT_H + 4;   // TMA box (inner extent a multiple of 16 bytes), origin (x0-2, y0-2)
+// TMA box: origin (x0 - CT_XO, y0 - 2).  The innermost start coordinate of a bulk-tensor copy must be a multiple
+// of 16 bytes (measured on B200: any other start raises "illegal instruction"), so the 2-pixel halo is fetched as
+// a 16-pixel apron on both sides; rows may start anywhere.  Out-of-image cells are zero-filled by the TMA unit.
+constexpr int CT_XO = 16;
+constexpr int CT_BW = CT_W + 2 * CT_XO, CT_BH = CT_H + 4;
+#define GRAY(r, c) g[(r)][(c) + CT_XO - 2]   // (r, c) relative to (y0 - 2, x0 - 2), as the stencil code indexes
 constexpr int kWeakBit = 0x40000000;
 constexpr int kIdxMask = 0x3fffffff;
 constexpr int kNoLabel = 0x7fffffff;
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(256) k_canny_tile(const __grid_constant__ CUte
     __shared__ alignas(128) uint8_t g[CT_BH][CT_BW];
     __shared__ int mag[CT_H + 2][CT_W + 2];
     __shared__ int lab[CT_H * CT_W];
-    __shared__ uint8_t cls[CT_H][CT_W];
+    __shared__ alignas(16) uint8_t cls[CT_H][CT_W];
     __shared__ alignas(8) uint64_t bar;
 
     const int f = blockIdx.z;
@@ -130,26 +135,26 @@ __global__ void __launch_bounds__(256) k_canny_tile(const __grid_constant__ CUte
         __syncthreads();
         if (tid == 0) {
             mbar_expect_tx(&bar, CT_BW * CT_BH);
-            tma_load_3d(&g[0][0], &tm_gray, x0 - 2, y0 - 2, f, &bar);
+            tma_load_3d(&g[0][0], &tm_gray, x0 - CT_XO, y0 - 2, f, &bar);
         }
         mbar_wait(&bar, 0);
         // BORDER_REPLICATE: cells outside the image take the value of the clamped cell (always inside this box)
-        const bool edge_tile = (x0 == 0) || (y0 == 0) || (x0 + CT_BW - 2 > w) || (y0 + CT_BH - 2 > h);
+        const bool edge_tile = (x0 == 0) || (y0 == 0) || (x0 + CT_W + 2 > w) || (y0 + CT_H + 2 > h);
         if (edge_tile) {
-            for (int i = tid; i < CT_BH * CT_BW; i += 256) {
-                const int r = i / CT_BW, c = i - r * CT_BW;
+            for (int i = tid; i < CT_BH * (CT_W + 4); i += 256) {
+                const int r = i / (CT_W + 4), c = i - r * (CT_W + 4);
                 const int gy = y0 - 2 + r, gx = x0 - 2 + c;
                 if (gx < 0 || gx >= w || gy < 0 || gy >= h) {
                     const int sy = min(max(gy, 0), h - 1) - (y0 - 2), sx = min(max(gx, 0), w - 1) - (x0 - 2);
-                    g[r][c] = g[sy][sx];
+                    GRAY(r, c) = GRAY(sy, sx);
                 }
             }
         }
     } else {
-        for (int i = tid; i < CT_BH * CT_BW; i += 256) {
-            const int r = i / CT_BW, c = i - r * CT_BW;
+        for (int i = tid; i < CT_BH * (CT_W + 4); i += 256) {
+            const int r = i / (CT_W + 4), c = i - r * (CT_W + 4);
             const int yy = min(max(y0 + r - 2, 0), h - 1), xx = min(max(x0 + c - 2, 0), w - 1);
-            g[r][c] = L.gray[(size_t)yy * w + xx];
+            GRAY(r, c) = L.gray[(size_t)yy * w + xx];
         }
     }
     __syncthreads();
@@ -160,8 +165,8 @@ __global__ void __launch_bounds__(256) k_canny_tile(const __grid_constant__ CUte
         const int yy = y0 + r - 1, xx = x0 + c - 1;
         int m = 0;
         if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-            const int gx = (g[r][c + 2] - g[r][c]) + 2 * (g[r + 1][c + 2] - g[r + 1][c]) + (g[r + 2][c + 2] - g[r + 2][c]);
-            const int gy = (g[r + 2][c] - g[r][c]) + 2 * (g[r + 2][c + 1] - g[r][c + 1]) + (g[r + 2][c + 2] - g[r][c + 2]);
+            const int gx = (GRAY(r, c + 2) - GRAY(r, c)) + 2 * (GRAY(r + 1, c + 2) - GRAY(r + 1, c)) + (GRAY(r + 2, c + 2) - GRAY(r + 2, c));
+            const int gy = (GRAY(r + 2, c) - GRAY(r, c)) + 2 * (GRAY(r + 2, c + 1) - GRAY(r, c + 1)) + (GRAY(r + 2, c + 2) - GRAY(r, c + 2));
             m = gx * gx + gy * gy;
         }
         mag[r][c] = m;
@@ -179,8 +184,8 @@ __global__ void __launch_bounds__(256) k_canny_tile(const __grid_constant__ CUte
             const int r = ty + 1, c = tx + 1;
             const int m = mag[r][c];
             if (m > low) {
-                const int xs = (g[r][c + 2] - g[r][c]) + 2 * (g[r + 1][c + 2] - g[r + 1][c]) + (g[r + 2][c + 2] - g[r + 2][c]);
-                const int ys = (g[r + 2][c] - g[r][c]) + 2 * (g[r + 2][c + 1] - g[r][c + 1]) + (g[r + 2][c + 2] - g[r][c + 2]);
+                const int xs = (GRAY(r, c + 2) - GRAY(r, c)) + 2 * (GRAY(r + 1, c + 2) - GRAY(r + 1, c)) + (GRAY(r + 2, c + 2) - GRAY(r + 2, c));
+                const int ys = (GRAY(r + 2, c) - GRAY(r, c)) + 2 * (GRAY(r + 2, c + 1) - GRAY(r, c + 1)) + (GRAY(r + 2, c + 2) - GRAY(r, c + 2));
                 const int ax = abs(xs), ay = abs(ys) << 15;
                 const int tg22x = ax * 13573;
                 bool cand;

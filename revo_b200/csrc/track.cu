@@ -214,7 +214,7 @@ __device__ __forceinline__ void solve6(const double *Au /* 21 upper slots */, co
 
 // ---- per-point work: PASS A + PASS B fused ---------------------------------------
 struct Proj {
-    float Wx, Wy, Wz, dx, dy;
+    float Wx, Wy, iz, dx, dy;
     const float4 *bp;
     int state;   // 0 = no point, 1 = in bounds (texels wanted), 2 = out of bounds
 };
@@ -226,14 +226,17 @@ __device__ __forceinline__ Proj project(bool exists, const float4 p, const Level
     Proj o;
     o.Wx = R[0] * p.x + R[3] * p.y + R[6] * p.z + t[0];
     o.Wy = R[1] * p.x + R[4] * p.y + R[7] * p.z + t[1];
-    o.Wz = R[2] * p.x + R[5] * p.y + R[8] * p.z + t[2];
-    const float u = o.Wx / o.Wz * L.fx + L.cx;
-    const float v = o.Wy / o.Wz * L.fy + L.cy;
+    const float Wz = R[2] * p.x + R[5] * p.y + R[8] * p.z + t[2];
+    // the reference divides (Wx/Wz*fx+cx); one correctly rounded reciprocal is shared by u, v and the Jacobian
+    // (differs from the quotient by <= 1 ulp, far inside the float tolerance of this path)
+    o.iz = __frcp_rn(Wz);
+    const float u = o.Wx * o.iz * L.fx + L.cx;
+    const float v = o.Wy * o.iz * L.fy + L.cy;
     const bool inb = (u > 1.f && v > 1.f && u < (float)(L.w - 2) && v < (float)(L.h - 2));   // NaN-safe (:100)
     const int ix = inb ? (int)u : 0, iy = inb ? (int)v : 0;
     o.dx = u - (float)ix;
     o.dy = v - (float)iy;
-    o.bp = L.opt + (size_t)iy * L.w + ix;
+    o.bp = L.opt + (unsigned)(iy * L.w + ix);
     o.state = exists ? (inb ? 1 : 2) : 0;
     return o;
 }
@@ -253,11 +256,11 @@ __device__ __forceinline__ void finish_point(const Proj &P, const float4 t00, co
         acc[kRecBad] += 1.f;
         return;
     }
-    const float wr = (r <= huber) ? 1.f : huber / r;                               // optimizer.h:159
+    const float wr = (r <= huber) ? 1.f : __fdividef(huber, r);                    // optimizer.h:159
     const float gx = L.fx * gxi, gy = L.fy * gyi;                                  // optimizer.cpp:119-120
     // calculateWarpUpdate, optimizer.cpp:204-228
-    const float Wx = P.Wx, Wy = P.Wy, Wz = P.Wz;
-    const float z = 1.0f / Wz, z_sqr = 1.0f / (Wz * Wz);
+    const float Wx = P.Wx, Wy = P.Wy;
+    const float z = P.iz, z_sqr = P.iz * P.iz;
     float J[6];
     J[0] = z * gx;
     J[1] = z * gy;
@@ -504,18 +507,36 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                     float acc[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-                    // two points per thread in flight: project both, issue all 8 texel loads, then finish both
-                    for (int i = lo + tid; i < hi; i += 2 * kThreads) {
-                        const int i1 = i + kThreads;
-                        const bool e1 = i1 < hi;
-                        const float4 p0 = __ldg(L.pts + i);
-                        const float4 p1 = __ldg(L.pts + (e1 ? i1 : i));
-                        const Proj a = project(true, p0, L, R, t);
-                        const Proj b = project(e1, p1, L, R, t);
-                        const float4 a00 = __ldg(a.bp), a10 = __ldg(a.bp + 1), a01 = __ldg(a.bp + L.w), a11 = __ldg(a.bp + L.w + 1);
-                        const float4 b00 = __ldg(b.bp), b10 = __ldg(b.bp + 1), b01 = __ldg(b.bp + L.w), b11 = __ldg(b.bp + L.w + 1);
-                        finish_point(a, a00, a10, a01, a11, L, ed, use_filter, huber, acc);
-                        finish_point(b, b00, b10, b01, b11, L, ed, use_filter, huber, acc);
+                    // Software pipeline, two register sets (A/B): while point k is being finished, the four texel
+                    // gathers of point k+1 and the list entry of point k+2 are already in flight.
+                    {
+                        const float4 *__restrict__ pts = L.pts;
+                        int i = lo + tid;
+                        bool eA = i < hi;
+                        float4 pA = __ldg(pts + (eA ? i : lo));
+                        i += kThreads;
+                        bool eB = i < hi;
+                        float4 pB = __ldg(pts + (eB ? i : lo));
+                        Proj A = project(eA, pA, L, R, t);
+                        float4 a00 = __ldg(A.bp), a10 = __ldg(A.bp + 1), a01 = __ldg(A.bp + L.w), a11 = __ldg(A.bp + L.w + 1);
+                        while (true) {
+                            i += kThreads;
+                            const bool eC = i < hi;
+                            const float4 pC = __ldg(pts + (eC ? i : lo));
+                            const Proj B = project(eB, pB, L, R, t);
+                            const float4 b00 = __ldg(B.bp), b10 = __ldg(B.bp + 1), b01 = __ldg(B.bp + L.w), b11 = __ldg(B.bp + L.w + 1);
+                            finish_point(A, a00, a10, a01, a11, L, ed, use_filter, huber, acc);
+                            if (!eB) break;
+                            i += kThreads;
+                            const bool eD = i < hi;
+                            const float4 pD = __ldg(pts + (eD ? i : lo));
+                            A = project(eC, pC, L, R, t);
+                            a00 = __ldg(A.bp); a10 = __ldg(A.bp + 1); a01 = __ldg(A.bp + L.w); a11 = __ldg(A.bp + L.w + 1);
+                            finish_point(B, b00, b10, b01, b11, L, ed, use_filter, huber, acc);
+                            if (!eC) break;
+                            eB = eD;
+                            pB = pD;
+                        }
                     }
                     reduce_record(acc);
                     evals_lvl[lvl]++;
