@@ -38,6 +38,7 @@ constexpr int CT_W = 128, CT_H = 16;                 // output tile
 constexpr int CT_XO = 16;
 constexpr int CT_BW = CT_W + 2 * CT_XO, CT_BH = CT_H + 4;
 #define GRAY(r, c) g[(r)][(c) + CT_XO - 2]   // (r, c) relative to (y0 - 2, x0 - 2), as the stencil code indexes
+constexpr int CT_MW = CT_W + 8;
 constexpr int kWeakBit = 0x40000000;
 constexpr int kIdxMask = 0x3fffffff;
 constexpr int kNoLabel = 0x7fffffff;
@@ -119,8 +120,8 @@ __global__ void __launch_bounds__(256) k_canny_tile(const __grid_constant__ CUte
                                                     const ImgLevel *__restrict__ desc, int w, int h, int low, int high)
 {
     __shared__ alignas(128) uint8_t g[CT_BH][CT_BW];
-    __shared__ int mag[CT_H + 2][CT_W + 2];
-    __shared__ int lab[CT_H * CT_W];
+    __shared__ alignas(16) int mag[CT_H + 2][CT_MW];   // pixel column tx lives at array column tx + 4
+    __shared__ alignas(16) int lab[CT_H * CT_W];
     __shared__ alignas(16) uint8_t cls[CT_H][CT_W];
     __shared__ alignas(8) uint64_t bar;
 
@@ -159,92 +160,165 @@ __global__ void __launch_bounds__(256) k_canny_tile(const __grid_constant__ CUte
     }
     __syncthreads();
 
-    // ---- squared gradient magnitude on tile + halo 1 (zero outside the image)
-    for (int i = tid; i < (CT_H + 2) * (CT_W + 2); i += 256) {
-        const int r = i / (CT_W + 2), c = i - r * (CT_W + 2);
-        const int yy = y0 + r - 1, xx = x0 + c - 1;
+    // ---- Sobel + squared magnitude, register tiled: thread -> 8 consecutive pixels of one row.
+    // Three rows x 24 bytes of the gray tile are read as 9 LDS.64; dx, dy and mag of the 8 pixels stay in registers.
+    const int ty = tid >> 4, tx0 = (tid & 15) * 8;
+    int dxs[8], dys[8], mid[10];
+    {
+        unsigned long long rw[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) rw[r][q] = *(const unsigned long long *)&g[ty + 1 + r][tx0 + 8 + 8 * q];
+        auto px = [&](int r, int j) -> int { return (int)((rw[r][j >> 3] >> ((j & 7) * 8)) & 0xffull); };
+        const bool row_in = (y0 + ty) < h;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int l = k + 7, c = k + 8, rr = k + 9;
+            const int gx = (px(0, rr) - px(0, l)) + 2 * (px(1, rr) - px(1, l)) + (px(2, rr) - px(2, l));
+            const int gy = (px(2, l) + 2 * px(2, c) + px(2, rr)) - (px(0, l) + 2 * px(0, c) + px(0, rr));
+            dxs[k] = gx;
+            dys[k] = gy;
+            mid[k + 1] = (row_in && (x0 + tx0 + k) < w) ? gx * gx + gy * gy : 0;
+        }
+        *(int4 *)&mag[ty + 1][tx0 + 4] = make_int4(mid[1], mid[2], mid[3], mid[4]);
+        *(int4 *)&mag[ty + 1][tx0 + 8] = make_int4(mid[5], mid[6], mid[7], mid[8]);
+    }
+    // halo ring of the magnitude tile (pixel rows -1 and CT_H, pixel columns -1 and CT_W)
+    for (int i = tid; i < 2 * (CT_W + 2) + 2 * CT_H; i += 256) {
+        int py, pxx;
+        if (i < CT_W + 2) { py = -1; pxx = i - 1; }
+        else if (i < 2 * (CT_W + 2)) { py = CT_H; pxx = i - (CT_W + 2) - 1; }
+        else if (i < 2 * (CT_W + 2) + CT_H) { py = i - 2 * (CT_W + 2); pxx = -1; }
+        else { py = i - 2 * (CT_W + 2) - CT_H; pxx = CT_W; }
+        const int yy = y0 + py, xx = x0 + pxx;
         int m = 0;
         if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+            const int r = py + 1, c = pxx + 1;   // top-left of the 3x3 window in GRAY coordinates
             const int gx = (GRAY(r, c + 2) - GRAY(r, c)) + 2 * (GRAY(r + 1, c + 2) - GRAY(r + 1, c)) + (GRAY(r + 2, c + 2) - GRAY(r + 2, c));
             const int gy = (GRAY(r + 2, c) - GRAY(r, c)) + 2 * (GRAY(r + 2, c + 1) - GRAY(r, c + 1)) + (GRAY(r + 2, c + 2) - GRAY(r, c + 2));
             m = gx * gx + gy * gy;
         }
-        mag[r][c] = m;
+        mag[py + 1][pxx + 4] = m;
     }
     __syncthreads();
 
-    // ---- non-maximum suppression: thread -> 8 consecutive pixels of one row
-    const int ty = tid >> 4, tx0 = (tid & 15) * 8;
+    // ---- non-maximum suppression from registers (rows above / below: 4 LDS.128 each)
+    int c8[8];
+    {
+        int up[16], dn[16];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int tx = tx0 + k;
-        const int x = x0 + tx, y = y0 + ty;
-        uint8_t c8 = 0;
-        if (x < w && y < h) {
-            const int r = ty + 1, c = tx + 1;
-            const int m = mag[r][c];
+        for (int q = 0; q < 4; ++q) {
+            const int4 u = *(const int4 *)&mag[ty][tx0 + 4 * q];
+            const int4 d = *(const int4 *)&mag[ty + 2][tx0 + 4 * q];
+            up[4 * q] = u.x; up[4 * q + 1] = u.y; up[4 * q + 2] = u.z; up[4 * q + 3] = u.w;
+            dn[4 * q] = d.x; dn[4 * q + 1] = d.y; dn[4 * q + 2] = d.z; dn[4 * q + 3] = d.w;
+        }
+        mid[0] = mag[ty + 1][tx0 + 3];
+        mid[9] = mag[ty + 1][tx0 + 12];
+        // pixel k sits at array column k + 4 of up/dn and k + 1 of mid
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int m = mid[k + 1];
+            int cls_k = 0;
             if (m > low) {
-                const int xs = (GRAY(r, c + 2) - GRAY(r, c)) + 2 * (GRAY(r + 1, c + 2) - GRAY(r + 1, c)) + (GRAY(r + 2, c + 2) - GRAY(r + 2, c));
-                const int ys = (GRAY(r + 2, c) - GRAY(r, c)) + 2 * (GRAY(r + 2, c + 1) - GRAY(r, c + 1)) + (GRAY(r + 2, c + 2) - GRAY(r, c + 2));
+                const int xs = dxs[k], ys = dys[k];
                 const int ax = abs(xs), ay = abs(ys) << 15;
                 const int tg22x = ax * 13573;
                 bool cand;
                 if (ay < tg22x) {
-                    cand = (m > mag[r][c - 1]) && (m >= mag[r][c + 1]);
+                    cand = (m > mid[k]) && (m >= mid[k + 2]);
                 } else {
                     const int tg67x = tg22x + (ax << 16);
-                    if (ay > tg67x) cand = (m > mag[r - 1][c]) && (m >= mag[r + 1][c]);
+                    if (ay > tg67x) cand = (m > up[k + 4]) && (m >= dn[k + 4]);
                     else {
-                        const int s = ((xs ^ ys) < 0) ? -1 : 1;
-                        cand = (m > mag[r - 1][c - s]) && (m > mag[r + 1][c + s]);
+                        const bool neg = (xs ^ ys) < 0;          // s = -1: compare (y-1, x+1) and (y+1, x-1)
+                        const int a = neg ? up[k + 5] : up[k + 3];
+                        const int b2 = neg ? dn[k + 3] : dn[k + 5];
+                        cand = (m > a) && (m > b2);
                     }
                 }
-                if (cand) c8 = (m > high) ? 2 : 1;
+                if (cand) cls_k = (m > high) ? 2 : 1;
             }
-        }
-        cls[ty][tx] = c8;
-        const int li = ty * CT_W + tx;
-        lab[li] = c8 ? ((c8 == 2 ? 0 : kWeakBit) | li) : kNoLabel;
-    }
-    __syncthreads();
-
-    // ---- hysteresis inside the tile: union with W, NW, N, NE candidates
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int tx = tx0 + k;
-        const int c8 = cls[ty][tx];
-        if (!c8) continue;
-        const int li = ty * CT_W + tx;
-        const int key = (c8 == 2 ? 0 : kWeakBit) | li;
-        if (tx > 0 && cls[ty][tx - 1]) uf_union_smem(lab, key, (cls[ty][tx - 1] == 2 ? 0 : kWeakBit) | (li - 1));
-        if (ty > 0) {
-            if (tx > 0 && cls[ty - 1][tx - 1]) uf_union_smem(lab, key, (cls[ty - 1][tx - 1] == 2 ? 0 : kWeakBit) | (li - CT_W - 1));
-            if (cls[ty - 1][tx]) uf_union_smem(lab, key, (cls[ty - 1][tx] == 2 ? 0 : kWeakBit) | (li - CT_W));
-            if (tx < CT_W - 1 && cls[ty - 1][tx + 1]) uf_union_smem(lab, key, (cls[ty - 1][tx + 1] == 2 ? 0 : kWeakBit) | (li - CT_W + 1));
+            c8[k] = cls_k;
         }
     }
-    __syncthreads();
 
-    // ---- write the class map (8 bytes per thread) and the global labels of the candidates
-    const int y = y0 + ty;
-    if (y < h && x0 + tx0 < w) {
-        uint8_t *erow = L.edges + (size_t)y * w + x0 + tx0;
-        if (x0 + tx0 + 8 <= w && ((((uintptr_t)erow) & 7) == 0)) {
-            *(uint2 *)erow = *(const uint2 *)&cls[ty][tx0];
-        } else {
-            for (int k = 0; k < 8 && x0 + tx0 + k < w; ++k) erow[k] = cls[ty][tx0 + k];
-        }
-        auto ld = [&](int i) { return lab[i]; };
+    // ---- labels: every horizontal run inside the thread's 8 pixels starts flat (all point to the run's minimum key)
+    int key[8];
+    {
+        int runmin[8];
+        const int li0 = ty * CT_W + tx0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int tx = tx0 + k;
-            const int c8 = cls[ty][tx];
-            if (!c8 || x0 + tx >= w) continue;
-            const int li = ty * CT_W + tx;
-            const int root = uf_find_key(ld, (c8 == 2 ? 0 : kWeakBit) | li);
+            key[k] = (c8[k] == 2 ? 0 : kWeakBit) | (li0 + k);
+            runmin[k] = c8[k] ? ((k > 0 && c8[k - 1]) ? min(runmin[k - 1], key[k]) : key[k]) : kNoLabel;
+        }
+#pragma unroll
+        for (int k = 6; k >= 0; --k)
+            if (c8[k] && c8[k + 1]) runmin[k] = min(runmin[k], runmin[k + 1]);
+        *(int4 *)&lab[li0] = make_int4(runmin[0], runmin[1], runmin[2], runmin[3]);
+        *(int4 *)&lab[li0 + 4] = make_int4(runmin[4], runmin[5], runmin[6], runmin[7]);
+        unsigned lo4 = 0, hi4 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { lo4 |= (unsigned)c8[k] << (8 * k); hi4 |= (unsigned)c8[k + 4] << (8 * k); }
+        *(uint2 *)&cls[ty][tx0] = make_uint2(lo4, hi4);
+    }
+    __syncthreads();
+
+    // ---- hysteresis inside the tile: runs are linked to their W neighbour and to the row above (N, else NW / NE)
+    {
+        const int li0 = ty * CT_W + tx0;
+        if (c8[0] && tx0 > 0) {
+            const int cw = cls[ty][tx0 - 1];
+            if (cw) uf_union_smem(lab, key[0], (cw == 2 ? 0 : kWeakBit) | (li0 - 1));
+        }
+        if (ty > 0) {
+            int cu[10];
+            cu[0] = tx0 > 0 ? cls[ty - 1][tx0 - 1] : 0;
+            {
+                const uint2 v = *(const uint2 *)&cls[ty - 1][tx0];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { cu[1 + k] = (v.x >> (8 * k)) & 255; cu[5 + k] = (v.y >> (8 * k)) & 255; }
+            }
+            cu[9] = tx0 + 8 < CT_W ? cls[ty - 1][tx0 + 8] : 0;
+            const int ui0 = li0 - CT_W;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (!c8[k]) continue;
+                if (cu[k + 1]) {
+                    uf_union_smem(lab, key[k], (cu[k + 1] == 2 ? 0 : kWeakBit) | (ui0 + k));
+                } else {
+                    if (cu[k]) uf_union_smem(lab, key[k], (cu[k] == 2 ? 0 : kWeakBit) | (ui0 + k - 1));
+                    if (cu[k + 2]) uf_union_smem(lab, key[k], (cu[k + 2] == 2 ? 0 : kWeakBit) | (ui0 + k + 1));
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- write the class map (class of the pixel's tile-local ROOT: 2 = its component holds a strong pixel, 1 = weak so
+    // far) and, for every candidate, the key of its tile-local root in global coordinates
+    const int y = y0 + ty;
+    if (y < h && x0 + tx0 < w) {
+        auto ld = [&](int i) { return lab[i]; };
+        unsigned lo4 = 0, hi4 = 0;
+        int *lrow = L.labels + (size_t)y * w + x0 + tx0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (!c8[k] || x0 + tx0 + k >= w) continue;
+            const int root = uf_find_key(ld, key[k]);
             const int ri = root & kIdxMask;
             const int gidx = (y0 + ri / CT_W) * w + (x0 + (ri % CT_W));
-            L.labels[(size_t)y * w + x0 + tx] = (root & kWeakBit) | gidx;
+            lrow[k] = (root & kWeakBit) | gidx;
+            const unsigned rc = (root & kWeakBit) ? 1u : 2u;
+            if (k < 4) lo4 |= rc << (8 * k); else hi4 |= rc << (8 * (k - 4));
+        }
+        uint8_t *erow = L.edges + (size_t)y * w + x0 + tx0;
+        if (x0 + tx0 + 8 <= w && ((((uintptr_t)erow) & 7) == 0)) {
+            *(uint2 *)erow = make_uint2(lo4, hi4);
+        } else {
+            for (int k = 0; k < 8 && x0 + tx0 + k < w; ++k) erow[k] = (uint8_t)(((k < 4 ? lo4 : hi4) >> (8 * (k & 3))) & 255u);
         }
     }
 }
@@ -273,7 +347,7 @@ __global__ void __launch_bounds__(192) k_canny_merge(const ImgLevel *__restrict_
         if (qx < 0 || qx >= w || qy < 0 || qy >= h || !other_tile(qx, qy)) return;
         const int q = qy * w + qx;
         const int cq = cls[q];
-        if (cq) uf_union_gmem(lab, key, (cq == 2 ? 0 : kWeakBit) | q);
+        if (cq && !(cp == 2 && cq == 2)) uf_union_gmem(lab, key, (cq == 2 ? 0 : kWeakBit) | q);   // strong-strong: nothing to learn
     };
     try_union(x - 1, y);
     try_union(x - 1, y - 1);
@@ -302,9 +376,10 @@ __global__ void __launch_bounds__(256) k_canny_final(const ImgLevel *__restrict_
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const uint32_t c = (wv[q] >> (8 * b)) & 255u;
-                    if (c) {
+                    if (c == 2) o |= 255u << (8 * b);        // its tile-local component already holds a strong pixel
+                    else if (c) {
                         const int p = (int)i0 + q * 4 + b;
-                        const int root = uf_find_key(ld, (c == 2 ? 0 : kWeakBit) | p);
+                        const int root = uf_find_key(ld, kWeakBit | p);
                         if (!(root & kWeakBit)) o |= 255u << (8 * b);
                     }
                 }
@@ -318,8 +393,9 @@ __global__ void __launch_bounds__(256) k_canny_final(const ImgLevel *__restrict_
         for (size_t i = i0; i < i0 + 16 && i < n; ++i) {
             const int c = e[i];
             uint8_t o = 0;
-            if (c) {
-                const int root = uf_find_key(ld, (c == 2 ? 0 : kWeakBit) | (int)i);
+            if (c == 2) o = 255;
+            else if (c) {
+                const int root = uf_find_key(ld, kWeakBit | (int)i);
                 o = (root & kWeakBit) ? 0 : 255;
             }
             e[i] = o;

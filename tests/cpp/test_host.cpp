@@ -1,0 +1,87 @@
+// C++ consumer of revo_b200/host/revo_host.hpp: the reference's call sequence
+//   ImgPyramidRGBD(settings, camPyr, rgb, depth, ts) x2 ; kf->makeKeyframe() ; TrackerNew::trackFrames(R, T, error, kf, cur)
+// (system/system.cpp:151-188) through the C ABI.
+//   test_host --selftest             : no GPU needed; settings/camera rules, error path without a device
+//   test_host <fixture.bin> <out.txt>: tracks the pair stored in the fixture and writes status, error, R, T, evals
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../revo_b200/host/revo_host.hpp"
+
+static int selftest()
+{
+    ImgPyramidSettings s;
+    s.PYR_MIN_LVL = 3; s.fx = 517.3f; s.fy = 516.5f; s.cx = 318.6f; s.cy = 255.3f;
+    if (s.nLevels() != 4) return 1;
+    CameraPyr cp(s);
+    if (cp.size() != 5 || cp.at(3).width != 80 || cp.at(3).height != 60) return 2;
+    if (std::fabs(cp.at(2).fx - 517.3f / 4) > 1e-4f) return 3;
+    OptimizerSettings o;
+    if (o.USE_EDGE_FILTER || o.maxItsPerLvl[0] != 100 || o.edgeDistanceLvl[0] != 30.f || o.huber_edge != 0.3f) return 4;
+    TrackerSettings t;
+    if (!t.optimizerSettings.USE_EDGE_FILTER || !t.CHECK_INIT_VALUES) return 5;
+    revo_opt_config c = t.optimizerSettings.c_config();
+    if (c.use_edge_filter != 1 || c.convergence_eps[2] != 0.999f) return 6;
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc >= 2 && !std::strcmp(argv[1], "--selftest")) {
+        int rc = selftest();
+        if (rc) { std::printf("selftest failed: %d\n", rc); return rc; }
+        try {
+            revo::Context ctx(0);
+            std::printf("selftest ok (device present)\n");
+        } catch (const revo::Error &e) {
+            if (e.code != REVO_ERR_NO_DEVICE) { std::printf("unexpected error %d: %s\n", e.code, e.what()); return 20; }
+            std::printf("selftest ok (no device: %s)\n", e.what());
+        }
+        return 0;
+    }
+    if (argc < 3) { std::printf("usage: test_host --selftest | <fixture.bin> <out.txt>\n"); return 2; }
+    FILE *f = std::fopen(argv[1], "rb");
+    if (!f) return 3;
+    int hdr[4];   // w, h, n_levels, reserved
+    float cam[4];
+    if (std::fread(hdr, sizeof(int), 4, f) != 4 || std::fread(cam, sizeof(float), 4, f) != 4) return 4;
+    const int w = hdr[0], h = hdr[1];
+    std::vector<uint8_t> bgr[2];
+    std::vector<float> depth[2];
+    for (int i = 0; i < 2; ++i) {
+        bgr[i].resize((size_t)w * h * 3);
+        depth[i].resize((size_t)w * h);
+        if (std::fread(bgr[i].data(), 1, bgr[i].size(), f) != bgr[i].size()) return 5;
+        if (std::fread(depth[i].data(), sizeof(float), depth[i].size(), f) != depth[i].size()) return 6;
+    }
+    std::fclose(f);
+    try {
+        auto ctx = std::make_shared<revo::Context>(0);
+        ImgPyramidSettings s;
+        s.PYR_MIN_LVL = hdr[2] - 1; s.width = w; s.height = h; s.fx = cam[0]; s.fy = cam[1]; s.cx = cam[2]; s.cy = cam[3];
+        auto camPyr = std::make_shared<CameraPyr>(s);
+        auto kf = std::make_shared<ImgPyramidRGBD>(ctx, s, camPyr, bgr[0].data(), 0, 3, depth[0].data(), 0, 0.0);
+        auto cur = std::make_shared<ImgPyramidRGBD>(ctx, s, camPyr, bgr[1].data(), 0, 3, depth[1].data(), 0, 1.0 / 30);
+        bool threw = false;
+        try { cur->returnOptimizationStructure(0); } catch (const revo::Error &e) { threw = e.code == REVO_ERR_NOT_KEYFRAME; }
+        kf->makeKeyframe();
+        TrackerNew tracker(ctx, TrackerSettings(), s);
+        revo::Mat3f R = revo::Mat3f::Identity();
+        revo::Vec3f T = revo::Vec3f::Zero();
+        float error = 0.f;
+        TrackerNew::TrackerStatus st = tracker.trackFrames(R, T, error, kf, cur);
+        FILE *o = std::fopen(argv[2], "w");
+        std::fprintf(o, "%d %d %.9g %d %d\n", (int)st, threw ? 1 : 0, error, cur->return3DEdgesCount(0), (int)kf->returnEdges(0).data.size());
+        for (int i = 0; i < 9; ++i) std::fprintf(o, "%.9g ", R.m[i]);
+        std::fprintf(o, "\n%.9g %.9g %.9g\n", T[0], T[1], T[2]);
+        for (int l = 0; l < 6; ++l) std::fprintf(o, "%d ", tracker.lastResult.n_evals[l]);
+        std::fprintf(o, "\n");
+        std::fclose(o);
+    } catch (const revo::Error &e) {
+        std::printf("error %d: %s\n", e.code, e.what());
+        return 10;
+    }
+    return 0;
+}
