@@ -2,6 +2,7 @@
 // Host-side orchestration only: memory layout in HBM, descriptor tables, launch sequencing.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -405,7 +406,7 @@ static int alloc_keyframe_mem(revo_ctx *ctx, revo_pyr *p)
     uint8_t *m = (uint8_t *)p->kf_mem;
     for (int l = 0; l < p->n_levels; ++l) {
         const size_t px = (size_t)p->lv[l].w * p->lv[l].h;
-        p->lv[l].opt = (float4 *)m;
+        p->lv[l].opt = (uint4 *)m;
         p->lv[l].dt = (float *)(m + px * 16);
         m += align_up(px * 20, 256);
     }
@@ -506,9 +507,15 @@ int revo_pyr_download(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int which, vo
         case REVO_ARRAY_DT:
             if (!pyr->is_keyframe) return REVO_ERR_NOT_KEYFRAME;
             src = L.dt; bytes = px * 4; break;
-        case REVO_ARRAY_OPTSTRUCT:
+        case REVO_ARRAY_OPTSTRUCT: {
+            // the reference's float4 layout is materialised on demand from the distance transform
             if (!pyr->is_keyframe) return REVO_ERR_NOT_KEYFRAME;
-            src = L.opt; bytes = px * 16; break;
+            int rc = ensure_scratch(ctx, px * 16);
+            if (rc) return rc;
+            rc = launch_opt_struct_f4(ctx, L.dt, L.w, L.h, (float4 *)ctx->scratch);
+            if (rc) return rc;
+            src = ctx->scratch; bytes = px * 16; break;
+        }
         case REVO_ARRAY_EDGES3D_DEVICE_ORDER: {
             int n = 0;
             int rc = revo_pyr_num_edges(ctx, pyr, lvl, &n);
@@ -560,7 +567,11 @@ int revo_pyr_upload_level(revo_ctx *ctx, revo_pyr *pyr, int lvl, const float *pt
         if (rc) return rc;
         if (dt) REVO_CUDA(ctx, cudaMemcpyAsync(L.dt, dt, px * 4, cudaMemcpyHostToDevice, ctx->stream));
         if (opt4) {
-            REVO_CUDA(ctx, cudaMemcpyAsync(L.opt, opt4, px * 16, cudaMemcpyHostToDevice, ctx->stream));
+            rc = ensure_scratch(ctx, px * 16);
+            if (rc) return rc;
+            REVO_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, opt4, px * 16, cudaMemcpyHostToDevice, ctx->stream));
+            rc = launch_opt_pack_from_f4(ctx, (const float4 *)ctx->scratch, L.w, L.h, L.opt);
+            if (rc) return rc;
             pyr->is_keyframe = true;
         }
     }
@@ -643,9 +654,15 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
             e = cudaMemcpyAsync(trace_counts, d_tc, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
         if (e != cudaSuccess) rc = cuda_fail(ctx, e, "trace download");
     }
+    unsigned long long prof[4] = {0, 0, 0, 0};
+    const bool want_prof = getenv("REVO_TRACK_PROF") != nullptr;
+    if (!rc && want_prof) cudaMemcpyAsync(prof, d_wc + 2, sizeof(prof), cudaMemcpyDeviceToHost, ctx->stream);
     cudaFreeAsync(ws, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess && !rc) rc = cuda_fail(ctx, e, "track kernel");
+    if (!rc && want_prof && prof[3])
+        fprintf(stderr, "[k_track prof] pairs %d evals %llu  cycles/eval: gather %.0f reduce %.0f serial+sync %.0f\n", n, prof[3],
+                (double)prof[0] / prof[3], (double)prof[1] / prof[3], (double)prof[2] / prof[3]);
     return rc;
 }
 

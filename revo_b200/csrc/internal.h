@@ -26,7 +26,7 @@ struct ImgLevel {
     int *labels;          // scratch h*w int32: union-find labels (Canny) / column distances (EDT)
     uint8_t *flags;       // scratch h*w u8: "component holds a strong pixel"
     float *dt;            // dtPyr[l]         h*w   (keyframes, else nullptr)
-    float4 *opt;          // optimizationStructure[l] h*w (keyframes, else nullptr)
+    uint4 *opt;           // optimizationStructure[l] in the device PAIR layout (see k_opt_struct), h*w (keyframes)
     int w, h;
     int pts_cap;
     int patch;            // distPatchSizes[l]
@@ -110,6 +110,8 @@ int launch_hist_fill(revo_ctx *ctx, const ImgLevel *d_desc, const ImgLevel *d_to
                      int patch_low, bool do_fill, float n_percentage);
 int launch_compact(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, float dmin, float dmax);
 int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h);
+int launch_opt_struct_f4(revo_ctx *ctx, const float *d_dt, int w, int h, float4 *d_out);
+int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uint4 *d_out);
 // reference-order (column-major scan) 3-D edge list into d_out (capacity w*h float4); *d_n receives the count
 int launch_edges3d_reference_order(revo_ctx *ctx, const ImgLevel *d_desc_one, int w, int h, float dmin, float dmax,
                                    float4 *d_out, int *d_n, int *d_col_off);
@@ -118,7 +120,7 @@ int launch_edges3d_reference_order(revo_ctx *ctx, const ImgLevel *d_desc_one, in
 struct LevelIn {
     const float4 *pts;
     const int *n_pts;
-    const float4 *opt;
+    const uint4 *opt;    // pair layout: {dt(x), dt(x+1), snorm16 gx|gy (x), snorm16 gx|gy (x+1)}
     float fx, fy, cx, cy;
     int w, h;
 };

@@ -429,6 +429,30 @@ __global__ void __launch_bounds__(256) k_edt_rows(const ImgLevel *__restrict__ d
     }
 }
 
+// The reference's {gx, gy, dt, .} float4 texel (imgpyramidrgbd.cpp:255-276) at linear index i; zeros in rows 0 and h-1.
+__device__ __forceinline__ float4 opt_texel(const float *__restrict__ dt, size_t i, int w, int h)
+{
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= (size_t)w && i < (size_t)w * (h - 1)) {
+        o.x = __fmul_rn(0.5f, __fsub_rn(dt[i - 1], dt[i + 1]));
+        o.y = __fmul_rn(0.5f, __fsub_rn(dt[i - w], dt[i + w]));
+        o.z = dt[i];
+    }
+    return o;
+}
+
+// Gradient components lie in [-1, 1] (|dt[a] - dt[b]| <= 2 for pixels two apart): 16-bit fixed point, step 1/32764 (a multiple of 4, so the frequent exact values 0, +-1/4, +-1/2, +-1 carry no rounding bias).
+__device__ __forceinline__ uint32_t pack_grad(float gx, float gy)
+{
+    const int qx = __float2int_rn(fminf(fmaxf(gx, -1.f), 1.f) * 32764.f);
+    const int qy = __float2int_rn(fminf(fmaxf(gy, -1.f), 1.f) * 32764.f);
+    return ((uint32_t)qx & 0xffffu) | ((uint32_t)qy << 16);
+}
+
+// K8 (device layout): one 16-byte record per pixel holding the texel PAIR (x, y), (x+1, y) the bilinear fetch of
+// the tracker needs from one row: {dt(x), dt(x+1), snorm16 gx,gy (x), snorm16 gx,gy (x+1)}.  A residual evaluation
+// then costs two 16-byte gathers per edge point instead of four; dt stays float32, only the Jacobian direction is
+// quantised (1.5e-5 absolute).  The reference's float4 array is produced on demand for the accessor (k_opt_struct_f4).
 __global__ void __launch_bounds__(256) k_opt_struct(const ImgLevel *__restrict__ desc, int w, int h)
 {
     const int f = blockIdx.z;
@@ -436,13 +460,42 @@ __global__ void __launch_bounds__(256) k_opt_struct(const ImgLevel *__restrict__
     const size_t n = (size_t)w * h;
     if (i >= n) return;
     const float *__restrict__ dt = desc[f].dt;
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i >= (size_t)w && i < (size_t)w * (h - 1)) {
-        o.x = __fmul_rn(0.5f, __fsub_rn(dt[i - 1], dt[i + 1]));
-        o.y = __fmul_rn(0.5f, __fsub_rn(dt[i - w], dt[i + w]));
-        o.z = dt[i];
-    }
-    desc[f].opt[i] = o;
+    const float4 a = opt_texel(dt, i, w, h);
+    const float4 b = (i + 1 < n) ? opt_texel(dt, i + 1, w, h) : make_float4(0.f, 0.f, 0.f, 0.f);
+    desc[f].opt[i] = make_uint4(__float_as_uint(a.z), __float_as_uint(b.z), pack_grad(a.x, a.y), pack_grad(b.x, b.y));
+}
+
+// the reference layout, for returnOptimizationStructure(): out[i] = {gx, gy, dt, 0}
+__global__ void __launch_bounds__(256) k_opt_struct_f4(const float *__restrict__ dt, int w, int h, float4 *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)w * h) return;
+    out[i] = opt_texel(dt, i, w, h);
+}
+
+// test hook: caller-provided float4 structure -> device pair layout
+__global__ void __launch_bounds__(256) k_opt_pack_from_f4(const float4 *__restrict__ in, int w, int h, uint4 *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)w * h;
+    if (i >= n) return;
+    const float4 a = in[i];
+    const float4 b = (i + 1 < n) ? in[i + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    out[i] = make_uint4(__float_as_uint(a.z), __float_as_uint(b.z), pack_grad(a.x, a.y), pack_grad(b.x, b.y));
+}
+
+int launch_opt_struct_f4(revo_ctx *ctx, const float *d_dt, int w, int h, float4 *d_out)
+{
+    k_opt_struct_f4<<<cdiv(w * h, 256), 256, 0, ctx->stream>>>(d_dt, w, h, d_out);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
+int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uint4 *d_out)
+{
+    k_opt_pack_from_f4<<<cdiv(w * h, 256), 256, 0, ctx->stream>>>(d_in, w, h, d_out);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
 }
 
 int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h)

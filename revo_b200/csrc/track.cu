@@ -21,6 +21,7 @@
 // iterations of a pair run without a host round trip.  No tensor cores: there is no dense contraction here.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "internal.h"
 
@@ -128,7 +129,7 @@ __device__ __forceinline__ void se3_exp(const double *xi, double *q, double *t)
     } else {
         double s, c;
         sincos(0.5 * theta, &s, &c);
-        const double inv_t = 1.0 / theta, inv_t2 = inv_t * inv_t;
+        const double inv_t = __drcp_rn(theta), inv_t2 = inv_t * inv_t;
         imag = s * inv_t;
         re = c;
         c1 = 2.0 * s * s * inv_t2;                       // (1 - cos t) / t^2
@@ -160,7 +161,7 @@ __device__ __forceinline__ void se3_mul(const double *qa, const double *ta, cons
     double z = aw * bz + az * bw + ax * by - ay * bx;
     const double sn = x * x + y * y + z * z + w * w;
     if (sn != 1.0) {
-        const double s = 2.0 / (1.0 + sn);
+        const double s = 2.0 * __drcp_rn(1.0 + sn);
         x *= s; y *= s; z *= s; w *= s;
     }
     q[0] = x; q[1] = y; q[2] = z; q[3] = w;
@@ -187,7 +188,7 @@ __device__ __forceinline__ void solve6(const double *Au /* 21 upper slots */, co
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         const double dk = a[k][k];
-        const double id = (dk > 0.0 && dk < 1e300) ? 1.0 / dk : 0.0;
+        const double id = (dk > 0.0 && dk < 1e300) ? __drcp_rn(dk) : 0.0;
         invd[k] = id;
 #pragma unroll
         for (int j = k + 1; j < 6; ++j) {
@@ -215,7 +216,7 @@ __device__ __forceinline__ void solve6(const double *Au /* 21 upper slots */, co
 // ---- per-point work: PASS A + PASS B fused ---------------------------------------
 struct Proj {
     float Wx, Wy, iz, dx, dy;
-    const float4 *bp;
+    const uint4 *bp;
     int state;   // 0 = no point, 1 = in bounds (texels wanted), 2 = out of bounds
 };
 
@@ -241,17 +242,29 @@ __device__ __forceinline__ Proj project(bool exists, const float4 p, const Level
     return o;
 }
 
-__device__ __forceinline__ void finish_point(const Proj &P, const float4 t00, const float4 t10, const float4 t01, const float4 t11,
-                                             const LevelIn &L, float edge_dist, bool use_filter, float huber, float (&acc)[32])
+// snorm16 pair -> floats (scale folded in by the caller)
+__device__ __forceinline__ void unpack_grad(uint32_t g, float &gx, float &gy)
+{
+    gx = (float)(short)(g & 0xffffu);
+    gy = (float)((int)g >> 16);
+}
+
+// r0 = pair record of row iy (texels (ix,iy),(ix+1,iy)), r1 = pair record of row iy+1
+__device__ __forceinline__ void finish_point(const Proj &P, const uint4 r0, const uint4 r1, const LevelIn &L, float edge_dist,
+                                             bool use_filter, float huber, float (&acc)[32])
 {
     if (P.state == 0) return;
     if (P.state == 2) { acc[kRecBad] += 1.f; return; }
     // getInterpolatedElement43, optimizer.h:173-185
     const float dxdy = P.dx * P.dy;
     const float w11 = dxdy, w01 = P.dy - dxdy, w10 = P.dx - dxdy, w00 = 1.f - P.dx - P.dy + dxdy;
-    const float gxi = w11 * t11.x + w01 * t01.x + w10 * t10.x + w00 * t00.x;
-    const float gyi = w11 * t11.y + w01 * t01.y + w10 * t10.y + w00 * t00.y;
-    const float r = w11 * t11.z + w01 * t01.z + w10 * t10.z + w00 * t00.z;
+    float gx00, gy00, gx10, gy10, gx01, gy01, gx11, gy11;
+    unpack_grad(r0.z, gx00, gy00); unpack_grad(r0.w, gx10, gy10);
+    unpack_grad(r1.z, gx01, gy01); unpack_grad(r1.w, gx11, gy11);
+    constexpr float kq = 1.0f / 32764.0f;
+    const float gxi = (w11 * gx11 + w01 * gx01 + w10 * gx10 + w00 * gx00) * kq;
+    const float gyi = (w11 * gy11 + w01 * gy01 + w10 * gy10 + w00 * gy00) * kq;
+    const float r = w11 * __uint_as_float(r1.y) + w01 * __uint_as_float(r1.x) + w10 * __uint_as_float(r0.y) + w00 * __uint_as_float(r0.x);
     if (use_filter && r > edge_dist) {                                             // optimizer.cpp:112
         acc[kRecBad] += 1.f;
         return;
@@ -331,14 +344,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-template <int kThreads>
-struct MinBlocks {
-    static constexpr int value = kThreads <= 128 ? 4 : (kThreads <= 256 ? 2 : 1);
-};
 
 // ---- the kernel ---------------------------------------------------------------
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads, MinBlocks<kThreads>::value)
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, revo_track_result *__restrict__ results,
         double *__restrict__ records, revo_trace_entry *__restrict__ trace, int *__restrict__ trace_counts,
         int *__restrict__ work_counter)
@@ -416,6 +425,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
         __syncthreads();
     };
 
+    long long prof_gather = 0, prof_reduce = 0, prof_serial = 0, prof_evals = 0;   // thread 0: cycles per phase
     int pair = cluster_id;
     while (pair < n_pairs) {
         const PairDesc &P = pairs[pair];
@@ -507,6 +517,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                     float acc[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                    const long long c_begin = clock64();
                     // Software pipeline, two register sets (A/B): while point k is being finished, the four texel
                     // gathers of point k+1 and the list entry of point k+2 are already in flight.
                     {
@@ -518,27 +529,29 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                         bool eB = i < hi;
                         float4 pB = __ldg(pts + (eB ? i : lo));
                         Proj A = project(eA, pA, L, R, t);
-                        float4 a00 = __ldg(A.bp), a10 = __ldg(A.bp + 1), a01 = __ldg(A.bp + L.w), a11 = __ldg(A.bp + L.w + 1);
+                        uint4 a0 = __ldg(A.bp), a1 = __ldg(A.bp + L.w);
                         while (true) {
                             i += kThreads;
                             const bool eC = i < hi;
                             const float4 pC = __ldg(pts + (eC ? i : lo));
                             const Proj B = project(eB, pB, L, R, t);
-                            const float4 b00 = __ldg(B.bp), b10 = __ldg(B.bp + 1), b01 = __ldg(B.bp + L.w), b11 = __ldg(B.bp + L.w + 1);
-                            finish_point(A, a00, a10, a01, a11, L, ed, use_filter, huber, acc);
+                            const uint4 b0 = __ldg(B.bp), b1 = __ldg(B.bp + L.w);
+                            finish_point(A, a0, a1, L, ed, use_filter, huber, acc);
                             if (!eB) break;
                             i += kThreads;
                             const bool eD = i < hi;
                             const float4 pD = __ldg(pts + (eD ? i : lo));
                             A = project(eC, pC, L, R, t);
-                            a00 = __ldg(A.bp); a10 = __ldg(A.bp + 1); a01 = __ldg(A.bp + L.w); a11 = __ldg(A.bp + L.w + 1);
-                            finish_point(B, b00, b10, b01, b11, L, ed, use_filter, huber, acc);
+                            a0 = __ldg(A.bp); a1 = __ldg(A.bp + L.w);
+                            finish_point(B, b0, b1, L, ed, use_filter, huber, acc);
                             if (!eC) break;
                             eB = eD;
                             pB = pD;
                         }
                     }
+                    const long long c_gather = clock64();
                     reduce_record(acc);
+                    const long long c_reduce = clock64();
                     evals_lvl[lvl]++;
                     last_good = (float)rec[kRecGood]; last_bad = (float)rec[kRecBad];
                     last_sw = (float)rec[kRecSW]; last_su = (float)rec[kRecSU];
@@ -599,7 +612,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                         }
                         if (propose && !done) {
                             // solve (A/n with diag *(1+lambda)) inc = (sum w r v)/n     :258-262
-                            solve6(lm.A, lm.b, 1.0 / lm.n, (double)(1.f + lm.lambda), lm.inc);
+                            solve6(lm.A, lm.b, __drcp_rn(lm.n), (double)(1.f + lm.lambda), lm.inc);
                             lm.incTry++; lm.tries++;
                             double qe[4], te[3];
                             se3_exp(lm.inc, qe, te);
@@ -620,6 +633,11 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                     }
                     first = false;
                     __syncthreads();
+                    if (tid == 0) {
+                        const long long c_end = clock64();
+                        prof_gather += c_gather - c_begin; prof_reduce += c_reduce - c_gather; prof_serial += c_end - c_reduce;
+                        prof_evals++;
+                    }
                     if (ctrl.level_done) break;
                 }
                 __syncthreads();
@@ -652,16 +670,23 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
         pair = *cluster.map_shared_rank(&ctrl.next_pair, 0);
         if (C > 1) cluster.sync(); else __syncthreads();
     }
+    if (tid == 0 && crank == 0) {   // phase cycle counters behind the work counter (read back when REVO_TRACK_PROF is set)
+        unsigned long long *prof = (unsigned long long *)(work_counter + 2);
+        atomicAdd(prof + 0, (unsigned long long)prof_gather);
+        atomicAdd(prof + 1, (unsigned long long)prof_reduce);
+        atomicAdd(prof + 2, (unsigned long long)prof_serial);
+        atomicAdd(prof + 3, (unsigned long long)prof_evals);
+    }
     if (C > 1 || world > 1) cluster.sync();   // nobody may exit while a peer can still read its shared memory
 }
 
 // ---- launcher -------------------------------------------------------------------
-template <int kThreads>
+template <int kThreads, int kMinBlocks>
 static int launch_track_t(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, int ctas_per_pair,
                           revo_track_result *d_results, double *d_records, revo_trace_entry *d_trace, int *d_trace_counts,
                           int *d_work_counter)
 {
-    auto kern = k_track<kThreads>;
+    auto kern = k_track<kThreads, kMinBlocks>;
     if (ctas_per_pair > 8) REVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -696,21 +721,25 @@ int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const Trac
 {
     if (n_pairs <= 0) return REVO_OK;
     const int T = ctx->track_threads > 0 ? ctx->track_threads : 256;
+    // register budget: "dense" = 85 registers/thread (3 CTAs of 256 or 6 of 128 per SM) instead of 128
+    static const bool dense = getenv("REVO_TRACK_DENSE") ? atoi(getenv("REVO_TRACK_DENSE")) != 0 : false;
     int C = ctx->track_ctas_per_pair;
     if (C <= 0) {
         // automatic: fill the CTA slots of the chip (SMs x resident CTAs of this shape); a pair alone gets a
         // full portable cluster
-        const int per_sm = T <= 128 ? 4 : (T <= 256 ? 2 : 1);
+        const int per_sm = (T <= 128 ? 4 : (T <= 256 ? 2 : 1)) + (dense && T <= 256 ? (T <= 128 ? 2 : 1) : 0);
         const int slots = ctx->prop.multiProcessorCount * per_sm;
         C = 1;
         while (C < 8 && n_pairs * (C * 2) <= slots) C *= 2;
     }
+#define REVO_TRACK_ARGS ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter
     switch (T) {
-        case 128: return launch_track_t<128>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter);
-        case 512: return launch_track_t<512>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter);
-        case 1024: return launch_track_t<1024>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter);
-        default: return launch_track_t<256>(ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter);
+        case 128: return dense ? launch_track_t<128, 6>(REVO_TRACK_ARGS) : launch_track_t<128, 4>(REVO_TRACK_ARGS);
+        case 512: return launch_track_t<512, 1>(REVO_TRACK_ARGS);
+        case 1024: return launch_track_t<1024, 1>(REVO_TRACK_ARGS);
+        default: return dense ? launch_track_t<256, 3>(REVO_TRACK_ARGS) : launch_track_t<256, 2>(REVO_TRACK_ARGS);
     }
+#undef REVO_TRACK_ARGS
 }
 
 }  // namespace revo
