@@ -617,6 +617,7 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     }
     if (!trace) trace_cap = 0;
     prm.trace_cap = trace_cap;
+    prm.profile = getenv("REVO_TRACK_PROF") != nullptr;
     // device workspace: pairs | results | records | trace | trace counts
     const size_t b_pairs = align_up(sizeof(PairDesc) * (size_t)n, 256);
     const size_t b_res = align_up(sizeof(revo_track_result) * (size_t)n, 256);

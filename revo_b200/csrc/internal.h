@@ -135,6 +135,7 @@ struct TrackParams {
     int mode;            // 0 = full trackFrames, 1 = single level (Optimizer::trackFrames), 2 = one evaluation
     int level;           // for modes 1,2
     int trace_cap;
+    int profile;         // 1: thread 0 accumulates clock64() cycles per phase (REVO_TRACK_PROF)
     // split mode
     int split_rank, split_world;
     unsigned long long split_seq0;

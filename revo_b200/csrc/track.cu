@@ -503,7 +503,11 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
             for (int lvl = min_lvl; lvl >= max_lvl; --lvl) {
                 const LevelIn L = P.lvl[lvl];
                 const int n = *L.n_pts;
-                const int lo = (int)((long long)n * member / n_members), hi = (int)((long long)n * (member + 1) / n_members);
+                // block-cyclic split of the list over the CTAs of the cluster (and the ranks of a GPU split): member m takes
+                // the blocks m, m + M, m + 2M, ... of kThreads points -- balanced (the cluster barrier waits for the slowest
+                // CTA) and the cluster as a whole still sweeps the tile-major list front to back
+                const int lo = 0, hi = n;
+                const int stride = n_members * kThreads;
                 const float ed = oc.edge_distance_lvl[lvl];
                 const float huber = oc.huber_edge;
                 bool first = true;
@@ -517,28 +521,28 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                     float acc[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-                    const long long c_begin = clock64();
+                    const long long c_begin = prm.profile ? clock64() : 0;
                     // Software pipeline, two register sets (A/B): while point k is being finished, the four texel
                     // gathers of point k+1 and the list entry of point k+2 are already in flight.
                     {
                         const float4 *__restrict__ pts = L.pts;
-                        int i = lo + tid;
+                        int i = member * kThreads + tid;
                         bool eA = i < hi;
                         float4 pA = __ldg(pts + (eA ? i : lo));
-                        i += kThreads;
+                        i += stride;
                         bool eB = i < hi;
                         float4 pB = __ldg(pts + (eB ? i : lo));
                         Proj A = project(eA, pA, L, R, t);
                         uint4 a0 = __ldg(A.bp), a1 = __ldg(A.bp + L.w);
                         while (true) {
-                            i += kThreads;
+                            i += stride;
                             const bool eC = i < hi;
                             const float4 pC = __ldg(pts + (eC ? i : lo));
                             const Proj B = project(eB, pB, L, R, t);
                             const uint4 b0 = __ldg(B.bp), b1 = __ldg(B.bp + L.w);
                             finish_point(A, a0, a1, L, ed, use_filter, huber, acc);
                             if (!eB) break;
-                            i += kThreads;
+                            i += stride;
                             const bool eD = i < hi;
                             const float4 pD = __ldg(pts + (eD ? i : lo));
                             A = project(eC, pC, L, R, t);
@@ -549,9 +553,9 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                             pB = pD;
                         }
                     }
-                    const long long c_gather = clock64();
+                    const long long c_gather = prm.profile ? clock64() : 0;
                     reduce_record(acc);
-                    const long long c_reduce = clock64();
+                    const long long c_reduce = prm.profile ? clock64() : 0;
                     evals_lvl[lvl]++;
                     last_good = (float)rec[kRecGood]; last_bad = (float)rec[kRecBad];
                     last_sw = (float)rec[kRecSW]; last_su = (float)rec[kRecSU];
@@ -633,7 +637,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                     }
                     first = false;
                     __syncthreads();
-                    if (tid == 0) {
+                    if (prm.profile && tid == 0) {
                         const long long c_end = clock64();
                         prof_gather += c_gather - c_begin; prof_reduce += c_reduce - c_gather; prof_serial += c_end - c_reduce;
                         prof_evals++;
@@ -670,7 +674,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
         pair = *cluster.map_shared_rank(&ctrl.next_pair, 0);
         if (C > 1) cluster.sync(); else __syncthreads();
     }
-    if (tid == 0 && crank == 0) {   // phase cycle counters behind the work counter (read back when REVO_TRACK_PROF is set)
+    if (prm.profile && tid == 0 && crank == 0) {   // phase cycle counters behind the work counter (read back when REVO_TRACK_PROF is set)
         unsigned long long *prof = (unsigned long long *)(work_counter + 2);
         atomicAdd(prof + 0, (unsigned long long)prof_gather);
         atomicAdd(prof + 1, (unsigned long long)prof_reduce);

@@ -47,6 +47,7 @@ class StreamTracker:
         self.total_evals = 0
         self.total_point_evals = 0          # sum over pairs/levels of n_pts * n_evals (roofline numerator / 60 B)
         self.last = None
+        self._pending = None
 
     def start(self, bgr, depth):
         """First frame of every stream: becomes the keyframe (system.cpp:151-175)."""
@@ -55,9 +56,23 @@ class StreamTracker:
         self.prev = None
         self.frame = 0
 
+    def prefetch(self, bgr, depth):
+        """Start building the pyramids of the NEXT frame: upload + kernels are enqueued asynchronously; with a backend
+        that owns a separate build stream they overlap the tracking of the current frame."""
+        self._pending = self.be.create(bgr, depth, self.B)
+
+    def step_pipelined(self, next_bgr=None, next_depth=None):
+        """Track the frame handed to prefetch() earlier and, before doing so, enqueue the build of the frame after it."""
+        cur = self._pending
+        self.be.wait_created()                       # frame k is complete on the build stream
+        self._pending = self.be.create(next_bgr, next_depth, self.B) if next_bgr is not None else None
+        return self._track(cur)
+
     def step(self, bgr, depth):
-        """Track the next frame of every stream against its keyframe."""
-        cur = self.be.create(bgr, depth, self.B)
+        """Build the pyramids of the next frame of every stream and track it against its keyframe."""
+        return self._track(self.be.create(bgr, depth, self.B))
+
+    def _track(self, cur):
         T_init = self.T_kf_prev @ self.T_nm1_n                     # system.cpp:268
         out = self.be.track(T_init[:, :3, :3], T_init[:, :3, 3], self.kf, cur)
         T_kf_n = np.tile(np.eye(4, dtype=np.float32), (self.B, 1, 1))
@@ -86,28 +101,34 @@ class StreamTracker:
         return out
 
     def close(self):
-        if self.prev is not None:
-            self.be.destroy(self.prev)
-        if self.kf is not None:
-            self.be.destroy(self.kf)
-        self.prev = self.kf = None
+        for h in (self.prev, self.kf, self._pending):
+            if h is not None:
+                self.be.destroy(h)
+        self.prev = self.kf = self._pending = None
 
 
 class CudaBackend:
     """The product path: everything through the C ABI (revo_b200/api.py)."""
 
-    def __init__(self, ctx, settings, tracker_settings=None):
+    def __init__(self, ctx, settings, tracker_settings=None, build_ctx=None):
+        """ctx: context (stream) that tracks and promotes keyframes; build_ctx: optional second context whose stream
+        uploads frames and builds pyramids, so that the H2D copy of frame k+1 overlaps the tracking of frame k."""
         from . import api
 
         self.api = api
         self.ctx = ctx
+        self.build_ctx = build_ctx or ctx
         self.settings = settings
         self.tracker = api.TrackerNew(ctx, tracker_settings or api.TrackerSettings(), settings)
         self.campyr = api.CameraPyr(settings)
 
     def create(self, bgr, depth, n):
-        return self.api.ImgPyramidRGBD.create_batch(self.ctx, self.settings, bgr, depth, n=n, channels=3, cameraPyr=self.campyr,
-                                                    synchronize=False)
+        return self.api.ImgPyramidRGBD.create_batch(self.build_ctx, self.settings, bgr, depth, n=n, channels=3,
+                                                    cameraPyr=self.campyr, synchronize=False)
+
+    def wait_created(self):
+        if self.build_ctx is not self.ctx:
+            self.build_ctx.synchronize()
 
     def make_keyframes(self, handles):
         self.api.ImgPyramidRGBD.makeKeyframes(self.ctx, handles)
