@@ -281,6 +281,7 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
     Slab *slab = new (std::nothrow) Slab();
     if (!slab) return REVO_ERR_INVALID_ARG;
     slab->n_frames = n; slab->live = n; slab->bytes = total; slab->mem = nullptr;
+    slab->stream = ctx->stream; slab->ready = nullptr;
     cudaError_t e = cudaMallocAsync(&slab->mem, total, ctx->stream);
     if (e != cudaSuccess) { delete slab; return cuda_fail(ctx, e, "cudaMallocAsync(slab)"); }
     uint8_t *base = (uint8_t *)slab->mem;
@@ -371,6 +372,7 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
     if (rc) return fail(rc);
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->ev_valid[0] = true;
+    if (cudaEventCreateWithFlags(&slab->ready, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(slab->ready, ctx->stream);
     for (int f = 0; f < n; ++f) pyr_out[f] = pyrs[f];
     return REVO_OK;
 }
@@ -395,6 +397,12 @@ int revo_pyr_create(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera
     int rc = revo_pyr_create_batch(ctx, cfg, cam0, 1, b.data(), channels, d.data(), &timestamp, pyr_out);
     if (!rc) cudaStreamSynchronize(ctx->stream);   // the temporaries die here
     return rc;
+}
+
+// A pyramid built on another context's stream: order this context's stream after the build (no host sync).
+static void wait_for_build(revo_ctx *ctx, const revo_pyr *p)
+{
+    if (p && p->slab && p->slab->ready && p->slab->stream != ctx->stream) cudaStreamWaitEvent(ctx->stream, p->slab->ready, 0);
 }
 
 static int alloc_keyframe_mem(revo_ctx *ctx, revo_pyr *p)
@@ -428,6 +436,7 @@ int revo_pyr_make_keyframe_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs)
     for (auto *p : todo)
         if (p->n_levels != NL || p->lv[0].w != todo[0]->lv[0].w || p->lv[0].h != todo[0]->lv[0].h) return REVO_ERR_INVALID_ARG;
     for (auto *p : todo) {
+        wait_for_build(ctx, p);
         int rc = alloc_keyframe_mem(ctx, p);
         if (rc) return rc;
     }
@@ -459,6 +468,7 @@ int revo_pyr_destroy(revo_ctx *ctx, revo_pyr *pyr)
     if (pyr->kf_mem) cudaFreeAsync(pyr->kf_mem, ctx->stream);
     Slab *s = pyr->slab;
     if (s && --s->live == 0) {
+        if (s->ready) cudaEventDestroy(s->ready);
         cudaFreeAsync(s->mem, ctx->stream);
         delete s;
     }
@@ -614,6 +624,8 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     for (int i = 0; i < n; ++i) {
         int rc = fill_pair(refs[i], curs[i], min_lvl, max_lvl, R9s + 9 * (size_t)i, t3s + 3 * (size_t)i, &host[i]);
         if (rc) return rc;
+        wait_for_build(ctx, refs[i]);
+        wait_for_build(ctx, curs[i]);
     }
     if (!trace) trace_cap = 0;
     prm.trace_cap = trace_cap;

@@ -84,6 +84,8 @@ struct Slab {
     size_t bytes;
     int n_frames;
     int live;             // pyramids still alive
+    cudaStream_t stream;  // stream the frames were built on
+    cudaEvent_t ready;    // recorded on `stream` when the build is complete; other streams wait on it before reading
     ImgLevel *d_desc[REVO_MAX_LEVELS];  // device descriptor tables, n_frames entries each (inside mem)
 };
 

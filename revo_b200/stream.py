@@ -52,6 +52,7 @@ class StreamTracker:
     def start(self, bgr, depth):
         """First frame of every stream: becomes the keyframe (system.cpp:151-175)."""
         self.kf = self.be.create(bgr, depth, self.B)
+        self.be.wait_created()
         self.be.make_keyframes(self.kf)
         self.prev = None
         self.frame = 0
