@@ -356,7 +356,16 @@ __global__ void __launch_bounds__(192) k_canny_merge(const ImgLevel *__restrict_
 }
 
 // ---- (C) ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_canny_final(const ImgLevel *__restrict__ desc, int w, int h)
+// Also accumulates the patch histogram of generateDistHistogram (imgpyramidrgbd.cpp:146-172) for the edge pixels it
+// emits (integer counters in the per-frame scratch, finalised to the reference's wrapping u8 by k_hist_finalize).
+__device__ __forceinline__ void hist_add(const ImgLevel &L, int *cnt, int p, int w, int P)
+{
+    const int y = p / w, x = p - y * w;
+    const int py = y / P, px = x / P;
+    if (py < L.hist_h && px < L.hist_w) atomicAdd(cnt + py * L.hist_w + px, 1);
+}
+
+__global__ void __launch_bounds__(256) k_canny_final(const ImgLevel *__restrict__ desc, int w, int h, int P)
 {
     const int f = blockIdx.z;
     const size_t n = (size_t)w * h;
@@ -364,6 +373,7 @@ __global__ void __launch_bounds__(256) k_canny_final(const ImgLevel *__restrict_
     if (i0 >= n) return;
     uint8_t *e = desc[f].edges, *eo = desc[f].edges_orig;
     const int *lab = desc[f].labels;
+    int *cnt = (int *)desc[f].flags;
     auto ld = [&](int i) { return __ldcg(lab + i); };
     if (i0 + 16 <= n && ((((uintptr_t)(e + i0)) & 15) == 0) && ((((uintptr_t)(eo + i0)) & 15) == 0)) {
         uint4 v = *(const uint4 *)(e + i0);
@@ -384,6 +394,9 @@ __global__ void __launch_bounds__(256) k_canny_final(const ImgLevel *__restrict_
                     }
                 }
                 wv[q] = o;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if ((o >> (8 * b)) & 255u) hist_add(desc[f], cnt, (int)i0 + q * 4 + b, w, P);
             }
             v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             *(uint4 *)(e + i0) = v;
@@ -400,6 +413,7 @@ __global__ void __launch_bounds__(256) k_canny_final(const ImgLevel *__restrict_
             }
             e[i] = o;
             eo[i] = o;
+            if (o) hist_add(desc[f], cnt, (int)i, w, P);
         }
     }
 }
@@ -439,8 +453,35 @@ bool make_gray_tensor_map(void *tmap_out, const uint8_t *base, int w, int h, int
     return r == CUDA_SUCCESS;
 }
 
-int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high, const void *gray_tmap)
+// counts -> wrapping u8 histogram + number of non-empty patches (countNonZero(dist), imgpyramidrgbd.cpp:160)
+__global__ void __launch_bounds__(256) k_hist_finalize(const ImgLevel *__restrict__ desc)
 {
+    __shared__ int red[8];
+    const ImgLevel &L = desc[blockIdx.x];
+    const int *cnt = (const int *)L.flags;
+    const int n = L.hist_w * L.hist_h;
+    int nz = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint8_t v = (uint8_t)(cnt[i] & 255);
+        L.hist[i] = v;
+        nz += v != 0;
+    }
+    nz = __reduce_add_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nz;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int k = 0; k < 8; ++k) s += red[k];
+        *L.nz_patches = s;
+    }
+}
+
+int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high, const void *gray_tmap, int patch,
+                 void *d_counts0, size_t counts_stride)
+{
+    const int hist_w = w / patch, hist_h = h / patch;
+    if (hist_w > 0 && hist_h > 0)
+        REVO_CUDA(ctx, cudaMemset2DAsync(d_counts0, counts_stride, 0, (size_t)hist_w * hist_h * sizeof(int), (size_t)n, ctx->stream));
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     const int use_tma = gray_tmap != nullptr;
@@ -451,8 +492,12 @@ int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int
     k_canny_merge<<<grid, 192, 0, ctx->stream>>>(d_desc, w, h);
     LAUNCH_CHECK(ctx);
     dim3 g3(cdiv(cdiv(w * h, 16), 256), 1, n);
-    k_canny_final<<<g3, 256, 0, ctx->stream>>>(d_desc, w, h);
+    k_canny_final<<<g3, 256, 0, ctx->stream>>>(d_desc, w, h, patch);
     LAUNCH_CHECK(ctx);
+    if (hist_w > 0 && hist_h > 0) {
+        k_hist_finalize<<<n, 256, 0, ctx->stream>>>(d_desc);
+        LAUNCH_CHECK(ctx);
+    }
     return REVO_OK;
 }
 

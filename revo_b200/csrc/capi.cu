@@ -361,7 +361,8 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
         if (!rc) {
             alignas(64) unsigned char tmap[128];
             const bool tma = make_gray_tensor_map(tmap, base + o_gray[l], g[l].w, g[l].h, n, align_up((size_t)g[l].w * g[l].h, 256));
-            rc = launch_canny(ctx, slab->d_desc[l], n, g[l].w, g[l].h, low, high, tma ? tmap : nullptr);
+            rc = launch_canny(ctx, slab->d_desc[l], n, g[l].w, g[l].h, low, high, tma ? tmap : nullptr, g[l].patch, base + o_flags,
+                              align_up((size_t)w0 * h0, 256));
         }
         // fill-in is only defined for the reference's 3 patch sizes (levels 1,2); see SURVEY D5
         const bool fill = cfg->use_edge_hist && l >= 1 && l <= 2;

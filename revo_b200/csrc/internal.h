@@ -24,7 +24,7 @@ struct ImgLevel {
     int *nz_patches;      // countNonZero(hist) (device scalar)
     int *tile_off;        // per-tile exclusive offsets of the compaction (n_tiles + 1)
     int *labels;          // scratch h*w int32: union-find labels (Canny) / column distances (EDT)
-    uint8_t *flags;       // scratch h*w u8: "component holds a strong pixel"
+    uint8_t *flags;       // scratch w0*h0 bytes per frame: integer patch counters of the histogram (K5)
     float *dt;            // dtPyr[l]         h*w   (keyframes, else nullptr)
     uint4 *opt;           // optimizationStructure[l] in the device PAIR layout (see k_opt_struct), h*w (keyframes)
     int w, h;
@@ -104,7 +104,10 @@ int launch_gray(revo_ctx *ctx, const uint8_t *d_bgr, size_t stride, int ch, size
 int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst,
                          int w_src, int h_src);
 // gray_tmap: host pointer to a CUtensorMap made by make_gray_tensor_map (nullptr = plain loads)
-int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high, const void *gray_tmap);
+// Also produces the patch histogram (hist, nz_patches) of the Canny output; d_counts0/counts_stride: the per-frame
+// scratch (ImgLevel::flags of frame 0, byte stride between frames) used for the integer counters.
+int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high, const void *gray_tmap, int patch,
+                 void *d_counts0, size_t counts_stride);
 // 3-D (x, y, frame) tensor map over the u8 gray images of one level of a slab; false if TMA cannot be used
 bool make_gray_tensor_map(void *tmap_out /* 128 bytes, 64-aligned */, const uint8_t *base, int w, int h, int n_frames,
                           size_t frame_stride);

@@ -214,9 +214,7 @@ int launch_hist_fill(revo_ctx *ctx, const ImgLevel *d_desc, const ImgLevel *d_to
 {
     const int hist_w = w / patch, hist_h = h / patch;
     if (hist_w > 0 && hist_h > 0) {
-        dim3 grid(hist_h, 1, n);
-        k_hist<<<grid, 256, hist_w * sizeof(int), ctx->stream>>>(d_desc, w, h, patch);
-        LAUNCH_CHECK(ctx);
+        // the histogram itself is produced by the Canny output kernel (canny.cu: k_canny_final + k_hist_finalize)
         if (do_fill) {
             dim3 block(32, 8), g2(cdiv(w, 32), cdiv(h, 8), n);
             k_fill_in<<<g2, block, 0, ctx->stream>>>(d_desc, d_top, w, h, patch, patch_low, n_percentage);
@@ -318,9 +316,68 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const ImgLevel *__restrict
     L.pts[o] = make_float4(X, Y, Z, 1.0f);
 }
 
+// Batched variant: ONE CTA (32 warps) per image does the whole compaction.  Every warp owns a contiguous range of
+// tiles: pass 1 counts its range, one block-level scan of the 32 range totals, pass 2 re-walks the range and
+// scatters with a running offset -- the same deterministic tile-major order as the three-kernel path, two block
+// barriers in total, no tile_off traffic.  The second walk hits L1/L2.
+__global__ void __launch_bounds__(1024) k_compact_image(const ImgLevel *__restrict__ desc, int w, int h, int tiles_x, int n_tiles,
+                                                        float dmin, float dmax)
+{
+    __shared__ int wsum[33];
+    const ImgLevel &L = desc[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n_tiles + 31) / 32;
+    const int t0 = warp * per, t1 = min(n_tiles, t0 + per);
+    const int lx = lane & 7, ly = lane >> 3;
+    int cnt = 0;
+    for (int t = t0; t < t1; ++t) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        float Z;
+        const bool ok = edge_point_ok(L, tx * kTileW + lx, ty * kTileH + ly, w, h, dmin, dmax, Z);
+        cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0) wsum[warp] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        const int v = wsum[lane];
+        int s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += u;
+        }
+        wsum[lane] = s - v;
+        if (lane == 31) wsum[32] = s;
+    }
+    __syncthreads();
+    int off = wsum[warp];
+    for (int t = t0; t < t1; ++t) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int x = tx * kTileW + lx, y = ty * kTileH + ly;
+        float Z;
+        const bool ok = edge_point_ok(L, x, y, w, h, dmin, dmax, Z);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const int o = off + __popc(m & ((1u << lane) - 1u));
+            if (o < L.pts_cap) {
+                const float X = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)x, L.cx)), L.fx);
+                const float Y = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)y, L.cy)), L.fy);
+                L.pts[o] = make_float4(X, Y, Z, 1.0f);
+            }
+        }
+        off += __popc(m);
+    }
+    if (threadIdx.x == 0) *L.n_pts = min(wsum[32], L.pts_cap);
+}
+
 int launch_compact(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, float dmin, float dmax)
 {
     const int tiles_x = cdiv(w, kTileW), tiles_y = cdiv(h, kTileH), n_tiles = tiles_x * tiles_y;
+    if (n >= 8) {
+        k_compact_image<<<n, 1024, 0, ctx->stream>>>(d_desc, w, h, tiles_x, n_tiles, dmin, dmax);
+        LAUNCH_CHECK(ctx);
+        return REVO_OK;
+    }
     dim3 grid(cdiv(n_tiles, 8), 1, n);
     k_tile_count<<<grid, 256, 0, ctx->stream>>>(d_desc, w, h, tiles_x, n_tiles, dmin, dmax);
     LAUNCH_CHECK(ctx);
