@@ -186,6 +186,7 @@ REVO_API int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, co
 REVO_API int revo_pyr_make_keyframe(revo_ctx *ctx, revo_pyr *pyr);
 REVO_API int revo_pyr_make_keyframe_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs);
 REVO_API int revo_pyr_destroy(revo_ctx *ctx, revo_pyr *pyr);
+REVO_API int revo_pyr_destroy_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs);
 REVO_API int revo_pyr_is_keyframe(const revo_pyr *pyr);
 REVO_API int revo_pyr_level_camera(const revo_pyr *pyr, int lvl, revo_camera *cam_out); /* cameraPyr->at(lvl) */
 REVO_API double revo_pyr_timestamp(const revo_pyr *pyr);

@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "revo_pyr_config_default", "revo_opt_config_default", "revo_tracker_config_default", "revo_ctx_create",
     "revo_ctx_destroy", "revo_ctx_synchronize", "revo_strerror", "revo_last_error", "revo_ctx_stream",
     "revo_ctx_launch_count", "revo_ctx_last_timings", "revo_pyr_create", "revo_pyr_create_batch", "revo_pyr_make_keyframe",
-    "revo_pyr_make_keyframe_batch", "revo_pyr_destroy", "revo_pyr_is_keyframe", "revo_pyr_level_camera",
+    "revo_pyr_make_keyframe_batch", "revo_pyr_destroy", "revo_pyr_destroy_batch", "revo_pyr_is_keyframe", "revo_pyr_level_camera",
     "revo_pyr_timestamp", "revo_pyr_num_edges", "revo_pyr_download", "revo_pyr_upload_level", "revo_eval",
     "revo_track_level", "revo_track", "revo_track_batch", "revo_ctx_set_track_shape", "revo_split_export",
     "revo_split_open", "revo_track_split",
@@ -126,6 +126,7 @@ def load_library():
     lib.revo_pyr_make_keyframe.argtypes = [vp, vp]
     lib.revo_pyr_make_keyframe_batch.argtypes = [vp, i32, C.POINTER(vp)]
     lib.revo_pyr_destroy.argtypes = [vp, vp]
+    lib.revo_pyr_destroy_batch.argtypes = [vp, i32, C.POINTER(vp)]
     lib.revo_pyr_is_keyframe.argtypes = [vp]
     lib.revo_pyr_level_camera.argtypes = [vp, i32, C.POINTER(revo_camera)]
     lib.revo_pyr_num_edges.argtypes = [vp, vp, i32, C.POINTER(i32)]
@@ -481,7 +482,7 @@ class ImgPyramidRGBD:
         self.ctx.check(self.ctx.lib.revo_pyr_upload_level(self.ctx.h, self.h, lvl, _ptr(pts4), n, _ptr(dt), _ptr(opt4)))
 
     def destroy(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None) and getattr(self, "_owned", True):
             self.ctx.lib.revo_pyr_destroy(self.ctx.h, self.h)
         self.h = None
 
@@ -490,6 +491,55 @@ class ImgPyramidRGBD:
             self.destroy()
         except Exception:
             pass
+
+
+class PyramidBatch:
+    """n ImgPyramidRGBD handles created by ONE revo_pyr_create_batch call, kept as a raw handle array: what the
+    throughput path (bench.py, stream.py) passes around instead of n python objects.  ``batch[i]`` gives a
+    non-owning :class:`ImgPyramidRGBD` view for the accessors."""
+
+    __slots__ = ("ctx", "settings", "n", "arr", "campyr", "_alive")
+
+    def __init__(self, ctx: Context, settings: ImgPyramidSettings, rgb, depth, n: int, channels: int = 3, timestamps=None,
+                 cameraPyr: Optional[CameraPyr] = None):
+        self.ctx, self.settings, self.n, self.campyr = ctx, settings, n, cameraPyr
+        cfg, cam = settings._c_cfg(), settings._c_cam()
+        self.arr = (C.c_void_p * n)()
+        ts = None if timestamps is None else np.ascontiguousarray(timestamps, np.float64)
+        ctx.check(ctx.lib.revo_pyr_create_batch(ctx.h, C.byref(cfg), C.byref(cam), n, _ptr(rgb), channels, _ptr(depth), _ptr(ts),
+                                                self.arr))
+        self._alive = True
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i) -> "ImgPyramidRGBD":
+        v = ImgPyramidRGBD(self.ctx, self.settings, self.campyr, None, None, _handle=C.c_void_p(self.arr[i]))
+        v._owned = False
+        return v
+
+    def makeKeyframes(self, ctx: Optional[Context] = None):
+        ctx = ctx or self.ctx
+        ctx.check(ctx.lib.revo_pyr_make_keyframe_batch(ctx.h, self.n, self.arr))
+
+    def destroy(self):
+        if self._alive and getattr(self.ctx, "h", None):
+            self.ctx.lib.revo_pyr_destroy_batch(self.ctx.h, self.n, self.arr)
+        self._alive = False
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def _handles(frames):
+    """(n, ctypes handle array) of a PyramidBatch or a sequence of ImgPyramidRGBD."""
+    if isinstance(frames, PyramidBatch):
+        return frames.n, frames.arr
+    n = len(frames)
+    return n, (C.c_void_p * n)(*[p.h for p in frames])
 
 
 def _R_to_c(R) -> np.ndarray:
@@ -571,12 +621,12 @@ class TrackerNew:
                          trace_cap: int = 0):
         """n independent pairs in one persistent-kernel launch.  Rs: (n,3,3), Ts: (n,3).
         Returns a structured array (TRACK_RESULT_DTYPE; R column-major) and, if trace_cap>0, the LM traces."""
-        n = len(refFrames)
+        n, refs = _handles(refFrames)
+        n2, curs = _handles(currFrames)
+        assert n == n2
         cfg = self._c_cfg()
         Rc = np.ascontiguousarray(np.asarray(Rs, np.float32).reshape(n, 3, 3).transpose(0, 2, 1).reshape(n, 9))
         Tc = np.ascontiguousarray(np.asarray(Ts, np.float32).reshape(n, 3))
-        refs = (C.c_void_p * n)(*[p.h for p in refFrames])
-        curs = (C.c_void_p * n)(*[p.h for p in currFrames])
         out = np.zeros(n, TRACK_RESULT_DTYPE)
         trace = counts = None
         if trace_cap > 0:

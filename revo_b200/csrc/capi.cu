@@ -292,7 +292,7 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
     for (int f = 0; f < n; ++f) {
         revo_pyr *p = new revo_pyr();
         p->slab = slab; p->index_in_slab = f; p->n_levels = NL; p->cfg = *cfg; p->cam0 = *cam0;
-        p->timestamp = timestamps ? timestamps[f] : 0.0; p->kf_mem = nullptr; p->is_keyframe = false;
+        p->timestamp = timestamps ? timestamps[f] : 0.0; p->kf_slab = nullptr; p->is_keyframe = false;
         for (int l = 0; l < NL; ++l) {
             ImgLevel &L = p->lv[l];
             const size_t px = (size_t)g[l].w * g[l].h;
@@ -406,18 +406,36 @@ static void wait_for_build(revo_ctx *ctx, const revo_pyr *p)
     if (p && p->slab && p->slab->ready && p->slab->stream != ctx->stream) cudaStreamWaitEvent(ctx->stream, p->slab->ready, 0);
 }
 
-static int alloc_keyframe_mem(revo_ctx *ctx, revo_pyr *p)
+// One stream-ordered allocation for the keyframe structures (dt 4 B/px + pair structure 16 B/px, all levels) of
+// every pyramid in `ps` that does not have them yet.
+static int alloc_keyframe_mem(revo_ctx *ctx, revo_pyr *const *ps, int n)
 {
-    if (p->kf_mem) return REVO_OK;
-    size_t bytes = 0;
-    for (int l = 0; l < p->n_levels; ++l) bytes += align_up((size_t)p->lv[l].w * p->lv[l].h * 20, 256);
-    REVO_CUDA(ctx, cudaMallocAsync(&p->kf_mem, bytes, ctx->stream));
-    uint8_t *m = (uint8_t *)p->kf_mem;
-    for (int l = 0; l < p->n_levels; ++l) {
-        const size_t px = (size_t)p->lv[l].w * p->lv[l].h;
-        p->lv[l].opt = (uint4 *)m;
-        p->lv[l].dt = (float *)(m + px * 16);
-        m += align_up(px * 20, 256);
+    auto bytes_of = [](const revo_pyr *p) {
+        size_t b = 0;
+        for (int l = 0; l < p->n_levels; ++l) b += align_up((size_t)p->lv[l].w * p->lv[l].h * 20, 256);
+        return b;
+    };
+    size_t total = 0;
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (!ps[i]->kf_slab) { total += bytes_of(ps[i]); ++m; }
+    if (!m) return REVO_OK;
+    KfSlab *ks = new (std::nothrow) KfSlab();
+    if (!ks) return REVO_ERR_INVALID_ARG;
+    ks->mem = nullptr; ks->live = m;
+    cudaError_t e = cudaMallocAsync(&ks->mem, total, ctx->stream);
+    if (e != cudaSuccess) { delete ks; return cuda_fail(ctx, e, "cudaMallocAsync(keyframe)"); }
+    uint8_t *mem = (uint8_t *)ks->mem;
+    for (int i = 0; i < n; ++i) {
+        revo_pyr *p = ps[i];
+        if (p->kf_slab) continue;
+        p->kf_slab = ks;
+        for (int l = 0; l < p->n_levels; ++l) {
+            const size_t px = (size_t)p->lv[l].w * p->lv[l].h;
+            p->lv[l].opt = (uint4 *)mem;
+            p->lv[l].dt = (float *)(mem + px * 16);
+            mem += align_up(px * 20, 256);
+        }
     }
     return REVO_OK;
 }
@@ -436,9 +454,9 @@ int revo_pyr_make_keyframe_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs)
     const int NL = todo[0]->n_levels;
     for (auto *p : todo)
         if (p->n_levels != NL || p->lv[0].w != todo[0]->lv[0].w || p->lv[0].h != todo[0]->lv[0].h) return REVO_ERR_INVALID_ARG;
-    for (auto *p : todo) {
-        wait_for_build(ctx, p);
-        int rc = alloc_keyframe_mem(ctx, p);
+    for (auto *p : todo) wait_for_build(ctx, p);
+    {
+        int rc = alloc_keyframe_mem(ctx, todo.data(), m);
         if (rc) return rc;
     }
     // temporary descriptor tables (with dt/opt set) in a stream-ordered allocation
@@ -461,12 +479,14 @@ int revo_pyr_make_keyframe_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs)
 
 int revo_pyr_make_keyframe(revo_ctx *ctx, revo_pyr *pyr) { return revo_pyr_make_keyframe_batch(ctx, 1, &pyr); }
 
-int revo_pyr_destroy(revo_ctx *ctx, revo_pyr *pyr)
+static void destroy_one(revo_ctx *ctx, revo_pyr *pyr)
 {
-    if (!pyr) return REVO_OK;
-    if (!ctx) return REVO_ERR_INVALID_ARG;
-    cudaSetDevice(ctx->device);
-    if (pyr->kf_mem) cudaFreeAsync(pyr->kf_mem, ctx->stream);
+    if (KfSlab *k = pyr->kf_slab) {
+        if (--k->live == 0) {
+            cudaFreeAsync(k->mem, ctx->stream);
+            delete k;
+        }
+    }
     Slab *s = pyr->slab;
     if (s && --s->live == 0) {
         if (s->ready) cudaEventDestroy(s->ready);
@@ -474,6 +494,24 @@ int revo_pyr_destroy(revo_ctx *ctx, revo_pyr *pyr)
         delete s;
     }
     delete pyr;
+}
+
+int revo_pyr_destroy(revo_ctx *ctx, revo_pyr *pyr)
+{
+    if (!pyr) return REVO_OK;
+    if (!ctx) return REVO_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    destroy_one(ctx, pyr);
+    (void)cudaGetLastError();
+    return REVO_OK;
+}
+
+int revo_pyr_destroy_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs)
+{
+    if (!ctx || (n > 0 && !pyrs)) return REVO_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < n; ++i)
+        if (pyrs[i]) destroy_one(ctx, pyrs[i]);
     (void)cudaGetLastError();
     return REVO_OK;
 }
@@ -574,7 +612,7 @@ int revo_pyr_upload_level(revo_ctx *ctx, revo_pyr *pyr, int lvl, const float *pt
         REVO_CUDA(ctx, cudaMemcpyAsync(L.n_pts, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (dt || opt4) {
-        int rc = alloc_keyframe_mem(ctx, pyr);
+        int rc = alloc_keyframe_mem(ctx, &pyr, 1);
         if (rc) return rc;
         if (dt) REVO_CUDA(ctx, cudaMemcpyAsync(L.dt, dt, px * 4, cudaMemcpyHostToDevice, ctx->stream));
         if (opt4) {

@@ -38,7 +38,8 @@ struct ImgLevel {
 constexpr int kTileW = 8;
 constexpr int kTileH = 4;
 
-struct Slab;  // one device allocation shared by the frames of a batch
+struct Slab;    // one device allocation shared by the frames of a batch
+struct KfSlab;  // one device allocation shared by the keyframe structures promoted together
 
 }  // namespace revo
 
@@ -51,7 +52,7 @@ struct revo_pyr {
     revo_camera cam0;
     double timestamp;
     revo::ImgLevel lv[REVO_MAX_LEVELS];    // host copy of the device descriptors
-    void *kf_mem;                          // keyframe allocation (dt + opt of all levels)
+    revo::KfSlab *kf_slab;                 // keyframe allocation (dt + pair structure of all levels), shared by a batch
     bool is_keyframe;
 };
 
@@ -87,6 +88,11 @@ struct Slab {
     cudaStream_t stream;  // stream the frames were built on
     cudaEvent_t ready;    // recorded on `stream` when the build is complete; other streams wait on it before reading
     ImgLevel *d_desc[REVO_MAX_LEVELS];  // device descriptor tables, n_frames entries each (inside mem)
+};
+
+struct KfSlab {
+    void *mem;
+    int live;
 };
 
 // error helper: records the failure text in ctx and returns REVO_ERR_CUDA

@@ -272,15 +272,18 @@ __device__ __forceinline__ void finish_point(const Proj &P, const uint4 r0, cons
     const float wr = (r <= huber) ? 1.f : __fdividef(huber, r);                    // optimizer.h:159
     const float gx = L.fx * gxi, gy = L.fy * gyi;                                  // optimizer.cpp:119-120
     // calculateWarpUpdate, optimizer.cpp:204-228
-    const float Wx = P.Wx, Wy = P.Wy;
-    const float z = P.iz, z_sqr = P.iz * P.iz;
+    // Same six entries, factored through a = x/z, b = y/z, t = a gx + b gy (12 flops instead of ~30):
+    //   v2 = -(a gx + b gy)/z, v3 = -(b t + gy), v4 = a t + gx, v5 = a gy - b gx.
+    const float z = P.iz;
+    const float a = P.Wx * z, b = P.Wy * z;
+    const float t = a * gx + b * gy;
     float J[6];
     J[0] = z * gx;
     J[1] = z * gy;
-    J[2] = (-Wx * z_sqr) * gx + (-Wy * z_sqr) * gy;
-    J[3] = (-Wx * Wy * z_sqr) * gx + (-(1.0f + Wy * Wy * z_sqr)) * gy;
-    J[4] = (1.0f + Wx * Wx * z_sqr) * gx + (Wx * Wy * z_sqr) * gy;
-    J[5] = (-Wy * z) * gx + (Wx * z) * gy;
+    J[2] = -(t * z);
+    J[3] = -(b * t + gy);
+    J[4] = a * t + gx;
+    J[5] = a * gy - b * gx;
     // LGS6::update, LGSX.h:392-398 (upper triangle only; A is symmetric)
     int s = 0;
 #pragma unroll
@@ -726,19 +729,23 @@ int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const Trac
     if (n_pairs <= 0) return REVO_OK;
     const int T = ctx->track_threads > 0 ? ctx->track_threads : 256;
     // register budget: "dense" = 85 registers/thread (3 CTAs of 256 or 6 of 128 per SM) instead of 128
-    static const bool dense = getenv("REVO_TRACK_DENSE") ? atoi(getenv("REVO_TRACK_DENSE")) != 0 : false;
+    static const int dense_mode = getenv("REVO_TRACK_DENSE") ? atoi(getenv("REVO_TRACK_DENSE")) : 0;
+    const bool dense = dense_mode == 1;
     int C = ctx->track_ctas_per_pair;
     if (C <= 0) {
         // automatic: fill the CTA slots of the chip (SMs x resident CTAs of this shape); a pair alone gets a
         // full portable cluster
-        const int per_sm = (T <= 128 ? 4 : (T <= 256 ? 2 : 1)) + (dense && T <= 256 ? (T <= 128 ? 2 : 1) : 0);
+        const int per_sm = (T <= 128 ? 4 : (T <= 256 ? 2 : 1)) + (dense && T <= 256 ? (T <= 128 ? 2 : 1) : 0) +
+                           (dense_mode == 2 && T <= 128 ? 1 : 0);
         const int slots = ctx->prop.multiProcessorCount * per_sm;
         C = 1;
         while (C < 8 && n_pairs * (C * 2) <= slots) C *= 2;
     }
 #define REVO_TRACK_ARGS ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter
     switch (T) {
-        case 128: return dense ? launch_track_t<128, 6>(REVO_TRACK_ARGS) : launch_track_t<128, 4>(REVO_TRACK_ARGS);
+        case 128:
+            if (dense_mode == 2) return launch_track_t<128, 5>(REVO_TRACK_ARGS);   // 102 registers, 5 CTAs / SM
+            return dense ? launch_track_t<128, 6>(REVO_TRACK_ARGS) : launch_track_t<128, 4>(REVO_TRACK_ARGS);
         case 512: return launch_track_t<512, 1>(REVO_TRACK_ARGS);
         case 1024: return launch_track_t<1024, 1>(REVO_TRACK_ARGS);
         default: return dense ? launch_track_t<256, 3>(REVO_TRACK_ARGS) : launch_track_t<256, 2>(REVO_TRACK_ARGS);

@@ -124,22 +124,20 @@ class CudaBackend:
         self.campyr = api.CameraPyr(settings)
 
     def create(self, bgr, depth, n):
-        return self.api.ImgPyramidRGBD.create_batch(self.build_ctx, self.settings, bgr, depth, n=n, channels=3,
-                                                    cameraPyr=self.campyr, synchronize=False)
+        return self.api.PyramidBatch(self.build_ctx, self.settings, bgr, depth, n, channels=3, cameraPyr=self.campyr)
 
     def wait_created(self):
         if self.build_ctx is not self.ctx:
             self.build_ctx.synchronize()
 
     def make_keyframes(self, handles):
-        self.api.ImgPyramidRGBD.makeKeyframes(self.ctx, handles)
+        handles.makeKeyframes(self.ctx)
 
     def track(self, Rs, Ts, refs, curs):
         out = self.tracker.trackFramesBatch(Rs, Ts, refs, curs)
         n = len(refs)
-        R = out["R"].reshape(n, 3, 3).transpose(0, 2, 1)
+        R = out["R"].reshape(n, 3, 3).transpose(0, 2, 1)   # column-major 9 floats -> (n, 3, 3)
         return dict(R=R, T=out["t"], status=out["status"], n_evals=out["n_evals"], n_pts=out["n_pts"], error=out["error"])
 
     def destroy(self, handles):
-        for h in handles:
-            h.destroy()
+        handles.destroy()
