@@ -223,6 +223,13 @@ REVO_API int revo_track_batch(revo_ctx *ctx, const revo_tracker_config *cfg, int
 /* Launch-shape override for revo_track_batch (0 = automatic): CTAs per pair (cluster size 1,2,4,8,16)
  * and threads per CTA. */
 REVO_API int revo_ctx_set_track_shape(revo_ctx *ctx, int ctas_per_pair, int threads_per_cta);
+/* Tracking engine: 0 = automatic, 1 = one thread-block cluster per pair (lowest single-pair latency; the only
+ * engine of revo_track_split), 2 = chip-wide task queue (every evaluation is cut into chunk tasks that any CTA of the
+ * persistent grid may run; highest batch throughput).  chunk_points: minimum points per task (0 = automatic). */
+REVO_API int revo_ctx_set_track_engine(revo_ctx *ctx, int engine, int chunk_points);
+/* Pre-size the device memory pool: later stream-ordered slab allocations up to `bytes` in total are served
+ * from cached memory instead of the driver (call once before a steady-state stream starts). */
+REVO_API int revo_ctx_reserve(revo_ctx *ctx, size_t bytes);
 
 /* ---- single pair split over several GPUs (BASELINE config 5) ------------- */
 /* One process per GPU.  Every rank builds the same pyramids; rank r evaluates the r-th contiguous

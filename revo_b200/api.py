@@ -92,7 +92,7 @@ EXPORTED_SYMBOLS = [
     "revo_pyr_make_keyframe_batch", "revo_pyr_destroy", "revo_pyr_destroy_batch", "revo_pyr_is_keyframe", "revo_pyr_level_camera",
     "revo_pyr_timestamp", "revo_pyr_num_edges", "revo_pyr_download", "revo_pyr_upload_level", "revo_eval",
     "revo_track_level", "revo_track", "revo_track_batch", "revo_ctx_set_track_shape", "revo_split_export",
-    "revo_split_open", "revo_track_split",
+    "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve",
 ]
 
 
@@ -139,6 +139,8 @@ def load_library():
     lib.revo_track_batch.argtypes = [vp, C.POINTER(revo_tracker_config), i32, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp,
                                      i32, vp]
     lib.revo_ctx_set_track_shape.argtypes = [vp, i32, i32]
+    lib.revo_ctx_set_track_engine.argtypes = [vp, i32, i32]
+    lib.revo_ctx_reserve.argtypes = [vp, C.c_size_t]
     lib.revo_split_export.argtypes = [vp, i32, i32, vp]
     lib.revo_split_open.argtypes = [vp, vp]
     lib.revo_track_split.argtypes = [vp, C.POINTER(revo_tracker_config), vp, vp, vp, vp, C.POINTER(revo_track_result)]
@@ -302,6 +304,14 @@ class Context:
 
     def set_track_shape(self, ctas_per_pair: int = 0, threads_per_cta: int = 0):
         self.check(self.lib.revo_ctx_set_track_shape(self.h, ctas_per_pair, threads_per_cta))
+
+    def set_track_engine(self, engine: int = 0, chunk_points: int = 0):
+        """0 = automatic, 1 = one cluster per pair, 2 = chip-wide task queue (see revo_ctx_set_track_engine)."""
+        self.check(self.lib.revo_ctx_set_track_engine(self.h, engine, chunk_points))
+
+    def reserve(self, nbytes: int):
+        """Pre-size the device memory pool (see revo_ctx_reserve)."""
+        self.check(self.lib.revo_ctx_reserve(self.h, int(nbytes)))
 
     def close(self):
         if getattr(self, "h", None):

@@ -143,7 +143,7 @@ int revo_ctx_create(int device, revo_ctx **out)
     ctx->device = device;
     ctx->launches = 0;
     ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0;
-    ctx->track_ctas_per_pair = 0; ctx->track_threads = 0;
+    ctx->track_ctas_per_pair = 0; ctx->track_threads = 0; ctx->track_engine = 0; ctx->track_chunk_points = 0;
     for (auto &v : ctx->ev_valid) v = false;
     ctx->split_rank = 0; ctx->split_world = 1; ctx->split_local = nullptr; ctx->split_seq = 0;
     for (auto &p : ctx->split_peers) p = nullptr;
@@ -218,6 +218,28 @@ int revo_ctx_set_track_shape(revo_ctx *ctx, int ctas_per_pair, int threads_per_c
         return REVO_ERR_INVALID_ARG;
     ctx->track_ctas_per_pair = ctas_per_pair;
     ctx->track_threads = threads_per_cta;
+    return REVO_OK;
+}
+
+int revo_ctx_set_track_engine(revo_ctx *ctx, int engine, int chunk_points)
+{
+    if (!ctx || engine < 0 || engine > 2 || chunk_points < 0) return REVO_ERR_INVALID_ARG;
+    ctx->track_engine = engine;
+    ctx->track_chunk_points = chunk_points;
+    return REVO_OK;
+}
+
+// Grow the device's stream-ordered memory pool to at least `bytes` of cached, reusable memory now (one allocation +
+// free on the context stream), so that later slab allocations of a steady-state stream never reach the driver.
+int revo_ctx_reserve(revo_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return REVO_ERR_INVALID_ARG;
+    if (bytes == 0) return REVO_OK;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    REVO_CUDA(ctx, cudaMallocAsync(&p, bytes, ctx->stream));
+    REVO_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return REVO_OK;
 }
 
@@ -406,13 +428,13 @@ static void wait_for_build(revo_ctx *ctx, const revo_pyr *p)
     if (p && p->slab && p->slab->ready && p->slab->stream != ctx->stream) cudaStreamWaitEvent(ctx->stream, p->slab->ready, 0);
 }
 
-// One stream-ordered allocation for the keyframe structures (dt 4 B/px + pair structure 16 B/px, all levels) of
+// One stream-ordered allocation for the keyframe structures (dt 4 B/px + quad structure 32 B/px, all levels) of
 // every pyramid in `ps` that does not have them yet.
 static int alloc_keyframe_mem(revo_ctx *ctx, revo_pyr *const *ps, int n)
 {
     auto bytes_of = [](const revo_pyr *p) {
         size_t b = 0;
-        for (int l = 0; l < p->n_levels; ++l) b += align_up((size_t)p->lv[l].w * p->lv[l].h * 20, 256);
+        for (int l = 0; l < p->n_levels; ++l) b += align_up((size_t)p->lv[l].w * p->lv[l].h * 36, 256);
         return b;
     };
     size_t total = 0;
@@ -433,8 +455,8 @@ static int alloc_keyframe_mem(revo_ctx *ctx, revo_pyr *const *ps, int n)
         for (int l = 0; l < p->n_levels; ++l) {
             const size_t px = (size_t)p->lv[l].w * p->lv[l].h;
             p->lv[l].opt = (uint4 *)mem;
-            p->lv[l].dt = (float *)(mem + px * 16);
-            mem += align_up(px * 20, 256);
+            p->lv[l].dt = (float *)(mem + px * 32);
+            mem += align_up(px * 36, 256);
         }
     }
     return REVO_OK;
@@ -676,20 +698,32 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     const size_t b_tr = align_up(sizeof(revo_trace_entry) * (size_t)trace_cap * n, 256);
     const size_t b_tc = align_up(sizeof(int) * (size_t)n, 256);
     uint8_t *ws = nullptr;
-    REVO_CUDA(ctx, cudaMallocAsync((void **)&ws, b_pairs + b_res + b_rec + b_tr + b_tc + 256, ctx->stream));
+    // engine: one cluster per pair (track.cu; measured faster at every batch size, scratch/track_bench.py) unless the
+    // caller / REVO_TRACK_ENGINE asks for the task queue (track_queue.cu); a pair split over several GPUs always uses
+    // the cluster engine (the peer mailboxes live there)
+    const int env_engine = getenv("REVO_TRACK_ENGINE") ? atoi(getenv("REVO_TRACK_ENGINE")) : 0;
+    int engine = ctx->track_engine ? ctx->track_engine : env_engine;
+    if (prm.split_world > 1) engine = 1;
+    if (engine != 2) engine = 1;
+    const size_t b_q = engine == 2 ? align_up(track_queue_workspace_bytes(n, 8 * ctx->prop.multiProcessorCount, nullptr), 256) : 0;
+    REVO_CUDA(ctx, cudaMallocAsync((void **)&ws, b_pairs + b_res + b_rec + b_tr + b_tc + 256 + b_q, ctx->stream));
     PairDesc *d_pairs = (PairDesc *)ws;
     revo_track_result *d_res = (revo_track_result *)(ws + b_pairs);
     double *d_rec = (double *)(ws + b_pairs + b_res);
     revo_trace_entry *d_tr = trace_cap ? (revo_trace_entry *)(ws + b_pairs + b_res + b_rec) : nullptr;
     int *d_tc = (int *)(ws + b_pairs + b_res + b_rec + b_tr);
     int *d_wc = (int *)(ws + b_pairs + b_res + b_rec + b_tr + b_tc);
+    uint8_t *d_q = ws + b_pairs + b_res + b_rec + b_tr + b_tc + 256;
     int rc = REVO_OK;
     cudaError_t e = cudaMemcpyAsync(d_pairs, host.data(), sizeof(PairDesc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_res, 0, b_res + b_rec, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_wc, 0, 256, ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "track upload");
     cudaEventRecord(ctx->ev[4], ctx->stream);
-    if (!rc) rc = launch_track(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);
+    if (!rc) {
+        if (engine == 2) rc = launch_track_queue(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_q, b_q);
+        else rc = launch_track(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);
+    }
     cudaEventRecord(ctx->ev[5], ctx->stream);
     ctx->ev_valid[2] = true;
     if (!rc && results) {
@@ -708,10 +742,34 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     }
     unsigned long long prof[4] = {0, 0, 0, 0};
     const bool want_prof = getenv("REVO_TRACK_PROF") != nullptr;
-    if (!rc && want_prof) cudaMemcpyAsync(prof, d_wc + 2, sizeof(prof), cudaMemcpyDeviceToHost, ctx->stream);
+    int q_ctl[4] = {0, 0, 0, 0};   // head, tail, pairs_done, abort of the queue engine
+    if (!rc && engine == 2) cudaMemcpyAsync(q_ctl, d_q, sizeof(q_ctl), cudaMemcpyDeviceToHost, ctx->stream);
+    std::vector<unsigned long long> q_prof;
+    if (!rc && engine == 2 && want_prof) {
+        q_prof.resize(9 + (size_t)n);
+        cudaMemcpyAsync(q_prof.data(), d_q + 16, q_prof.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (!rc && want_prof && engine == 1) cudaMemcpyAsync(prof, d_wc + 2, sizeof(prof), cudaMemcpyDeviceToHost, ctx->stream);
     cudaFreeAsync(ws, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess && !rc) rc = cuda_fail(ctx, e, "track kernel");
+    if (!rc && engine == 2 && (q_ctl[3] != 0 || q_ctl[2] != n)) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "track queue watchdog: abort=%d pairs_done=%d/%d head=%u tail=%u", q_ctl[3], q_ctl[2], n,
+                 (unsigned)q_ctl[0], (unsigned)q_ctl[1]);
+        ctx->last_error = buf;
+        rc = REVO_ERR_CUDA;
+    }
+    if (!rc && want_prof && engine == 2) {
+        const unsigned long long *st = q_prof.data() + 1;
+        std::vector<unsigned long long> fin(q_prof.begin() + 9, q_prof.end());
+        std::sort(fin.begin(), fin.end());
+        const double nt = (double)std::max<unsigned long long>(st[4], 1), nl = (double)std::max<unsigned long long>(st[5], 1);
+        fprintf(stderr, "[k_track_queue prof] pairs %d ctas %llu tasks %llu evals %llu | cycles/task: pop %.0f gather %.0f partial %.0f | "
+                        "cycles/last-arrival %.0f | pair finish us: min %.0f p25 %.0f p50 %.0f p75 %.0f p90 %.0f max %.0f\n",
+                n, st[6], st[4], st[5], st[0] / nt, st[1] / nt, st[2] / nt, st[3] / nl, fin.front() * 1e-3, fin[fin.size() / 4] * 1e-3,
+                fin[fin.size() / 2] * 1e-3, fin[fin.size() * 3 / 4] * 1e-3, fin[fin.size() * 9 / 10] * 1e-3, fin.back() * 1e-3);
+    }
     if (!rc && want_prof && prof[3])
         fprintf(stderr, "[k_track prof] pairs %d evals %llu  cycles/eval: gather %.0f reduce %.0f serial+sync %.0f\n", n, prof[3],
                 (double)prof[0] / prof[3], (double)prof[1] / prof[3], (double)prof[2] / prof[3]);

@@ -26,7 +26,7 @@ struct ImgLevel {
     int *labels;          // scratch h*w int32: union-find labels (Canny) / column distances (EDT)
     uint8_t *flags;       // scratch w0*h0 bytes per frame: integer patch counters of the histogram (K5)
     float *dt;            // dtPyr[l]         h*w   (keyframes, else nullptr)
-    uint4 *opt;           // optimizationStructure[l] in the device PAIR layout (see k_opt_struct), h*w (keyframes)
+    uint4 *opt;           // optimizationStructure[l] in the device QUAD layout (see k_opt_struct), 2 x uint4 per pixel (keyframes)
     int w, h;
     int pts_cap;
     int patch;            // distPatchSizes[l]
@@ -69,6 +69,8 @@ struct revo_ctx {
     size_t pinned_bytes;
     int track_ctas_per_pair;
     int track_threads;
+    int track_engine;        // 0 = automatic, 1 = one cluster per pair (track.cu), 2 = task queue (track_queue.cu)
+    int track_chunk_points;  // queue engine: minimum points per task (0 = automatic)
     cudaEvent_t ev[6];      // pyramid begin/end, keyframe begin/end, track kernel begin/end
     bool ev_valid[3];
     // split mode (multi-GPU single pair)
@@ -131,7 +133,7 @@ int launch_edges3d_reference_order(revo_ctx *ctx, const ImgLevel *d_desc_one, in
 struct LevelIn {
     const float4 *pts;
     const int *n_pts;
-    const uint4 *opt;    // pair layout: {dt(x), dt(x+1), snorm16 gx|gy (x), snorm16 gx|gy (x+1)}
+    const uint4 *opt;    // quad layout, 32 B per pixel: dt of (x,y),(x+1,y),(x,y+1),(x+1,y+1) | snorm16 gx|gy of the same four
     float fx, fy, cx, cy;
     int w, h;
 };
@@ -155,5 +157,11 @@ struct TrackParams {
 int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm,
                  revo_track_result *d_results, double *d_records, revo_trace_entry *d_trace, int *d_trace_counts,
                  int *d_work_counter);
+
+// ---- track_queue.cu ----------------------------------------------------------
+// Task-queue engine: device workspace size for n_pairs (ring + pair states + partial tables) and the launcher.
+size_t track_queue_workspace_bytes(int n_pairs, int grid_cap, unsigned *cap_out);
+int launch_track_queue(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, revo_track_result *d_results,
+                       double *d_records, revo_trace_entry *d_trace, int *d_trace_counts, void *d_ws, size_t ws_bytes);
 
 }  // namespace revo

@@ -506,10 +506,17 @@ __device__ __forceinline__ uint32_t pack_grad(float gx, float gy)
     return ((uint32_t)qx & 0xffffu) | ((uint32_t)qy << 16);
 }
 
-// K8 (device layout): one 16-byte record per pixel holding the texel PAIR (x, y), (x+1, y) the bilinear fetch of
-// the tracker needs from one row: {dt(x), dt(x+1), snorm16 gx,gy (x), snorm16 gx,gy (x+1)}.  A residual evaluation
-// then costs two 16-byte gathers per edge point instead of four; dt stays float32, only the Jacobian direction is
-// quantised (1.5e-5 absolute).  The reference's float4 array is produced on demand for the accessor (k_opt_struct_f4).
+// K8 (device layout): one 32-byte QUAD record per pixel (x,y) holding everything the bilinear fetch of the tracker
+// needs for a point that projects into [x,x+1) x [y,y+1): {dt(x,y), dt(x+1,y), dt(x,y+1), dt(x+1,y+1)} as float32 and
+// the snorm16 (gx,gy) of the same four texels.  A residual evaluation then costs ONE 256-bit gather per edge point
+// instead of four 16-byte texel fetches; dt stays float32, only the Jacobian direction is quantised (1.5e-5 absolute).
+// The reference's float4 array is produced on demand for the accessor (k_opt_struct_f4).
+__device__ __forceinline__ void store_quad(uint4 *__restrict__ out, size_t i, const float4 a, const float4 b, const float4 c, const float4 d)
+{
+    out[2 * i] = make_uint4(__float_as_uint(a.z), __float_as_uint(b.z), __float_as_uint(c.z), __float_as_uint(d.z));
+    out[2 * i + 1] = make_uint4(pack_grad(a.x, a.y), pack_grad(b.x, b.y), pack_grad(c.x, c.y), pack_grad(d.x, d.y));
+}
+
 __global__ void __launch_bounds__(256) k_opt_struct(const ImgLevel *__restrict__ desc, int w, int h)
 {
     const int f = blockIdx.z;
@@ -517,9 +524,12 @@ __global__ void __launch_bounds__(256) k_opt_struct(const ImgLevel *__restrict__
     const size_t n = (size_t)w * h;
     if (i >= n) return;
     const float *__restrict__ dt = desc[f].dt;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 a = opt_texel(dt, i, w, h);
-    const float4 b = (i + 1 < n) ? opt_texel(dt, i + 1, w, h) : make_float4(0.f, 0.f, 0.f, 0.f);
-    desc[f].opt[i] = make_uint4(__float_as_uint(a.z), __float_as_uint(b.z), pack_grad(a.x, a.y), pack_grad(b.x, b.y));
+    const float4 b = (i + 1 < n) ? opt_texel(dt, i + 1, w, h) : z;
+    const float4 c = (i + w < n) ? opt_texel(dt, i + w, w, h) : z;
+    const float4 d = (i + w + 1 < n) ? opt_texel(dt, i + w + 1, w, h) : z;
+    store_quad(desc[f].opt, i, a, b, c, d);
 }
 
 // the reference layout, for returnOptimizationStructure(): out[i] = {gx, gy, dt, 0}
@@ -530,15 +540,18 @@ __global__ void __launch_bounds__(256) k_opt_struct_f4(const float *__restrict__
     out[i] = opt_texel(dt, i, w, h);
 }
 
-// test hook: caller-provided float4 structure -> device pair layout
+// test hook: caller-provided float4 structure -> device quad layout
 __global__ void __launch_bounds__(256) k_opt_pack_from_f4(const float4 *__restrict__ in, int w, int h, uint4 *__restrict__ out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n = (size_t)w * h;
     if (i >= n) return;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 a = in[i];
-    const float4 b = (i + 1 < n) ? in[i + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-    out[i] = make_uint4(__float_as_uint(a.z), __float_as_uint(b.z), pack_grad(a.x, a.y), pack_grad(b.x, b.y));
+    const float4 b = (i + 1 < n) ? in[i + 1] : z;
+    const float4 c = (i + w < n) ? in[i + w] : z;
+    const float4 d = (i + w + 1 < n) ? in[i + w + 1] : z;
+    store_quad(out, i, a, b, c, d);
 }
 
 int launch_opt_struct_f4(revo_ctx *ctx, const float *d_dt, int w, int h, float4 *d_out)

@@ -16,6 +16,14 @@ from conftest import rot_angle, synth_pair
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["queue", "cluster"], autouse=True)
+def engine(request, ctx):
+    """Every test of this file runs on both tracking engines (task queue: track_queue.cu, cluster per pair: track.cu)."""
+    ctx.set_track_engine(2 if request.param == "queue" else 1, 0)
+    yield request.param
+    ctx.set_track_engine(0, 0)
+
+
 def _settings(cam, n_levels):
     from revo_b200 import api
 
