@@ -265,42 +265,46 @@ def main():
 
     build_ctx = api.Context(local_rank)    # second stream: upload + pyramid build of frame k+1 overlap tracking of frame k
 
-    def timed_run(src_bgr, src_depth, sample_clocks, pipelined=False):
+    def timed_run(src_bgr, src_depth, sample_clocks, pipelined=False, K=K):
         be = CudaBackend(ctx, settings, build_ctx=build_ctx if pipelined else None)
         st = StreamTracker(be, B, args.kf_interval)
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
             sampler.start()     # sampled from the warm-up on: the GPU is under the same load throughout
         st.start(src_bgr[0], src_depth[0])
-        if pipelined:
+        if pipelined:   # two frames in flight: upload of k+2 | build of k+1 | track of k
             st.prefetch(src_bgr[fidx(1)], src_depth[fidx(1)])
+            st.prefetch(src_bgr[fidx(2)], src_depth[fidx(2)])
         for i in range(1, W + 1):
             if pipelined:
-                st.step_pipelined(src_bgr[fidx(i + 1)], src_depth[fidx(i + 1)])
+                st.step_pipelined(src_bgr[fidx(i + 2)], src_depth[fidx(i + 2)])
             else:
                 st.step(src_bgr[fidx(i)], src_depth[fidx(i)])
         ctx.synchronize()
         build_ctx.synchronize()
         ev0, pe0, l0 = st.total_evals, st.total_point_evals, ctx.launch_count + build_ctx.launch_count
         k9_ms = pyr_ms = kf_ms = 0.0
+        step_wall = []
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(ext_stream)
         for i in range(W + 1, W + 1 + K):
+            ts = time.perf_counter()
             if pipelined:
-                st.step_pipelined(src_bgr[fidx(i + 1)], src_depth[fidx(i + 1)])   # the last prefetch is part of the cost
+                st.step_pipelined(src_bgr[fidx(i + 2)], src_depth[fidx(i + 2)])   # the prefetches beyond the last step are part of the cost
             else:
                 st.step(src_bgr[fidx(i)], src_depth[fidx(i)])
-            p, kf, k9 = ctx.last_timings()
-            if pipelined:
-                p = build_ctx.last_timings()[0]
-            pyr_ms += p
-            k9_ms += k9
-            if st.frame % args.kf_interval == 0:
-                kf_ms += kf
+            if not pipelined:     # per-phase CUDA-event times: only in the serial pass (querying them synchronises the streams)
+                p, kf, k9 = ctx.last_timings()
+                pyr_ms += p
+                k9_ms += k9
+                if st.frame % args.kf_interval == 0:
+                    kf_ms += kf
+            step_wall.append((time.perf_counter() - ts) * 1e3)
+        build_ctx.synchronize()     # the uploads / builds enqueued by the last steps are part of the timed region
         e1.record(ext_stream)
-        build_ctx.synchronize()
+        upload_ms = build_ctx.last_upload_ms() if pipelined else ctx.last_upload_ms()
         barrier()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
@@ -310,7 +314,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         res = dict(ms=ms, wall=wall, evals=st.total_evals - ev0, point_evals=st.total_point_evals - pe0,
-                   launches=ctx.launch_count + build_ctx.launch_count - l0, k9_ms=k9_ms, pyr_ms=pyr_ms, kf_ms=kf_ms, T_w_c=st.T_w_c.copy(), clocks=clocks,
+                   launches=ctx.launch_count + build_ctx.launch_count - l0, step_wall=step_wall, upload_ms=upload_ms, k9_ms=k9_ms, pyr_ms=pyr_ms, kf_ms=kf_ms, T_w_c=st.T_w_c.copy(), clocks=clocks,
                    n_pts=st.last["n_pts"].mean(axis=0).tolist(), n_evals=st.last["n_evals"].mean(axis=0).tolist())
         st.close()
         return res
@@ -321,12 +325,30 @@ def main():
             sys.stderr.flush()
 
     note(f"inputs rendered: {n_frames} frames x {B} streams")
-    dev_run = timed_run(bgr_d, depth_d, sample_clocks=True)       # inputs resident in HBM
-    note("device-resident run done")
+    # inputs resident in HBM; the same two-stream pipeline as the end-to-end run (build of frame k+1 overlaps tracking of k)
+    dev_run = timed_run(bgr_d, depth_d, sample_clocks=True, pipelined=not args.no_pipeline)
+    note("device-resident run done; host ms per step: " + " ".join(f"{x:.2f}" for x in dev_run["step_wall"]))
     # pinned host inputs, H2D inside the timed region; the upload + pyramid build of frame k+1 run on a second stream
     # while frame k is tracked (same public API, two contexts)
     host_run = timed_run(bgr_h, depth_h, sample_clocks=False, pipelined=not args.no_pipeline)
-    note("host-input (e2e) run done")
+    note("host-input (e2e) run done; host ms per step: " + " ".join(f"{x:.2f}" for x in host_run["step_wall"]))
+    # kernel-level numbers (phase times, roofline of k_track) from a pass in which nothing else runs beside the kernel being
+    # timed: same workload, device-resident, one stream, no overlap
+    iso_run = timed_run(bgr_d, depth_d, sample_clocks=False, pipelined=False, K=min(K, 10))
+    K_iso = min(K, 10)
+    note("isolated-kernel pass done")
+
+    # what the host link can do: one pinned -> device copy of a batch of bgr frames, timed alone
+    tmp = torch.empty_like(bgr_d[0])
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tmp.copy_(bgr_h[0], non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record()
+    tmp.copy_(bgr_h[1], non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = bgr_h[1].numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del tmp
 
     frames_rank = K * B
     tot = torch.tensor([float(dev_run["evals"]), float(dev_run["point_evals"]), float(dev_run["launches"])], device="cuda",
@@ -345,8 +367,8 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    k9_s = dev_run["k9_ms"] * 1e-3
-    achieved = 60.0 * dev_run["point_evals"] / k9_s / 1e9 if k9_s > 0 else 0.0
+    k9_s = iso_run["k9_ms"] * 1e-3
+    achieved = 60.0 * iso_run["point_evals"] / k9_s / 1e9 if k9_s > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k_track_traffic.json")
     if os.path.exists(tp):
@@ -370,17 +392,22 @@ def main():
                    "l2_policy": f"inputs larger than L2: every step touches {B} new frames "
                                 f"({B * w * h * 7 / 1e6:.0f} MB of bgr+depth) plus {B} keyframe structures"},
         "gn_iters_per_sec": evals_all / (dev_run["ms"] * 1e-3),
-        "gn_iters_per_sec_tracking_kernel": dev_run["evals"] / k9_s if k9_s > 0 else None,
+        "gn_iters_per_sec_tracking_kernel": iso_run["evals"] / k9_s if k9_s > 0 else None,
         "gpu_launches": int(launches_all),
-        "phase_ms_per_step": {"pyramid": dev_run["pyr_ms"] / K, "keyframe": dev_run["kf_ms"] / K, "track_kernel": dev_run["k9_ms"] / K,
-                              "whole_step": dev_run["ms"] / K},
+        "phase_ms_per_step": {"pyramid": iso_run["pyr_ms"] / K_iso, "keyframe": iso_run["kf_ms"] / K_iso,
+                              "track_kernel": iso_run["k9_ms"] / K_iso, "whole_step_serial": iso_run["ms"] / K_iso,
+                              "whole_step_pipelined": dev_run["ms"] / K,
+                              "note": "phases timed with CUDA events in a separate pass without stream overlap; the value run "
+                                      "overlaps the pyramid build of frame k+1 with the tracking of frame k on two streams"},
         "mean_edge_points_per_level": dev_run["n_pts"], "mean_evals_per_level": dev_run["n_evals"],
         "pose_error_vs_ground_truth": {"rot_rad": er, "trans_m": et},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * w * h * 7), "d2h_bytes_per_step": int(B * 128),
-                "ms_per_step": host_run["ms"] / K},
+                "ms_per_step": host_run["ms"] / K, "h2d_link_gbs_measured": h2d_gbs, "upload_ms_last_batch": host_run["upload_ms"],
+                "h2d_floor_ms_per_step": B * w * h * 7 / (h2d_gbs * 1e9) * 1e3},
         "roofline": {"kernel": "k_track (persistent residual/Jacobian/6x6 reduce + LM)", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                     "traffic": traffic, "algorithmic_bytes": 60.0 * dev_run["point_evals"] / K,
+                     "traffic": traffic, "algorithmic_bytes": 60.0 * iso_run["point_evals"] / K_iso,
+                     "timing": "CUDA events around the kernel on its launch stream, pass without concurrent kernels",
                      "note": "algorithmic bytes = 60 B x sum(n_pts x n_evals); keyframe structures of a pair stay L2-resident "
                              "across its LM iterations, so achieved may exceed DRAM traffic"},
         "clocks": dev_run["clocks"],
@@ -400,7 +427,7 @@ def main():
                                           f"cv2 {cv2.__version__} ({cv2.getNumThreads()} threads) + C port of the reference loops/tracker"}
     print(json.dumps(line))
     sys.stderr.write(f"[bench] {value:.0f} frames/s (e2e {e2e:.0f}), {line['gn_iters_per_sec']:.0f} GN-iters/s, step {dev_run['ms'] / K:.2f} ms = "
-                     f"pyr {dev_run['pyr_ms'] / K:.2f} + kf {dev_run['kf_ms'] / K:.2f} + track {dev_run['k9_ms'] / K:.2f} ms, "
+                     f"pyr {iso_run['pyr_ms'] / K_iso:.2f} + kf {iso_run['kf_ms'] / K_iso:.2f} + track {iso_run['k9_ms'] / K_iso:.2f} ms (serial {iso_run['ms'] / K_iso:.2f}), "
                      f"k_track {achieved:.0f} GB/s algorithmic = {achieved / peak:.3f} of HBM peak\n")
     if dist is not None:
         dist.destroy_process_group()

@@ -169,6 +169,8 @@ REVO_API uint64_t revo_ctx_launch_count(revo_ctx *ctx);
 /* Device time (CUDA events on the context stream) of the most recent completed pyramid-construction,
  * keyframe-promotion and tracking-kernel launches, in milliseconds (0 if none yet). Synchronises. */
 REVO_API int revo_ctx_last_timings(revo_ctx *ctx, float *pyramid_ms, float *keyframe_ms, float *track_kernel_ms);
+/* Device time of the most recent host-to-device upload of a frame batch (CUDA events on the copy stream). Synchronises it. */
+REVO_API int revo_ctx_last_upload_ms(revo_ctx *ctx, float *upload_ms);
 
 /* ---- ImgPyramidRGBD ------------------------------------------------------ */
 /* ImgPyramidRGBD(settings, camPyr, rgb, depth, ts) -- imgpyramidrgbd.cpp:43-96.

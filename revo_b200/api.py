@@ -92,7 +92,7 @@ EXPORTED_SYMBOLS = [
     "revo_pyr_make_keyframe_batch", "revo_pyr_destroy", "revo_pyr_destroy_batch", "revo_pyr_is_keyframe", "revo_pyr_level_camera",
     "revo_pyr_timestamp", "revo_pyr_num_edges", "revo_pyr_download", "revo_pyr_upload_level", "revo_eval",
     "revo_track_level", "revo_track", "revo_track_batch", "revo_ctx_set_track_shape", "revo_split_export",
-    "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve",
+    "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve", "revo_ctx_last_upload_ms",
 ]
 
 
@@ -141,6 +141,7 @@ def load_library():
     lib.revo_ctx_set_track_shape.argtypes = [vp, i32, i32]
     lib.revo_ctx_set_track_engine.argtypes = [vp, i32, i32]
     lib.revo_ctx_reserve.argtypes = [vp, C.c_size_t]
+    lib.revo_ctx_last_upload_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.revo_split_export.argtypes = [vp, i32, i32, vp]
     lib.revo_split_open.argtypes = [vp, vp]
     lib.revo_track_split.argtypes = [vp, C.POINTER(revo_tracker_config), vp, vp, vp, vp, C.POINTER(revo_track_result)]
@@ -301,6 +302,11 @@ class Context:
         a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
         self.check(self.lib.revo_ctx_last_timings(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def last_upload_ms(self) -> float:
+        a = C.c_float(0)
+        self.check(self.lib.revo_ctx_last_upload_ms(self.h, C.byref(a)))
+        return a.value
 
     def set_track_shape(self, ctas_per_pair: int = 0, threads_per_cta: int = 0):
         self.check(self.lib.revo_ctx_set_track_shape(self.h, ctas_per_pair, threads_per_cta))
@@ -532,9 +538,13 @@ class PyramidBatch:
         ctx = ctx or self.ctx
         ctx.check(ctx.lib.revo_pyr_make_keyframe_batch(ctx.h, self.n, self.arr))
 
-    def destroy(self):
-        if self._alive and getattr(self.ctx, "h", None):
-            self.ctx.lib.revo_pyr_destroy_batch(self.ctx.h, self.n, self.arr)
+    def destroy(self, ctx: Optional[Context] = None):
+        """Release the batch.  ctx: the context whose stream orders the release (default: the creating context).  A
+        pipeline that builds on one context and tracks on another should release on the TRACKING context: its stream is
+        past the last use, so the memory is immediately reusable by the upload of a later batch."""
+        ctx = ctx or self.ctx
+        if self._alive and getattr(ctx, "h", None):
+            ctx.lib.revo_pyr_destroy_batch(ctx.h, self.n, self.arr)
         self._alive = False
 
     def __del__(self):

@@ -16,6 +16,7 @@
 // The result is the unique fixed point of OpenCV's hysteresis (every 8-connected component of candidates that
 // contains a strong pixel), independent of thread order.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "internal.h"
@@ -476,9 +477,425 @@ __global__ void __launch_bounds__(256) k_hist_finalize(const ImgLevel *__restric
     }
 }
 
+// ===================================================================================================================
+// Canny v4: bit-mask pipeline (default).  Same result as the tile / union-find path above, bit for bit:
+//  (1) k_canny_nms : streaming, no shared memory.  A lane owns 4 pixel columns and slides down a strip of rows keeping
+//      three rows of squared gradient magnitudes in registers; the 3x3 Sobel of a pixel is five DP4A (u8 x s8 dot
+//      products) on byte-aligned windows built with PRMT from the lane's own 32-bit load and its neighbours' (two
+//      shuffles); non-maximum suppression with OpenCV's TG22 fixed-point sector test; the result is TWO BITS per pixel,
+//      written as two bit masks (candidates C, strong S; 64 pixels per 64-bit word, LSB = leftmost) into the frame's
+//      label plane: 1/16 of the bytes of a class map, and the form the hysteresis wants.
+//  (2) k_canny_hyst: one CTA per image.  Hysteresis = S <- every candidate 8-connected to a strong pixel.  A warp owns
+//      a band of rows, a lane owns a 64-bit word of a row; a row is flooded in O(1) word operations with the carry
+//      trick  up = (((C + S) ^ C) & C) | S  (and its bit-reversed twin for the other direction), lanes exchange their
+//      edge bits by shuffle; sweeping a band down and up propagates any distance inside the band, bands exchange
+//      boundary rows between sweeps (block barrier) until no bit changes: exact, typically 2-4 sweeps.
+//  (3) k_canny_expand: S -> edges / edges_orig bytes (0 / 255) + the integer patch counters of the histogram.
+// ===================================================================================================================
+constexpr int NMS_RS = 33;      // output rows per warp strip (a multiple of the 3-fold register rotation)
+constexpr int NMS_PX = 4;       // pixels per lane
+
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ unsigned rep_byte(unsigned b) { return (b & 0xffu) * 0x01010101u; }
+
+// Requires w % 4 == 0, w >= 8 and a 4-byte aligned gray plane (launch_canny checks).
+__global__ void __launch_bounds__(128) k_canny_nms(const ImgLevel *__restrict__ desc, int w, int h, int low, int high, int wp32)
+{
+    const int f = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y0 = (blockIdx.y * 4 + warp) * NMS_RS;
+    if (y0 >= h) return;
+    const int xw = blockIdx.x * 32 * NMS_PX;          // first column of the warp
+    const int x = xw + lane * NMS_PX;                 // first column of the lane
+    const uint8_t *__restrict__ g = desc[f].gray;
+    unsigned *__restrict__ maskC = (unsigned *)desc[f].labels;
+    unsigned *__restrict__ maskS = maskC + (size_t)wp32 * h;
+    constexpr int W_DX1 = 0x000100FF, W_DX2 = 0x000200FE, W_DYM = 0x00FFFEFF, W_DYP = 0x00010201;
+
+    // per-lane constants of the BORDER_REPLICATE column handling
+    const bool beyond = x >= w;                        // lane entirely right of the image: replicates column w-1
+    const int xl = beyond ? w - 4 : x;                 // column of the word this lane loads
+    const bool halo_l_in = x >= 4, halo_r_in = x + 4 < w;
+    // magnitude columns x-1 .. x+4 that lie inside the image (magnitudes outside are 0), as AND masks
+    int cm[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) cm[c] = (x - 1 + c >= 0 && x - 1 + c < w) ? -1 : 0;
+    unsigned own_px = 0;                               // the lane's own pixels inside the image (4 bits)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) own_px |= (x + k < w ? 1u : 0u) << k;
+    const int wi = (xw >> 5) + (lane >> 3);
+    const bool writer = (lane & 7) == 0 && wi < wp32;
+
+    // A gray row is fetched one step ahead of its use (raw own word + the halo word of lanes 0 / 31), then turned into
+    // aligned windows: aw[c] = bytes of columns (x-2+c .. x+1+c), c = 0..5  <->  pixel column x-1+c
+    const bool edge_lane = lane == 0 || lane == 31;
+    const int xh = lane == 0 ? x - 4 : x + 4;          // column of the halo word an edge lane loads (if inside the image)
+    const bool halo_in = lane == 0 ? halo_l_in : halo_r_in;
+    auto issue_row = [&](int y, unsigned &v, unsigned &hv) {
+        const uint8_t *row = g + (size_t)min(max(y, 0), h - 1) * w;
+        v = __ldg((const unsigned *)(row + xl));
+        hv = 0;
+        if (edge_lane && halo_in) hv = __ldg((const unsigned *)(row + xh));
+    };
+    auto finish_row = [&](unsigned v, unsigned hv, unsigned (&aw)[6]) {
+        const unsigned w1 = beyond ? rep_byte(v >> 24) : v;
+        unsigned w0 = __shfl_up_sync(0xffffffffu, w1, 1), w2 = __shfl_down_sync(0xffffffffu, w1, 1);
+        if (lane == 0) w0 = halo_l_in ? hv : rep_byte(w1);
+        if (lane == 31) w2 = halo_r_in ? hv : rep_byte(w1 >> 24);
+        aw[0] = __byte_perm(w0, w1, 0x5432);
+        aw[1] = __byte_perm(w0, w1, 0x6543);
+        aw[2] = w1;
+        aw[3] = __byte_perm(w1, w2, 0x4321);
+        aw[4] = __byte_perm(w1, w2, 0x5432);
+        aw[5] = __byte_perm(w1, w2, 0x6543);
+    };
+    auto load_row = [&](int y, unsigned (&aw)[6]) {
+        unsigned v, hv;
+        issue_row(y, v, hv);
+        finish_row(v, hv, aw);
+    };
+    // squared magnitude of row ym for the 6 columns x-1..x+4 (0 outside the image) and dx, dy of the lane's own 4
+    auto mag_row = [&](int ym, const unsigned (&r0)[6], const unsigned (&r1)[6], const unsigned (&r2)[6], int (&mg)[6], int (&dxo)[4],
+                       int (&dyo)[4]) {
+        const int rowm = (ym >= 0 && ym < h) ? -1 : 0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int dx = dp4a_us(r0[c], W_DX1, dp4a_us(r1[c], W_DX2, dp4a_us(r2[c], W_DX1, 0)));
+            const int dy = dp4a_us(r2[c], W_DYP, dp4a_us(r0[c], W_DYM, 0));
+            mg[c] = (dx * dx + dy * dy) & cm[c] & rowm;
+            if (c >= 1 && c <= 4) { dxo[c - 1] = dx; dyo[c - 1] = dy; }
+        }
+    };
+    // non-maximum suppression of row yn (middle magnitudes mm, rows above / below mu / md) -> 4 candidate / strong bits
+    auto nms_row = [&](int yn, const int (&mu)[6], const int (&mm)[6], const int (&md)[6], const int (&dxs)[4], const int (&dys)[4]) {
+        if (yn >= h) return;                              // warp-uniform
+        unsigned cb = 0, sb = 0;
+        const int mx = max(max(mm[1], mm[2]), max(mm[3], mm[4]));
+        if (__any_sync(0xffffffffu, mx > low)) {          // most 128-pixel row segments of a real image hold no candidate
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int m = mm[k + 1];
+                const int xs = dxs[k], ys = dys[k];
+                const int ax = abs(xs), ay = abs(ys) << 15;
+                const int tg22x = ax * 13573;
+                const int tg67x = tg22x + (ax << 16);
+                const bool horiz = ay < tg22x, vert = ay > tg67x;
+                const bool neg = (xs ^ ys) < 0;           // s = -1: compare (y-1, x+1) and (y+1, x-1)
+                const int a = horiz ? mm[k] : (vert ? mu[k + 1] : (neg ? mu[k + 2] : mu[k]));
+                const int b = horiz ? mm[k + 2] : (vert ? md[k + 1] : (neg ? md[k] : md[k + 2]));
+                // horizontal / vertical: m > a && m >= b ; diagonal: m > a && m > b   <=>   m > b - (horiz || vert)
+                const bool cand = (m > low) && (m > a) && (m > b - ((horiz || vert) ? 1 : 0));
+                cb |= (cand ? 1u : 0u) << k;
+                sb |= ((cand && m > high) ? 1u : 0u) << k;
+            }
+            cb &= own_px;
+            sb &= own_px;
+        }
+        // OR over the 8 lanes of a mask word (xor butterflies stay inside the aligned group of 8)
+        unsigned wc = cb << (4 * (lane & 7)), wsx = sb << (4 * (lane & 7));
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            wc |= __shfl_xor_sync(0xffffffffu, wc, d);
+            wsx |= __shfl_xor_sync(0xffffffffu, wsx, d);
+        }
+        if (writer) {
+            maskC[(size_t)yn * wp32 + wi] = wc;
+            maskS[(size_t)yn * wp32 + wi] = wsx;
+        }
+    };
+
+    unsigned ra[6], rb[6], rc[6];
+    int ma[6], mb[6], mc[6];
+    int dxa[4], dya[4], dxb[4], dyb[4], dxc[4], dyc[4];
+    // prologue: magnitudes of row y0-1 need gray rows y0-2 .. y0
+    load_row(y0 - 2, ra);
+    load_row(y0 - 1, rb);
+    load_row(y0, rc);
+    mag_row(y0 - 1, ra, rb, rc, ma, dxa, dya);       // slot a: row y0-1
+    load_row(y0 + 1, ra);
+    mag_row(y0, rb, rc, ra, mb, dxb, dyb);           // slot b: row y0
+    // steady state, unrolled by three so that the register slots rotate without moves:
+    //   gray rows held: (rc, ra) = (y, y+1) ; magnitudes held: (ma, mb) = (y-1, y) ; row y+2 is in flight (pv, ph)
+    const int y_end = min(y0 + NMS_RS, h);
+    unsigned pv, ph, qv, qh;
+    issue_row(y0 + 2, pv, ph);
+    for (int y = y0; y < y_end; y += 3) {
+        issue_row(y + 3, qv, qh);
+        finish_row(pv, ph, rb);
+        mag_row(y + 1, rc, ra, rb, mc, dxc, dyc);
+        nms_row(y, ma, mb, mc, dxb, dyb);
+        issue_row(y + 4, pv, ph);
+        finish_row(qv, qh, rc);
+        mag_row(y + 2, ra, rb, rc, ma, dxa, dya);
+        nms_row(y + 1, mb, mc, ma, dxc, dyc);
+        issue_row(y + 5, qv, qh);
+        finish_row(pv, ph, ra);
+        mag_row(y + 3, rb, rc, ra, mb, dxb, dyb);
+        nms_row(y + 2, mc, ma, mb, dxa, dya);
+        pv = qv; ph = qh;
+    }
+}
+
+// ---- (2) hysteresis on the bit masks --------------------------------------------------------------------------
+// Word type W: a lane owns one W of a row.  32-bit words serve rows of up to 1024 pixels with single-instruction
+// arithmetic; 64-bit words rows of up to 2048 pixels.  The masks are the same bytes either way (little endian).
+template <typename W> struct WordOps;
+template <> struct WordOps<unsigned> {
+    static constexpr int kBits = 32;
+    static __device__ __forceinline__ unsigned rev(unsigned v) { return __brev(v); }
+};
+template <> struct WordOps<unsigned long long> {
+    static constexpr int kBits = 64;
+    static __device__ __forceinline__ unsigned long long rev(unsigned long long v) { return __brevll(v); }
+};
+
+// Flood towards higher bit positions over the whole row (lane = word, lane 0 = leftmost pixels): the row is one long
+// integer, up = (((C + S) ^ C) & C) | S with the carries between the lanes' words resolved by carry look-ahead on two
+// ballots: G = lanes whose word overflows, P = lanes whose word is all ones (would pass a carry on); the lanes that
+// receive a carry are ((G << 1) + P) ^ P.  Constant time, whatever the length of a run.
+template <typename W>
+__device__ __forceinline__ W flood_up_row(W c, W s, int lane)
+{
+    const W sum = c + s;
+    const unsigned G = __ballot_sync(0xffffffffu, sum < c);
+    const unsigned P = __ballot_sync(0xffffffffu, sum == (W)~(W)0);
+    const unsigned cin = (((G << 1) + P) ^ P);
+    const W tot = sum + (W)((cin >> lane) & 1u);
+    return (((tot ^ c) & c) | s);
+}
+
+// all candidate bits of the row connected to a seed bit, in both directions
+template <typename W>
+__device__ __forceinline__ W flood_row(W c, W s, int lane)
+{
+    s &= c;
+    const W up = flood_up_row<W>(c, s, lane);
+    // the other direction: the same on the mirrored row (bits reversed inside the words, lane order reversed)
+    const W rc = WordOps<W>::rev(__shfl_sync(0xffffffffu, c, 31 - lane));
+    const W rs = WordOps<W>::rev(__shfl_sync(0xffffffffu, s, 31 - lane));
+    const W dn = WordOps<W>::rev(__shfl_sync(0xffffffffu, flood_up_row<W>(rc, rs, lane), 31 - lane));
+    return up | dn;
+}
+
+// seeds a strong row hands to the row next to it: the bits themselves and their left / right neighbours (8-connectivity)
+template <typename W>
+__device__ __forceinline__ W spread_row(W p, int lane)
+{
+    constexpr int kTop = WordOps<W>::kBits - 1;
+    const unsigned from_left = __shfl_up_sync(0xffffffffu, (unsigned)(p >> kTop), 1);
+    const unsigned from_right = __shfl_down_sync(0xffffffffu, (unsigned)(p & (W)1), 1);
+    W o = p | (p << 1) | (p >> 1);
+    if (lane > 0) o |= (W)from_left;
+    if (lane < 31) o |= (W)from_right << kTop;
+    return o;
+}
+
+// Fallback for images whose masks do not fit shared memory: blind down / up sweeps per band on the masks in L2.
+__global__ void __launch_bounds__(1024) k_canny_hyst(const ImgLevel *__restrict__ desc, int w, int h, int wp64)
+{
+    typedef unsigned long long W;
+    const ImgLevel &L = desc[blockIdx.x];
+    const W *__restrict__ C = (const W *)L.labels;
+    W *S = (W *)L.labels + (size_t)wp64 * h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int R = (h + n_warps - 1) / n_warps;
+    const int y_lo = warp * R, y_hi = min(h, y_lo + R);
+    const bool act = lane < wp64;
+    auto ldS = [&](int y) -> W { return act ? __ldcg(S + (size_t)y * wp64 + lane) : (W)0; };
+    auto ldC = [&](int y) -> W { return act ? __ldg(C + (size_t)y * wp64 + lane) : (W)0; };
+    while (true) {
+        int changed = 0;
+        if (y_lo < y_hi) {
+            W prev = y_lo > 0 ? ldS(y_lo - 1) : (W)0;
+            W c = ldC(y_lo), s0 = ldS(y_lo);
+            for (int y = y_lo; y < y_hi; ++y) {           // down
+                W cn = 0, sn = 0;
+                if (y + 1 < y_hi) { cn = ldC(y + 1); sn = ldS(y + 1); }
+                const W s2 = flood_row<W>(c, s0 | spread_row<W>(prev, lane), lane);
+                if (s2 != s0) { S[(size_t)y * wp64 + lane] = s2; changed = 1; }
+                prev = s2; c = cn; s0 = sn;
+            }
+            W nxt = y_hi < h ? ldS(y_hi) : (W)0;
+            for (int y = y_hi - 1; y >= y_lo; --y) {      // up (prev = last row of the band, just computed)
+                const W cy = ldC(y), sy = (y == y_hi - 1) ? prev : ldS(y);
+                const W s2 = flood_row<W>(cy, sy | spread_row<W>(nxt, lane), lane);
+                if (s2 != sy) { S[(size_t)y * wp64 + lane] = s2; changed = 1; }
+                nxt = s2;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+}
+
+// Default variant: both masks of the image staged in shared memory (2 * ceil(w/64) * 8 * h bytes: 77 KB at VGA) and a
+// DIRTY-ROW worklist instead of blind sweeps.  A row is dirty when one of its two neighbour rows has gained strong bits
+// that hand it a seed it does not have yet (all rows are dirty at the start).  A warp walks the dirty rows of its band
+// downwards, then upwards; visiting a row floods it from its own strong bits and the 8-connected bits of both neighbour
+// rows, and a row that changed marks its neighbours (across band boundaries through a per-warp word in shared memory,
+// taken at the next block barrier).  The first round costs about two floods per row, every later round only touches
+// the handful of rows a weak chain is still creeping along.  wp = row pitch in words of type W.
+template <typename W>
+__global__ void __launch_bounds__(1024) k_canny_hyst_smem(const ImgLevel *__restrict__ desc, int w, int h, int wp)
+{
+    extern __shared__ unsigned long long hs_mem[];
+    __shared__ unsigned incoming[2][32];
+    const ImgLevel &L = desc[blockIdx.x];
+    const size_t nw = (size_t)wp * h;
+    W *gC = (W *)L.labels, *gS = gC + nw;
+    W *C = (W *)hs_mem, *S = C + nw;
+    for (size_t i = threadIdx.x; i < nw; i += blockDim.x) { C[i] = gC[i]; S[i] = gS[i]; }
+    if (threadIdx.x < 64) incoming[threadIdx.x >> 5][threadIdx.x & 31] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int R = (h + n_warps - 1) / n_warps;          // <= 32 (launcher)
+    const int y_lo = warp * R, y_hi = min(h, y_lo + R);
+    const int n_rows = y_hi > y_lo ? y_hi - y_lo : 0;
+    const bool act = lane < wp;
+    const int col = act ? lane : 0;
+    unsigned dirty = n_rows >= 32 ? 0xffffffffu : ((1u << n_rows) - 1u);
+    unsigned fresh = dirty;                               // rows not yet flooded from their own strong bits
+    auto row = [&](const W *M, int y) -> W { return act ? M[(size_t)y * wp + col] : (W)0; };
+    for (int it = 0;; ++it) {
+        const int par = it & 1;
+        unsigned inc = 0;
+        if (lane == 0) inc = atomicExch(&incoming[par][warp], 0u);
+        dirty |= __shfl_sync(0xffffffffu, inc, 0);
+        int sent = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            int pos = pass == 0 ? 0 : 32;                 // down: next row >= pos ; up: next row < pos
+            while (true) {
+                const unsigned m = pass == 0 ? (pos < 32 ? dirty & ~((1u << pos) - 1u) : 0u)
+                                             : (pos > 0 ? dirty & (pos >= 32 ? 0xffffffffu : ((1u << pos) - 1u)) : 0u);
+                if (!m) break;
+                const int r = pass == 0 ? __ffs(m) - 1 : 31 - __clz(m);
+                pos = pass == 0 ? r + 1 : r;
+                dirty &= ~(1u << r);
+                const int y = y_lo + r;
+                const W c = row(C, y), s0 = row(S, y);
+                W nb = 0;
+                if (y > 0) nb = row(S, y - 1);
+                if (y + 1 < h) nb |= row(S, y + 1);
+                const W seeds = spread_row<W>(nb, lane) & c & ~s0;
+                const bool first = (fresh >> r) & 1u;
+                fresh &= ~(1u << r);
+                if (!first && !__any_sync(0xffffffffu, seeds != 0)) continue;
+                const W s2 = flood_row<W>(c, s0 | seeds, lane);
+                const W delta = s2 & ~s0;
+                if (!__any_sync(0xffffffffu, delta != 0)) continue;
+                if (delta) S[(size_t)y * wp + col] = s2;
+                // a neighbour row must be (re)visited only if the new bits hand it a seed it does not have yet
+                const W sp = spread_row<W>(delta, lane);
+                if (y > 0 && __any_sync(0xffffffffu, (sp & row(C, y - 1) & ~row(S, y - 1)) != 0)) {
+                    if (r > 0) dirty |= 1u << (r - 1);
+                    else { if (lane == 0) atomicOr(&incoming[par ^ 1][warp - 1], 1u << (R - 1)); sent = 1; }
+                }
+                if (y + 1 < h && __any_sync(0xffffffffu, (sp & row(C, y + 1) & ~row(S, y + 1)) != 0)) {
+                    if (r + 1 < n_rows) dirty |= 1u << (r + 1);
+                    else { if (lane == 0) atomicOr(&incoming[par ^ 1][warp + 1], 1u); sent = 1; }
+                }
+            }
+        }
+        if (!__syncthreads_or((dirty != 0u) || sent)) break;
+    }
+    for (size_t i = threadIdx.x; i < nw; i += blockDim.x) gS[i] = S[i];
+}
+
+// ---- (3) bit mask -> byte maps + patch counters ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_canny_expand(const ImgLevel *__restrict__ desc, int w, int h, int wp32, int P)
+{
+    const int f = blockIdx.z;
+    const ImgLevel &L = desc[f];
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (y >= h || x0 >= w) return;
+    const unsigned *__restrict__ maskS = (const unsigned *)L.labels + (size_t)wp32 * h;
+    const unsigned bits = (__ldcg(maskS + (size_t)y * wp32 + (x0 >> 5)) >> (x0 & 31)) & 0xffffu;
+    uint8_t *e = L.edges + (size_t)y * w + x0, *eo = L.edges_orig + (size_t)y * w + x0;
+    unsigned o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const unsigned nib = (bits >> (4 * q)) & 15u;
+        // 4 bits -> 4 bytes of 0 / 255
+        o[q] = ((nib & 1u) * 0xffu) | (((nib >> 1) & 1u) * 0xff00u) | (((nib >> 2) & 1u) * 0xff0000u) | (((nib >> 3) & 1u) * 0xff000000u);
+    }
+    if (x0 + 16 <= w && ((((uintptr_t)e) & 15) == 0) && ((((uintptr_t)eo) & 15) == 0)) {
+        const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
+        *(uint4 *)e = v;
+        *(uint4 *)eo = v;
+    } else {
+        for (int k = 0; k < 16 && x0 + k < w; ++k) {
+            const uint8_t v = (bits >> k) & 1u ? 255 : 0;
+            e[k] = v; eo[k] = v;
+        }
+    }
+    if (bits && L.hist_w > 0 && L.hist_h > 0) {
+        int *cnt = (int *)L.flags;
+        const int py = y / P;
+        if (py < L.hist_h)
+            for (unsigned mm = bits; mm;) {
+                const int b = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const int px = (x0 + b) / P;
+                if (px < L.hist_w) atomicAdd(cnt + py * L.hist_w + px, 1);
+            }
+    }
+}
+
+static int launch_canny_bits(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high, int patch,
+                             void *d_counts0, size_t counts_stride)
+{
+    const int hist_w = w / patch, hist_h = h / patch;
+    if (hist_w > 0 && hist_h > 0)
+        REVO_CUDA(ctx, cudaMemset2DAsync(d_counts0, counts_stride, 0, (size_t)hist_w * hist_h * sizeof(int), (size_t)n, ctx->stream));
+    const int wp64 = cdiv(w, 64), wp32 = 2 * wp64;
+    {
+        dim3 grid(cdiv(w, 32 * NMS_PX), cdiv(cdiv(h, NMS_RS), 4), n);
+        k_canny_nms<<<grid, 128, 0, ctx->stream>>>(d_desc, w, h, low, high, wp32);
+        LAUNCH_CHECK(ctx);
+    }
+    {
+        int warps = cdiv(h, 8);
+        warps = warps < 1 ? 1 : (warps > 32 ? 32 : warps);
+        const size_t smem = (size_t)2 * wp64 * 8 * h;
+        if (smem <= 200 * 1024 && cdiv(h, warps) <= 32) {
+            if (wp32 <= 32) {
+                REVO_CUDA(ctx, cudaFuncSetAttribute(k_canny_hyst_smem<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                k_canny_hyst_smem<unsigned><<<n, warps * 32, smem, ctx->stream>>>(d_desc, w, h, wp32);
+            } else {
+                REVO_CUDA(ctx, cudaFuncSetAttribute(k_canny_hyst_smem<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    200 * 1024));
+                k_canny_hyst_smem<unsigned long long><<<n, warps * 32, smem, ctx->stream>>>(d_desc, w, h, wp64);
+            }
+        } else {
+            k_canny_hyst<<<n, warps * 32, 0, ctx->stream>>>(d_desc, w, h, wp64);
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    {
+        dim3 block(32, 8), grid(cdiv(cdiv(w, 16), 32), cdiv(h, 8), n);
+        k_canny_expand<<<grid, block, 0, ctx->stream>>>(d_desc, w, h, wp32, patch);
+        LAUNCH_CHECK(ctx);
+    }
+    if (hist_w > 0 && hist_h > 0) {
+        k_hist_finalize<<<n, 256, 0, ctx->stream>>>(d_desc);
+        LAUNCH_CHECK(ctx);
+    }
+    return REVO_OK;
+}
+
 int launch_canny(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, int low, int high, const void *gray_tmap, int patch,
                  void *d_counts0, size_t counts_stride)
 {
+    // bit-mask pipeline: rows of up to 2048 pixels (a lane owns one 64-bit word of a row in the hysteresis); the two
+    // masks must fit the frame's label plane (2 * ceil(w/64) * 8 * h bytes <= 4 * w0 * h0: always)
+    static const int force_tile = getenv("REVO_CANNY_TILE") ? atoi(getenv("REVO_CANNY_TILE")) : 0;
+    if (!force_tile && w <= 2048 && w >= 8 && (w & 3) == 0) return launch_canny_bits(ctx, d_desc, n, w, h, low, high, patch, d_counts0, counts_stride);
     const int hist_w = w / patch, hist_h = h / patch;
     if (hist_w > 0 && hist_h > 0)
         REVO_CUDA(ctx, cudaMemset2DAsync(d_counts0, counts_stride, 0, (size_t)hist_w * hist_h * sizeof(int), (size_t)n, ctx->stream));

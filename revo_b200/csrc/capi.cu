@@ -142,13 +142,16 @@ int revo_ctx_create(int device, revo_ctx **out)
     if (!ctx) return REVO_ERR_INVALID_ARG;
     ctx->device = device;
     ctx->launches = 0;
-    ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+    ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0; ctx->pinned_kf = nullptr; ctx->pinned_kf_bytes = 0; ctx->pinned_kf_busy = false;
+    for (int i = 0; i < 2; ++i) { ctx->stage[i] = nullptr; ctx->stage_bytes[i] = 0; ctx->stage_used[i] = false; }
+    ctx->stage_next = 0;
     ctx->track_ctas_per_pair = 0; ctx->track_threads = 0; ctx->track_engine = 0; ctx->track_chunk_points = 0;
     for (auto &v : ctx->ev_valid) v = false;
     ctx->split_rank = 0; ctx->split_world = 1; ctx->split_local = nullptr; ctx->split_seq = 0;
     for (auto &p : ctx->split_peers) p = nullptr;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         (void)cudaGetLastError();
         delete ctx;
         return REVO_ERR_CUDA;
@@ -160,6 +163,8 @@ int revo_ctx_create(int device, revo_ctx **out)
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&ctx->pinned_kf_read, cudaEventDisableTiming);
+    for (auto &e : ctx->stage_consumed) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     (void)cudaGetLastError();
     *out = ctx;
     return REVO_OK;
@@ -175,7 +180,12 @@ int revo_ctx_destroy(revo_ctx *ctx)
     if (ctx->split_local) cudaFree(ctx->split_local);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pinned_kf) cudaFreeHost(ctx->pinned_kf);
+    cudaEventDestroy(ctx->pinned_kf_read);
+    for (int i = 0; i < 2; ++i) { if (ctx->stage[i]) cudaFree(ctx->stage[i]); cudaEventDestroy(ctx->stage_consumed[i]); }
     for (auto &e : ctx->ev) cudaEventDestroy(e);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     (void)cudaGetLastError();
     delete ctx;
@@ -185,6 +195,7 @@ int revo_ctx_destroy(revo_ctx *ctx)
 int revo_ctx_synchronize(revo_ctx *ctx)
 {
     if (!ctx) return REVO_ERR_INVALID_ARG;
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return REVO_OK;
 }
@@ -204,6 +215,16 @@ int revo_ctx_last_timings(revo_ctx *ctx, float *pyramid_ms, float *keyframe_ms, 
         *out[i] = 0.f;
         if (ctx->ev_valid[i]) REVO_CUDA(ctx, cudaEventElapsedTime(out[i], ctx->ev[2 * i], ctx->ev[2 * i + 1]));
     }
+    return REVO_OK;
+}
+
+int revo_ctx_last_upload_ms(revo_ctx *ctx, float *upload_ms)
+{
+    if (!ctx || !upload_ms) return REVO_ERR_INVALID_ARG;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    *upload_ms = 0.f;
+    if (ctx->ev_valid[3]) REVO_CUDA(ctx, cudaEventElapsedTime(upload_ms, ctx->ev[6], ctx->ev[7]));
     return REVO_OK;
 }
 
@@ -300,11 +321,16 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
     const size_t o_flags = take((size_t)w0 * h0);
     const size_t total = off;
 
+    // Host inputs are uploaded on the context's COPY stream (slab allocation, descriptor tables, bgr staging and depth),
+    // the kernels run on the main stream behind an event: the H2D of the next batch overlaps the kernels of this one.
+    const bool host_in = !is_device_ptr(bgr);
+    cudaStream_t up = host_in ? ctx->copy_stream : ctx->stream;
+
     Slab *slab = new (std::nothrow) Slab();
     if (!slab) return REVO_ERR_INVALID_ARG;
     slab->n_frames = n; slab->live = n; slab->bytes = total; slab->mem = nullptr;
     slab->stream = ctx->stream; slab->ready = nullptr;
-    cudaError_t e = cudaMallocAsync(&slab->mem, total, ctx->stream);
+    cudaError_t e = cudaMallocAsync(&slab->mem, total, up);
     if (e != cudaSuccess) { delete slab; return cuda_fail(ctx, e, "cudaMallocAsync(slab)"); }
     uint8_t *base = (uint8_t *)slab->mem;
     auto chunk = [&](size_t o, size_t per_frame, int f) { return base + o + align_up(per_frame, 256) * (size_t)f; };
@@ -337,35 +363,61 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
         }
         pyrs[f] = p;
     }
+    int stage_slot = -1;     // which of the context's two bgr staging buffers this call uploads into
     auto fail = [&](int code) {
         for (auto *p : pyrs) delete p;
-        cudaFreeAsync(slab->mem, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);   // error path only: nothing may still be using the slab
+        cudaFreeAsync(slab->mem, up);
         delete slab;
         return code;
     };
     for (int l = 0; l < NL; ++l) {
         slab->d_desc[l] = (ImgLevel *)(base + o_desc[l]);
-        e = cudaMemcpyAsync(slab->d_desc[l], &host_desc[(size_t)l * n], sizeof(ImgLevel) * (size_t)n, cudaMemcpyHostToDevice,
-                            ctx->stream);
+        e = cudaMemcpyAsync(slab->d_desc[l], &host_desc[(size_t)l * n], sizeof(ImgLevel) * (size_t)n, cudaMemcpyHostToDevice, up);
         if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memcpy(desc)"));
     }
-    e = cudaMemsetAsync(base + o_counters, 0, sizeof(int) * 2 * NL * (size_t)n, ctx->stream);
+    e = cudaMemsetAsync(base + o_counters, 0, sizeof(int) * 2 * NL * (size_t)n, up);
     if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memset(counters)"));
 
     // ---- inputs -------------------------------------------------------------------------------------
     const size_t bgr_frame = (size_t)w0 * h0 * channels;
     const uint8_t *d_bgr = bgr;
-    if (!is_device_ptr(bgr)) {
-        rc = ensure_scratch(ctx, bgr_frame * (size_t)n);
-        if (rc) return fail(rc);
-        e = cudaMemcpyAsync(ctx->scratch, bgr, bgr_frame * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (host_in) {
+        // persistent double buffer: no allocator dependency between this upload and the kernels of the previous batch
+        stage_slot = ctx->stage_next;
+        ctx->stage_next ^= 1;
+        const size_t need = bgr_frame * (size_t)n;
+        if (ctx->stage_bytes[stage_slot] < need) {
+            if (ctx->stage[stage_slot]) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaStreamSynchronize(up);
+                cudaFree(ctx->stage[stage_slot]);
+                ctx->stage[stage_slot] = nullptr; ctx->stage_bytes[stage_slot] = 0; ctx->stage_used[stage_slot] = false;
+            }
+            e = cudaMalloc(&ctx->stage[stage_slot], need);
+            if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc(bgr staging)"));
+            ctx->stage_bytes[stage_slot] = need;
+        }
+        if (ctx->stage_used[stage_slot]) cudaStreamWaitEvent(up, ctx->stage_consumed[stage_slot], 0);   // gray of two batches ago
+        cudaEventRecord(ctx->ev[6], up);
+        e = cudaMemcpyAsync(ctx->stage[stage_slot], bgr, need, cudaMemcpyHostToDevice, up);
         if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memcpy(bgr)"));
-        d_bgr = (const uint8_t *)ctx->scratch;
+        d_bgr = (const uint8_t *)ctx->stage[stage_slot];
     }
     {
         const size_t fb = (size_t)w0 * h0 * 4;
-        e = cudaMemcpy2DAsync(base + o_depth[0], align_up(fb, 256), depth, fb, fb, (size_t)n, cudaMemcpyDefault, ctx->stream);
+        e = cudaMemcpy2DAsync(base + o_depth[0], align_up(fb, 256), depth, fb, fb, (size_t)n, cudaMemcpyDefault, up);
         if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memcpy(depth)"));
+    }
+    if (host_in) {
+        cudaEventRecord(ctx->ev[7], up);
+        ctx->ev_valid[3] = true;
+        cudaEvent_t uploaded;
+        e = cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(uploaded, up);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, uploaded, 0);
+        if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "upload event"));
+        cudaEventDestroy(uploaded);   // released by the runtime once the wait has been satisfied
     }
 
     // ---- the pyramid (imgpyramidrgbd.cpp:43-96) -------------------------------------------------
@@ -378,6 +430,10 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
     rc = launch_gray(ctx, d_bgr, (size_t)w0 * channels, channels, bgr_frame, slab->d_desc[0], n, w0, h0);
+    if (stage_slot >= 0) {
+        cudaEventRecord(ctx->stage_consumed[stage_slot], ctx->stream);
+        ctx->stage_used[stage_slot] = true;
+    }
     for (int l = 0; l < NL && !rc; ++l) {
         if (l > 0) rc = launch_pyrdown_depth(ctx, slab->d_desc[l - 1], slab->d_desc[l], n, g[l].w, g[l].h, g[l - 1].w, g[l - 1].h);
         if (!rc) {
@@ -476,18 +532,33 @@ int revo_pyr_make_keyframe_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs)
     const int NL = todo[0]->n_levels;
     for (auto *p : todo)
         if (p->n_levels != NL || p->lv[0].w != todo[0]->lv[0].w || p->lv[0].h != todo[0]->lv[0].h) return REVO_ERR_INVALID_ARG;
-    for (auto *p : todo) wait_for_build(ctx, p);
+    for (size_t i = 0; i < todo.size(); ++i)
+        if (i == 0 || todo[i]->slab != todo[i - 1]->slab) wait_for_build(ctx, todo[i]);
     {
         int rc = alloc_keyframe_mem(ctx, todo.data(), m);
         if (rc) return rc;
     }
-    // temporary descriptor tables (with dt/opt set) in a stream-ordered allocation
-    std::vector<ImgLevel> host((size_t)NL * m);
+    // temporary descriptor tables (with dt/opt set) in a stream-ordered allocation, filled from pinned mapped host memory by
+    // a kernel (not by the copy engine, which may be busy for milliseconds with the frame uploads of the next batches)
+    const size_t tab_bytes = sizeof(ImgLevel) * (size_t)NL * m;
+    if (ctx->pinned_kf_busy) { REVO_CUDA(ctx, cudaEventSynchronize(ctx->pinned_kf_read)); ctx->pinned_kf_busy = false; }
+    if (ctx->pinned_kf_bytes < tab_bytes + 16) {
+        if (ctx->pinned_kf) REVO_CUDA(ctx, cudaFreeHost(ctx->pinned_kf));
+        ctx->pinned_kf = nullptr;
+        ctx->pinned_kf_bytes = align_up(2 * tab_bytes + 16, 1 << 16);
+        REVO_CUDA(ctx, cudaMallocHost(&ctx->pinned_kf, ctx->pinned_kf_bytes));
+    }
+    ImgLevel *host = (ImgLevel *)ctx->pinned_kf;
     for (int l = 0; l < NL; ++l)
         for (int i = 0; i < m; ++i) host[(size_t)l * m + i] = todo[i]->lv[l];
     ImgLevel *d_tab = nullptr;
-    REVO_CUDA(ctx, cudaMallocAsync((void **)&d_tab, sizeof(ImgLevel) * host.size(), ctx->stream));
-    REVO_CUDA(ctx, cudaMemcpyAsync(d_tab, host.data(), sizeof(ImgLevel) * host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    REVO_CUDA(ctx, cudaMallocAsync((void **)&d_tab, tab_bytes + 16, ctx->stream));
+    {
+        int rc = launch_stage_in(ctx, host, d_tab, tab_bytes);
+        if (rc) return rc;
+        cudaEventRecord(ctx->pinned_kf_read, ctx->stream);
+        ctx->pinned_kf_busy = true;
+    }
     int rc = REVO_OK;
     cudaEventRecord(ctx->ev[2], ctx->stream);
     for (int l = 0; l < NL && !rc; ++l) rc = launch_keyframe(ctx, d_tab + (size_t)l * m, m, todo[0]->lv[l].w, todo[0]->lv[l].h);
@@ -681,12 +752,18 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     REVO_CUDA(ctx, cudaSetDevice(ctx->device));
     const int min_lvl = prm.mode == 0 ? prm.cfg.pyr_min_lvl : prm.level;
     const int max_lvl = prm.mode == 0 ? prm.cfg.pyr_max_lvl : prm.level;
-    std::vector<PairDesc> host(n);
+    // descriptors are written straight into pinned, device-mapped host memory (see k_stage_in)
+    {
+        int rc = ensure_pinned(ctx, align_up(sizeof(PairDesc) * (size_t)n, 16));
+        if (rc) return rc;
+    }
+    PairDesc *host = (PairDesc *)ctx->pinned;
     for (int i = 0; i < n; ++i) {
         int rc = fill_pair(refs[i], curs[i], min_lvl, max_lvl, R9s + 9 * (size_t)i, t3s + 3 * (size_t)i, &host[i]);
         if (rc) return rc;
-        wait_for_build(ctx, refs[i]);
-        wait_for_build(ctx, curs[i]);
+        // one device-side wait per distinct batch (the pairs of a batch share two slabs)
+        if (i == 0 || refs[i]->slab != refs[i - 1]->slab) wait_for_build(ctx, refs[i]);
+        if (i == 0 || curs[i]->slab != curs[i - 1]->slab) wait_for_build(ctx, curs[i]);
     }
     if (!trace) trace_cap = 0;
     prm.trace_cap = trace_cap;
@@ -715,8 +792,8 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     int *d_wc = (int *)(ws + b_pairs + b_res + b_rec + b_tr + b_tc);
     uint8_t *d_q = ws + b_pairs + b_res + b_rec + b_tr + b_tc + 256;
     int rc = REVO_OK;
-    cudaError_t e = cudaMemcpyAsync(d_pairs, host.data(), sizeof(PairDesc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_res, 0, b_res + b_rec, ctx->stream);
+    rc = launch_stage_in(ctx, host, d_pairs, sizeof(PairDesc) * (size_t)n);
+    cudaError_t e = cudaMemsetAsync(d_res, 0, b_res + b_rec, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_wc, 0, 256, ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "track upload");
     cudaEventRecord(ctx->ev[4], ctx->stream);

@@ -59,20 +59,31 @@ struct revo_pyr {
 struct revo_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t copy_stream;   // uploads of host inputs (so that the H2D of the next batch overlaps the kernels of this one)
     cudaDeviceProp prop;
     std::string last_error;
     uint64_t launches;
     // scratch
     void *scratch;        // generic device scratch (descriptor tables, staging of uploads)
     size_t scratch_bytes;
-    void *pinned;         // pinned host staging for small results
+    void *pinned;         // pinned, device-mapped host staging of the pair descriptors (run_track)
     size_t pinned_bytes;
+    void *pinned_kf;      // same for the descriptor tables of keyframe promotion
+    size_t pinned_kf_bytes;
+    cudaEvent_t pinned_kf_read;   // recorded after the kernel that reads pinned_kf
+    bool pinned_kf_busy;
+    // double-buffered device staging of uploaded host bgr frames: the upload of batch k+2 must not wait for the build of k+1
+    void *stage[2];
+    size_t stage_bytes[2];
+    cudaEvent_t stage_consumed[2];   // recorded on the main stream after the gray kernel that read the buffer
+    bool stage_used[2];
+    int stage_next;
     int track_ctas_per_pair;
     int track_threads;
     int track_engine;        // 0 = automatic, 1 = one cluster per pair (track.cu), 2 = task queue (track_queue.cu)
     int track_chunk_points;  // queue engine: minimum points per task (0 = automatic)
-    cudaEvent_t ev[6];      // pyramid begin/end, keyframe begin/end, track kernel begin/end
-    bool ev_valid[3];
+    cudaEvent_t ev[8];      // pyramid begin/end, keyframe begin/end, track kernel begin/end, upload begin/end (copy stream)
+    bool ev_valid[4];
     // split mode (multi-GPU single pair)
     int split_rank, split_world;
     void *split_local;                 // this rank's mailbox (device memory, IPC-exported)
@@ -157,6 +168,8 @@ struct TrackParams {
 int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm,
                  revo_track_result *d_results, double *d_records, revo_trace_entry *d_trace, int *d_trace_counts,
                  int *d_work_counter);
+
+int launch_stage_in(revo_ctx *ctx, const void *src_mapped_host, void *dst, size_t bytes);
 
 // ---- track_queue.cu ----------------------------------------------------------
 // Task-queue engine: device workspace size for n_pairs (ring + pair states + partial tables) and the launcher.

@@ -91,70 +91,97 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return i;
 }
 
-constexpr int PD_TW = 32, PD_TH = 8;
+// Register-tiled: one thread -> 4 horizontally adjacent outputs of one row.  Per input row (5 of them) the 11 bytes it
+// needs come from four aligned 32-bit loads (columns 2x-4 .. 2x+11); the 2.5-fold vertical reuse of input rows between
+// neighbouring output rows is served by L1.  Border threads take a byte-wise path with the REFLECT_101 index map.
 __global__ void __launch_bounds__(256) k_pyrdown(const ImgLevel *__restrict__ src, const ImgLevel *__restrict__ dst, int ws,
                                                  int hs, int wd, int hd)
 {
-    __shared__ uint8_t tile[2 * PD_TH + 3][2 * PD_TW + 4];
-    __shared__ uint16_t hb[2 * PD_TH + 3][PD_TW];
     const int f = blockIdx.z;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= wd || y >= hd) return;
     const uint8_t *__restrict__ in = src[f].gray;
     uint8_t *__restrict__ out = dst[f].gray;
-    const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH;
-    const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    constexpr int IW = 2 * PD_TW + 3, IH = 2 * PD_TH + 3;
-    for (int i = tid; i < IW * IH; i += 256) {
-        const int r = i / IW, c = i - r * IW;
-        tile[r][c] = in[(size_t)reflect101(iy0 + r, hs) * ws + reflect101(ix0 + c, ws)];
+    const int c0 = 2 * x0 - 4;   // column of byte 0 of the 16-byte window
+    const bool fast = (c0 >= 0) && (c0 + 16 <= ws) && ((ws & 3) == 0) && ((((uintptr_t)in) & 3) == 0) && (x0 + 4 <= wd);
+    int hsum[5][4];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const uint8_t *__restrict__ row = in + (size_t)reflect101(2 * y - 2 + r, hs) * ws;
+        int b[16];
+        if (fast) {
+            const uint32_t *q = (const uint32_t *)(row + c0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t v = __ldg(q + k);
+                b[4 * k] = v & 255; b[4 * k + 1] = (v >> 8) & 255; b[4 * k + 2] = (v >> 16) & 255; b[4 * k + 3] = v >> 24;
+            }
+        } else {
+#pragma unroll
+            for (int i = 2; i <= 12; ++i) b[i] = row[reflect101(c0 + i, ws)];
+            b[0] = b[1] = b[13] = b[14] = b[15] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 2 * k + 4;
+            hsum[r][k] = b[i - 2] + 4 * b[i - 1] + 6 * b[i] + 4 * b[i + 1] + b[i + 2];
+        }
     }
-    __syncthreads();
-    for (int i = tid; i < IH * PD_TW; i += 256) {
-        const int r = i / PD_TW, c = i - r * PD_TW;
-        const uint8_t *t = &tile[r][2 * c];
-        hb[r][c] = (uint16_t)(t[0] + 4 * t[1] + 6 * t[2] + 4 * t[3] + t[4]);
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int v = hsum[0][k] + 4 * hsum[1][k] + 6 * hsum[2][k] + 4 * hsum[3][k] + hsum[4][k];
+        o |= (uint32_t)((v + 128) >> 8) << (8 * k);
     }
-    __syncthreads();
-    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
-    if (ox < wd && oy < hd) {
-        const int r = 2 * threadIdx.y, c = threadIdx.x;
-        const int s = hb[r][c] + 4 * hb[r + 1][c] + 6 * hb[r + 2][c] + 4 * hb[r + 3][c] + hb[r + 4][c];
-        out[(size_t)oy * wd + ox] = (uint8_t)((s + 128) >> 8);
+    uint8_t *op = out + (size_t)y * wd + x0;
+    if (x0 + 4 <= wd && ((((uintptr_t)op) & 3) == 0)) {
+        *(uint32_t *)op = o;
+    } else {
+        for (int k = 0; k < 4 && x0 + k < wd; ++k) op[k] = (uint8_t)(o >> (8 * k));
     }
 }
 
 // K4: FilterSubsampleWithHoles: mean of the >0 entries of each 2x2 block (NaN excluded by the compare).
+__device__ __forceinline__ float depth_half_of(float a, float b, float c, float d)
+{
+    float acc = 0.f, n = 0.f;
+    if (a > 0.0f) { acc = __fadd_rn(acc, a); n += 1.f; }
+    if (b > 0.0f) { acc = __fadd_rn(acc, b); n += 1.f; }
+    if (c > 0.0f) { acc = __fadd_rn(acc, c); n += 1.f; }
+    if (d > 0.0f) { acc = __fadd_rn(acc, d); n += 1.f; }
+    if (n > 0.f) acc = __fdiv_rn(acc, n);
+    return acc;
+}
+
+// one thread -> 4 outputs of one row: two float4 loads from each of the two input rows, one float4 store
 __global__ void __launch_bounds__(256) k_depth_half(const ImgLevel *__restrict__ src, const ImgLevel *__restrict__ dst, int ws,
                                                     int wd, int hd)
 {
     const int f = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= wd || y >= hd) return;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= wd || y >= hd) return;
     const float *__restrict__ in = src[f].depth;
-    const float2 a = *(const float2 *)(in + (size_t)(2 * y) * ws + 2 * x);
-    const float2 b = *(const float2 *)(in + (size_t)(2 * y + 1) * ws + 2 * x);
-    float acc = 0.f, n = 0.f;
-    if (a.x > 0.0f) { acc = __fadd_rn(acc, a.x); n += 1.f; }
-    if (a.y > 0.0f) { acc = __fadd_rn(acc, a.y); n += 1.f; }
-    if (b.x > 0.0f) { acc = __fadd_rn(acc, b.x); n += 1.f; }
-    if (b.y > 0.0f) { acc = __fadd_rn(acc, b.y); n += 1.f; }
-    if (n > 0.f) acc = __fdiv_rn(acc, n);
-    dst[f].depth[(size_t)y * wd + x] = acc;
+    float *__restrict__ out = dst[f].depth + (size_t)y * wd + x0;
+    const float *r0 = in + (size_t)(2 * y) * ws + 2 * x0, *r1 = r0 + ws;
+    if (x0 + 4 <= wd && ((ws & 3) == 0) && ((wd & 3) == 0) && ((((uintptr_t)in) & 15) == 0) && ((((uintptr_t)dst[f].depth) & 15) == 0)) {
+        const float4 a0 = __ldg((const float4 *)r0), a1 = __ldg((const float4 *)r0 + 1);
+        const float4 b0 = __ldg((const float4 *)r1), b1 = __ldg((const float4 *)r1 + 1);
+        *(float4 *)out = make_float4(depth_half_of(a0.x, a0.y, b0.x, b0.y), depth_half_of(a0.z, a0.w, b0.z, b0.w),
+                                     depth_half_of(a1.x, a1.y, b1.x, b1.y), depth_half_of(a1.z, a1.w, b1.z, b1.w));
+    } else {
+        for (int k = 0; k < 4 && x0 + k < wd; ++k) out[k] = depth_half_of(r0[2 * k], r0[2 * k + 1], r1[2 * k], r1[2 * k + 1]);
+    }
 }
 
 int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst,
                          int w_src, int h_src)
 {
-    {
-        dim3 block(PD_TW, PD_TH), grid(cdiv(w_dst, PD_TW), cdiv(h_dst, PD_TH), n);
-        k_pyrdown<<<grid, block, 0, ctx->stream>>>(d_src, d_dst, w_src, h_src, w_dst, h_dst);
-        LAUNCH_CHECK(ctx);
-    }
-    {
-        dim3 block(32, 8), grid(cdiv(w_dst, 32), cdiv(h_dst, 8), n);
-        k_depth_half<<<grid, block, 0, ctx->stream>>>(d_src, d_dst, w_src, w_dst, h_dst);
-        LAUNCH_CHECK(ctx);
-    }
+    dim3 block(32, 8), grid(cdiv(cdiv(w_dst, 4), 32), cdiv(h_dst, 8), n);
+    k_pyrdown<<<grid, block, 0, ctx->stream>>>(d_src, d_dst, w_src, h_src, w_dst, h_dst);
+    LAUNCH_CHECK(ctx);
+    k_depth_half<<<grid, block, 0, ctx->stream>>>(d_src, d_dst, w_src, w_dst, h_dst);
+    LAUNCH_CHECK(ctx);
     return REVO_OK;
 }
 
@@ -316,65 +343,115 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const ImgLevel *__restrict
     L.pts[o] = make_float4(X, Y, Z, 1.0f);
 }
 
-// Batched variant: ONE CTA (32 warps) per image does the whole compaction.  Every warp owns a contiguous range of
-// tiles: pass 1 counts its range, one block-level scan of the 32 range totals, pass 2 re-walks the range and
-// scatters with a running offset -- the same deterministic tile-major order as the three-kernel path, two block
-// barriers in total, no tile_off traffic.  The second walk hits L1/L2.
-__global__ void __launch_bounds__(1024) k_compact_image(const ImgLevel *__restrict__ desc, int w, int h, int tiles_x, int n_tiles,
-                                                        float dmin, float dmax)
+// Batched variant (n >= 8 frames): two streaming kernels, one warp per GROUP of 32 horizontally adjacent tiles
+// (a 256 x 4 pixel strip, so every edge-map row segment a warp touches is one coalesced 256-byte read).
+//   k_group_mask : lane = tile; the four 8-byte row segments of the tile -> 32-bit mask of its edge pixels, depth is
+//                  fetched only for set bits (~7 % of the pixels), the validity mask goes to tile_off[tile] and the
+//                  number of points of the group to gcnt[group] (scratch: the frame's label plane, free after Canny);
+//   k_group_scatter: group offset = sum of the counts of all preceding groups (a few hundred ints, warp-reduced),
+//                  exclusive scan over the 32 tiles, then every lane writes the points of its set bits.
+// Same deterministic tile-major order as the three-kernel path.
+constexpr int kGroupTiles = 32;
+
+__device__ __forceinline__ unsigned tile_edge_mask(const ImgLevel &L, int tx, int ty, int w, int h, float dmin, float dmax)
 {
-    __shared__ int wsum[33];
-    const ImgLevel &L = desc[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per = (n_tiles + 31) / 32;
-    const int t0 = warp * per, t1 = min(n_tiles, t0 + per);
-    const int lx = lane & 7, ly = lane >> 3;
-    int cnt = 0;
-    for (int t = t0; t < t1; ++t) {
-        const int ty = t / tiles_x, tx = t - ty * tiles_x;
-        float Z;
-        const bool ok = edge_point_ok(L, tx * kTileW + lx, ty * kTileH + ly, w, h, dmin, dmax, Z);
-        cnt += __popc(__ballot_sync(0xffffffffu, ok));
-    }
-    if (lane == 0) wsum[warp] = cnt;
-    __syncthreads();
-    if (warp == 0) {
-        const int v = wsum[lane];
-        int s = v;
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    unsigned m = 0;
+    const bool fast = (x0 + kTileW <= w) && ((w & 7) == 0) && ((((uintptr_t)L.edges) & 7) == 0);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, s, d);
-            if (lane >= d) s += u;
+    for (int r = 0; r < kTileH; ++r) {
+        const int y = y0 + r;
+        if (y >= h) break;
+        unsigned long long e8 = 0;
+        if (fast) {
+            e8 = *(const unsigned long long *)(L.edges + (size_t)y * w + x0);
+        } else {
+            for (int c = 0; c < kTileW && x0 + c < w; ++c) e8 |= (unsigned long long)L.edges[(size_t)y * w + x0 + c] << (8 * c);
         }
-        wsum[lane] = s - v;
-        if (lane == 31) wsum[32] = s;
+        if (!e8) continue;
+#pragma unroll
+        for (int c = 0; c < kTileW; ++c)
+            if ((e8 >> (8 * c)) & 0xffull) m |= 1u << (r * kTileW + c);
     }
-    __syncthreads();
-    int off = wsum[warp];
-    for (int t = t0; t < t1; ++t) {
-        const int ty = t / tiles_x, tx = t - ty * tiles_x;
-        const int x = tx * kTileW + lx, y = ty * kTileH + ly;
-        float Z;
-        const bool ok = edge_point_ok(L, x, y, w, h, dmin, dmax, Z);
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            const int o = off + __popc(m & ((1u << lane) - 1u));
-            if (o < L.pts_cap) {
-                const float X = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)x, L.cx)), L.fx);
-                const float Y = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)y, L.cy)), L.fy);
-                L.pts[o] = make_float4(X, Y, Z, 1.0f);
-            }
-        }
-        off += __popc(m);
+    // depth test only where an edge pixel is (isfinite, dmin < Z < dmax: imgpyramidrgbd.cpp:210-214)
+    unsigned keep = 0;
+    for (unsigned mm = m; mm;) {
+        const int b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const float Z = L.depth[(size_t)(y0 + (b >> 3)) * w + x0 + (b & 7)];
+        if (isfinite(Z) && Z > dmin && Z < dmax) keep |= 1u << b;
     }
-    if (threadIdx.x == 0) *L.n_pts = min(wsum[32], L.pts_cap);
+    return keep;
+}
+
+__global__ void __launch_bounds__(256) k_group_mask(const ImgLevel *__restrict__ desc, int w, int h, int tiles_x, int tiles_y, int groups_x,
+                                                    float dmin, float dmax)
+{
+    const int f = blockIdx.z;
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= groups_x * tiles_y) return;
+    const int lane = threadIdx.x & 31;
+    const ImgLevel &L = desc[f];
+    const int ty = g / groups_x, tx = (g - ty * groups_x) * kGroupTiles + lane;
+    unsigned keep = 0;
+    if (tx < tiles_x) {
+        keep = tile_edge_mask(L, tx, ty, w, h, dmin, dmax);
+        ((unsigned *)L.tile_off)[ty * tiles_x + tx] = keep;
+    }
+    const int cnt = __reduce_add_sync(0xffffffffu, __popc(keep));
+    if (lane == 0) L.labels[g] = cnt;
+}
+
+__global__ void __launch_bounds__(256) k_group_scatter(const ImgLevel *__restrict__ desc, int w, int h, int tiles_x, int tiles_y,
+                                                       int groups_x)
+{
+    const int f = blockIdx.z;
+    const int n_groups = groups_x * tiles_y;
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    const int lane = threadIdx.x & 31;
+    const ImgLevel &L = desc[f];
+    const int *__restrict__ gcnt = L.labels;
+    int before = 0;
+    for (int i = lane; i < g; i += 32) before += gcnt[i];
+    before = __reduce_add_sync(0xffffffffu, before);
+    const int ty = g / groups_x, tx = (g - ty * groups_x) * kGroupTiles + lane;
+    const unsigned keep = tx < tiles_x ? ((const unsigned *)L.tile_off)[ty * tiles_x + tx] : 0u;
+    const int c = __popc(keep);
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    int o = before + incl - c;
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    for (unsigned mm = keep; mm; ++o) {
+        const int b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if (o >= L.pts_cap) break;
+        const int x = x0 + (b & 7), y = y0 + (b >> 3);
+        const float Z = L.depth[(size_t)y * w + x];
+        const float X = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)x, L.cx)), L.fx);
+        const float Y = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)y, L.cy)), L.fy);
+        L.pts[o] = make_float4(X, Y, Z, 1.0f);
+    }
+    if (g == n_groups - 1) {
+        const int total = before + __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) *L.n_pts = min(total, L.pts_cap);
+    }
 }
 
 int launch_compact(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, float dmin, float dmax)
 {
     const int tiles_x = cdiv(w, kTileW), tiles_y = cdiv(h, kTileH), n_tiles = tiles_x * tiles_y;
-    if (n >= 8) {
-        k_compact_image<<<n, 1024, 0, ctx->stream>>>(d_desc, w, h, tiles_x, n_tiles, dmin, dmax);
+    const int groups_x = cdiv(tiles_x, kGroupTiles), n_groups = groups_x * tiles_y;
+    // the group counts live in the label plane of the frame (w0*h0 ints); it always holds n_groups <= w*h/4 + h ints
+    if (n >= 8 && (size_t)n_groups <= (size_t)w * h) {
+        dim3 grid(cdiv(n_groups, 8), 1, n);
+        k_group_mask<<<grid, 256, 0, ctx->stream>>>(d_desc, w, h, tiles_x, tiles_y, groups_x, dmin, dmax);
+        LAUNCH_CHECK(ctx);
+        k_group_scatter<<<grid, 256, 0, ctx->stream>>>(d_desc, w, h, tiles_x, tiles_y, groups_x);
         LAUNCH_CHECK(ctx);
         return REVO_OK;
     }

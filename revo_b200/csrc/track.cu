@@ -399,6 +399,25 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
     if (C > 1 || world > 1) cluster.sync();   // nobody may exit while a peer can still write into its shared memory
 }
 
+// Descriptor upload without the copy engine: the host writes the pair descriptors into pinned, device-mapped memory and
+// this kernel pulls them into the workspace.  A cudaMemcpyAsync would queue behind the multi-hundred-megabyte frame
+// uploads of the next batches on the same H2D engine and stall the tracker for milliseconds.
+__global__ void __launch_bounds__(256) k_stage_in(const uint4 *__restrict__ src_mapped_host, uint4 *__restrict__ dst, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src_mapped_host[i];
+}
+
+int launch_stage_in(revo_ctx *ctx, const void *src_mapped_host, void *dst, size_t bytes)
+{
+    const size_t n16 = (bytes + 15) / 16;
+    const int blocks = (int)((n16 + 255) / 256 < 64 ? (n16 + 255) / 256 : 64);
+    k_stage_in<<<blocks < 1 ? 1 : blocks, 256, 0, ctx->stream>>>((const uint4 *)src_mapped_host, (uint4 *)dst, n16);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "k_stage_in launch");
+    ctx->launches++;
+    return REVO_OK;
+}
+
 // ---- launcher -------------------------------------------------------------------
 template <int kThreads, int kMinBlocks>
 static int launch_track_t(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, int ctas_per_pair,

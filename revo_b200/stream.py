@@ -47,10 +47,12 @@ class StreamTracker:
         self.total_evals = 0
         self.total_point_evals = 0          # sum over pairs/levels of n_pts * n_evals (roofline numerator / 60 B)
         self.last = None
-        self._pending = None
+        self._pending = []                  # batches whose upload + build are in flight, oldest first
 
     def start(self, bgr, depth):
         """First frame of every stream: becomes the keyframe (system.cpp:151-175)."""
+        if hasattr(self.be, "reserve"):
+            self.be.reserve(self.B)          # size the device memory pool for the steady state before the first frame
         self.kf = self.be.create(bgr, depth, self.B)
         self.be.wait_created()
         self.be.make_keyframes(self.kf)
@@ -58,16 +60,17 @@ class StreamTracker:
         self.frame = 0
 
     def prefetch(self, bgr, depth):
-        """Start building the pyramids of the NEXT frame: upload + kernels are enqueued asynchronously; with a backend
-        that owns a separate build stream they overlap the tracking of the current frame."""
-        self._pending = self.be.create(bgr, depth, self.B)
+        """Start uploading / building the pyramids of a FUTURE frame: everything is enqueued asynchronously (upload on the
+        backend's copy stream, kernels on its build stream), so it overlaps the tracking of earlier frames.  Call it
+        twice before the first step_pipelined() to keep two frames in flight (upload of k+2 | build of k+1 | track of k)."""
+        self._pending.append(self.be.create(bgr, depth, self.B))
 
     def step_pipelined(self, next_bgr=None, next_depth=None):
-        """Track the frame handed to prefetch() earlier and, before doing so, enqueue the build of the frame after it."""
-        cur = self._pending
-        self.be.wait_created()                       # frame k is complete on the build stream
-        self._pending = self.be.create(next_bgr, next_depth, self.B) if next_bgr is not None else None
-        return self._track(cur)
+        """Enqueue the upload + build of one more future frame, then track the oldest frame in flight.  No host wait for
+        the build: the tracking stream waits for the batch's build-complete event on the device."""
+        if next_bgr is not None:
+            self._pending.append(self.be.create(next_bgr, next_depth, self.B))
+        return self._track(self._pending.pop(0))
 
     def step(self, bgr, depth):
         """Build the pyramids of the next frame of every stream and track it against its keyframe."""
@@ -102,10 +105,11 @@ class StreamTracker:
         return out
 
     def close(self):
-        for h in (self.prev, self.kf, self._pending):
+        for h in [self.prev, self.kf] + list(self._pending):
             if h is not None:
                 self.be.destroy(h)
-        self.prev = self.kf = self._pending = None
+        self.prev = self.kf = None
+        self._pending = []
 
 
 class CudaBackend:
@@ -122,6 +126,15 @@ class CudaBackend:
         self.settings = settings
         self.tracker = api.TrackerNew(ctx, tracker_settings or api.TrackerSettings(), settings)
         self.campyr = api.CameraPyr(settings)
+
+    def reserve(self, n_streams: int):
+        """Steady state of a stream batch: keyframe + previous + current (+ one being built) frame slabs and two
+        generations of keyframe structures (the new one is built before the old one is released)."""
+        px = sum((self.settings.width >> l) * (self.settings.height >> l) for l in range(self.settings.nLevels()))
+        frame = px * (1 + 4 + 1 + 1 + 8) + self.settings.width * self.settings.height * 5 + 65536    # gray, depth, edges x2, list; labels + counters
+        kf = px * 36 + 4096
+        total = int(n_streams * (5 * frame + 2 * kf + self.settings.width * self.settings.height * 3) * 1.1) + (64 << 20)
+        self.ctx.reserve(total)
 
     def create(self, bgr, depth, n):
         return self.api.PyramidBatch(self.build_ctx, self.settings, bgr, depth, n, channels=3, cameraPyr=self.campyr)
@@ -140,4 +153,4 @@ class CudaBackend:
         return dict(R=R, T=out["t"], status=out["status"], n_evals=out["n_evals"], n_pts=out["n_pts"], error=out["error"])
 
     def destroy(self, handles):
-        handles.destroy()
+        handles.destroy(self.ctx)     # on the tracking stream (past the last use), not behind the builds in flight
