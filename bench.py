@@ -121,6 +121,8 @@ class OracleBackend:
         self.ocfg = self.orc.default_cfg()
 
     def create(self, bgr, depth, n):
+        if depth.dtype == np.uint16:     # the reference's reader: depth.convertTo(CV_32FC1, 1.0f / DEPTH_SCALE_FACTOR), iowrapperRGBD.cpp:327
+            depth = depth.astype(np.float32) * (np.float32(1.0) / np.float32(5000.0))
         return [self.O.build_pyramid(self.orc, self.cfg, self.cam, bgr[i], depth[i]) for i in range(n)]
 
     def wait_created(self):
@@ -208,7 +210,8 @@ def main():
         O.build()
         import cv2
 
-        r = run_cpu(args, bgr.numpy(), depth.numpy(), cam, S, K, W, fidx)
+        depth16 = np.round(depth.numpy().astype(np.float64) * 5000.0).astype(np.uint16)   # the wire format (TUM 16-bit depth)
+        r = run_cpu(args, bgr.numpy(), depth16, cam, S, K, W, fidx)
         er, et = pose_errors(r["T_w_c"], poses, fidx(W + K))
         fps = r["frames"] / r["seconds"]
         cores = os.cpu_count()
@@ -253,6 +256,13 @@ def main():
     cam, poses = synth_torch.render_streams(seeds, n_frames, w, h, torch.device("cuda", local_rank), bgr_h, depth_h)
     bgr_d = bgr_h.to(torch.device("cuda", local_rank))
     depth_d = depth_h.to(torch.device("cuda", local_rank))
+    # the sensor / dataset wire format of the depth (TUM: 16-bit, 5000 units per metre): what the end-to-end run uploads
+    depth16_h = torch.empty((n_frames, B, h, w), dtype=torch.int16).pin_memory()
+    for fi in range(n_frames):
+        z = (depth_d[fi].double() * 5000.0).round().to(torch.int32)
+        back = (z.double() * float(np.float32(1.0) / np.float32(5000.0))).float()
+        assert torch.equal(back, depth_d[fi]), "16-bit depth does not reproduce the float depth bit for bit"
+        depth16_h[fi].copy_(z.to(torch.int16))     # two's-complement wrap: the same 16 bits as uint16
     torch.cuda.synchronize()
 
     fx, fy, cx, cy, _, _ = cam
@@ -330,7 +340,8 @@ def main():
     note("device-resident run done; host ms per step: " + " ".join(f"{x:.2f}" for x in dev_run["step_wall"]))
     # pinned host inputs, H2D inside the timed region; the upload + pyramid build of frame k+1 run on a second stream
     # while frame k is tracked (same public API, two contexts)
-    host_run = timed_run(bgr_h, depth_h, sample_clocks=False, pipelined=not args.no_pipeline)
+    host_run = timed_run(bgr_h, depth16_h, sample_clocks=False, pipelined=not args.no_pipeline)
+    host_run_f32 = timed_run(bgr_h, depth_h, sample_clocks=False, pipelined=not args.no_pipeline)   # float-depth interface
     note("host-input (e2e) run done; host ms per step: " + " ".join(f"{x:.2f}" for x in host_run["step_wall"]))
     # kernel-level numbers (phase times, roofline of k_track) from a pass in which nothing else runs beside the kernel being
     # timed: same workload, device-resident, one stream, no overlap
@@ -401,9 +412,13 @@ def main():
                                       "overlaps the pyramid build of frame k+1 with the tracking of frame k on two streams"},
         "mean_edge_points_per_level": dev_run["n_pts"], "mean_evals_per_level": dev_run["n_evals"],
         "pose_error_vs_ground_truth": {"rot_rad": er, "trans_m": et},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * w * h * 7), "d2h_bytes_per_step": int(B * 128),
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * w * h * 5), "d2h_bytes_per_step": int(B * 128),
+                "input": "pinned host bgr u8 + raw 16-bit depth (TUM wire format, converted on the device like the reference's reader "
+                         "does on the host); float-depth interface (7 B/px): see float_depth",
+                "float_depth": {"value": frames_all / (host_run_f32["ms"] * 1e-3), "unit": "frames/s",
+                                "h2d_bytes_per_step": int(B * w * h * 7), "ms_per_step": host_run_f32["ms"] / K},
                 "ms_per_step": host_run["ms"] / K, "h2d_link_gbs_measured": h2d_gbs, "upload_ms_last_batch": host_run["upload_ms"],
-                "h2d_floor_ms_per_step": B * w * h * 7 / (h2d_gbs * 1e9) * 1e3},
+                "h2d_floor_ms_per_step": B * w * h * 5 / (h2d_gbs * 1e9) * 1e3},
         "roofline": {"kernel": "k_track (persistent residual/Jacobian/6x6 reduce + LM)", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "algorithmic_bytes": 60.0 * iso_run["point_evals"] / K_iso,
@@ -420,7 +435,7 @@ def main():
         import cv2
 
         S = min(args.ref_streams, B)
-        r = run_cpu(args, bgr_h.numpy(), depth_h.numpy(), cam, S, min(K, 10), 1, fidx)
+        r = run_cpu(args, bgr_h.numpy(), depth16_h.numpy().view(np.uint16), cam, S, min(K, 10), 1, fidx)
         line["cpu_baseline"] = {"value": r["frames"] / r["seconds"], "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                 "gn_iters_per_sec": r["evals"] / r["seconds"],
                                 "sample": f"{S} of the {B} streams x {min(K, 10)} frames ({r['frames']} frames, {r['seconds']:.1f} s); "

@@ -184,6 +184,13 @@ REVO_API int revo_pyr_create(revo_ctx *ctx, const revo_pyr_config *cfg, const re
 REVO_API int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera *cam0, int n,
                                    const uint8_t *bgr, int channels, const float *depth,
                                    const double *timestamps, revo_pyr **pyr_out);
+/* Same with the depth in the sensor / dataset wire format: 16-bit raw values (TUM: 16-bit PNG, 5000 units per metre).
+ * metres = float(raw) * depth_scale with depth_scale = 1.0f / DEPTH_SCALE_FACTOR, i.e. exactly
+ * depth.convertTo(depth, CV_32FC1, 1.0f / depthScaleFactor) of the reference's reader (io/iowrapperRGBD.cpp:327), done on the
+ * device: 2 instead of 4 bytes per pixel cross the host link. */
+REVO_API int revo_pyr_create_batch_u16(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera *cam0, int n,
+                                       const uint8_t *bgr, int channels, const uint16_t *depth_raw, float depth_scale,
+                                       const double *timestamps, revo_pyr **pyr_out);
 /* makeKeyframe() -- imgpyramidrgbd.cpp:231-252: exact L2 EDT + {gx,gy,dt,0} structure, all levels. Idempotent. */
 REVO_API int revo_pyr_make_keyframe(revo_ctx *ctx, revo_pyr *pyr);
 REVO_API int revo_pyr_make_keyframe_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs);

@@ -92,7 +92,7 @@ EXPORTED_SYMBOLS = [
     "revo_pyr_make_keyframe_batch", "revo_pyr_destroy", "revo_pyr_destroy_batch", "revo_pyr_is_keyframe", "revo_pyr_level_camera",
     "revo_pyr_timestamp", "revo_pyr_num_edges", "revo_pyr_download", "revo_pyr_upload_level", "revo_eval",
     "revo_track_level", "revo_track", "revo_track_batch", "revo_ctx_set_track_shape", "revo_split_export",
-    "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve", "revo_ctx_last_upload_ms",
+    "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve", "revo_ctx_last_upload_ms", "revo_pyr_create_batch_u16",
 ]
 
 
@@ -123,6 +123,8 @@ def load_library():
                                     C.c_size_t, C.c_double, C.POINTER(vp)]
     lib.revo_pyr_create_batch.argtypes = [vp, C.POINTER(revo_pyr_config), C.POINTER(revo_camera), i32, vp, i32, vp, vp,
                                           C.POINTER(vp)]
+    lib.revo_pyr_create_batch_u16.argtypes = [vp, C.POINTER(revo_pyr_config), C.POINTER(revo_camera), i32, vp, i32, vp, C.c_float,
+                                              vp, C.POINTER(vp)]
     lib.revo_pyr_make_keyframe.argtypes = [vp, vp]
     lib.revo_pyr_make_keyframe_batch.argtypes = [vp, i32, C.POINTER(vp)]
     lib.revo_pyr_destroy.argtypes = [vp, vp]
@@ -517,13 +519,20 @@ class PyramidBatch:
     __slots__ = ("ctx", "settings", "n", "arr", "campyr", "_alive")
 
     def __init__(self, ctx: Context, settings: ImgPyramidSettings, rgb, depth, n: int, channels: int = 3, timestamps=None,
-                 cameraPyr: Optional[CameraPyr] = None):
+                 cameraPyr: Optional[CameraPyr] = None, depth_scale_factor: float = 5000.0):
+        """depth: float32 metres, or uint16 raw sensor / dataset values (then metres = raw / depth_scale_factor, converted
+        on the device like the reference's reader does on the host, io/iowrapperRGBD.cpp:327)."""
         self.ctx, self.settings, self.n, self.campyr = ctx, settings, n, cameraPyr
         cfg, cam = settings._c_cfg(), settings._c_cam()
         self.arr = (C.c_void_p * n)()
         ts = None if timestamps is None else np.ascontiguousarray(timestamps, np.float64)
-        ctx.check(ctx.lib.revo_pyr_create_batch(ctx.h, C.byref(cfg), C.byref(cam), n, _ptr(rgb), channels, _ptr(depth), _ptr(ts),
-                                                self.arr))
+        if "int16" in str(getattr(depth, "dtype", "")):     # uint16 (numpy / torch), or int16 holding the same bits
+            scale = float(np.float32(1.0) / np.float32(depth_scale_factor))
+            ctx.check(ctx.lib.revo_pyr_create_batch_u16(ctx.h, C.byref(cfg), C.byref(cam), n, _ptr(rgb), channels, _ptr(depth),
+                                                        scale, _ptr(ts), self.arr))
+        else:
+            ctx.check(ctx.lib.revo_pyr_create_batch(ctx.h, C.byref(cfg), C.byref(cam), n, _ptr(rgb), channels, _ptr(depth), _ptr(ts),
+                                                    self.arr))
         self._alive = True
 
     def __len__(self):

@@ -505,11 +505,12 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c)
 __device__ __forceinline__ unsigned rep_byte(unsigned b) { return (b & 0xffu) * 0x01010101u; }
 
 // Requires w % 4 == 0, w >= 8 and a 4-byte aligned gray plane (launch_canny checks).
-__global__ void __launch_bounds__(128) k_canny_nms(const ImgLevel *__restrict__ desc, int w, int h, int low, int high, int wp32)
+__global__ void __launch_bounds__(128) k_canny_nms(const ImgLevel *__restrict__ desc, int w, int h, int low, int high, int wp32,
+                                                   int rows_per_strip /* multiple of 3 */)
 {
     const int f = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int y0 = (blockIdx.y * 4 + warp) * NMS_RS;
+    const int y0 = (blockIdx.y * 4 + warp) * rows_per_strip;
     if (y0 >= h) return;
     const int xw = blockIdx.x * 32 * NMS_PX;          // first column of the warp
     const int x = xw + lane * NMS_PX;                 // first column of the lane
@@ -622,7 +623,7 @@ __global__ void __launch_bounds__(128) k_canny_nms(const ImgLevel *__restrict__ 
     mag_row(y0, rb, rc, ra, mb, dxb, dyb);           // slot b: row y0
     // steady state, unrolled by three so that the register slots rotate without moves:
     //   gray rows held: (rc, ra) = (y, y+1) ; magnitudes held: (ma, mb) = (y-1, y) ; row y+2 is in flight (pv, ph)
-    const int y_end = min(y0 + NMS_RS, h);
+    const int y_end = min(y0 + rows_per_strip, h);
     unsigned pv, ph, qv, qh;
     issue_row(y0 + 2, pv, ph);
     for (int y = y0; y < y_end; y += 3) {
@@ -855,8 +856,10 @@ static int launch_canny_bits(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w
         REVO_CUDA(ctx, cudaMemset2DAsync(d_counts0, counts_stride, 0, (size_t)hist_w * hist_h * sizeof(int), (size_t)n, ctx->stream));
     const int wp64 = cdiv(w, 64), wp32 = 2 * wp64;
     {
-        dim3 grid(cdiv(w, 32 * NMS_PX), cdiv(cdiv(h, NMS_RS), 4), n);
-        k_canny_nms<<<grid, 128, 0, ctx->stream>>>(d_desc, w, h, low, high, wp32);
+        // rows per warp strip: long strips amortise the 2-row prologue, short ones keep the small levels parallel
+        const int rs = h >= 400 ? NMS_RS : (h >= 200 ? 18 : 9);
+        dim3 grid(cdiv(w, 32 * NMS_PX), cdiv(cdiv(h, rs), 4), n);
+        k_canny_nms<<<grid, 128, 0, ctx->stream>>>(d_desc, w, h, low, high, wp32, rs);
         LAUNCH_CHECK(ctx);
     }
     {

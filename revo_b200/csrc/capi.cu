@@ -244,7 +244,7 @@ int revo_ctx_set_track_shape(revo_ctx *ctx, int ctas_per_pair, int threads_per_c
 
 int revo_ctx_set_track_engine(revo_ctx *ctx, int engine, int chunk_points)
 {
-    if (!ctx || engine < 0 || engine > 2 || chunk_points < 0) return REVO_ERR_INVALID_ARG;
+    if (!ctx || engine < 0 || engine > 3 || chunk_points < 0) return REVO_ERR_INVALID_ARG;
     ctx->track_engine = engine;
     ctx->track_chunk_points = chunk_points;
     return REVO_OK;
@@ -291,10 +291,12 @@ static int level_geometry(const revo_pyr_config *cfg, const revo_camera *cam0, L
     return REVO_OK;
 }
 
-int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera *cam0, int n, const uint8_t *bgr,
-                          int channels, const float *depth, const double *timestamps, revo_pyr **pyr_out)
+// depth16 != nullptr: raw 16-bit depth (units of depth_scale metres), converted on the device (K0 k_depth_u16)
+static int create_batch_impl(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera *cam0, int n, const uint8_t *bgr,
+                             int channels, const float *depth, const uint16_t *depth16, float depth_scale,
+                             const double *timestamps, revo_pyr **pyr_out)
 {
-    if (!ctx || !cfg || !cam0 || !bgr || !depth || !pyr_out || n < 1 || (channels != 3 && channels != 4))
+    if (!ctx || !cfg || !cam0 || !bgr || (!depth && !depth16) || !pyr_out || n < 1 || (channels != 3 && channels != 4))
         return REVO_ERR_INVALID_ARG;
     REVO_CUDA(ctx, cudaSetDevice(ctx->device));
     LevelGeom g[REVO_MAX_LEVELS];
@@ -386,7 +388,8 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
         // persistent double buffer: no allocator dependency between this upload and the kernels of the previous batch
         stage_slot = ctx->stage_next;
         ctx->stage_next ^= 1;
-        const size_t need = bgr_frame * (size_t)n;
+        const size_t bgr_bytes = align_up(bgr_frame * (size_t)n, 256);
+        const size_t need = bgr_bytes + (depth16 ? (size_t)w0 * h0 * 2 * (size_t)n : 0);
         if (ctx->stage_bytes[stage_slot] < need) {
             if (ctx->stage[stage_slot]) {
                 cudaStreamSynchronize(ctx->stream);
@@ -400,11 +403,17 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
         }
         if (ctx->stage_used[stage_slot]) cudaStreamWaitEvent(up, ctx->stage_consumed[stage_slot], 0);   // gray of two batches ago
         cudaEventRecord(ctx->ev[6], up);
-        e = cudaMemcpyAsync(ctx->stage[stage_slot], bgr, need, cudaMemcpyHostToDevice, up);
+        e = cudaMemcpyAsync(ctx->stage[stage_slot], bgr, bgr_frame * (size_t)n, cudaMemcpyHostToDevice, up);
         if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memcpy(bgr)"));
         d_bgr = (const uint8_t *)ctx->stage[stage_slot];
+        if (depth16) {
+            uint8_t *d16 = (uint8_t *)ctx->stage[stage_slot] + bgr_bytes;
+            e = cudaMemcpyAsync(d16, depth16, (size_t)w0 * h0 * 2 * (size_t)n, cudaMemcpyHostToDevice, up);
+            if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memcpy(depth16)"));
+            depth16 = (const uint16_t *)d16;
+        }
     }
-    {
+    if (!depth16) {
         const size_t fb = (size_t)w0 * h0 * 4;
         e = cudaMemcpy2DAsync(base + o_depth[0], align_up(fb, 256), depth, fb, fb, (size_t)n, cudaMemcpyDefault, up);
         if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "memcpy(depth)"));
@@ -430,6 +439,7 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
     rc = launch_gray(ctx, d_bgr, (size_t)w0 * channels, channels, bgr_frame, slab->d_desc[0], n, w0, h0);
+    if (!rc && depth16) rc = launch_depth_u16(ctx, depth16, (size_t)w0 * h0, depth_scale, slab->d_desc[0], n, w0 * h0);
     if (stage_slot >= 0) {
         cudaEventRecord(ctx->stage_consumed[stage_slot], ctx->stream);
         ctx->stage_used[stage_slot] = true;
@@ -454,6 +464,21 @@ int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_
     if (cudaEventCreateWithFlags(&slab->ready, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(slab->ready, ctx->stream);
     for (int f = 0; f < n; ++f) pyr_out[f] = pyrs[f];
     return REVO_OK;
+}
+
+int revo_pyr_create_batch(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera *cam0, int n, const uint8_t *bgr,
+                          int channels, const float *depth, const double *timestamps, revo_pyr **pyr_out)
+{
+    if (!depth) return REVO_ERR_INVALID_ARG;
+    return create_batch_impl(ctx, cfg, cam0, n, bgr, channels, depth, nullptr, 0.f, timestamps, pyr_out);
+}
+
+int revo_pyr_create_batch_u16(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera *cam0, int n, const uint8_t *bgr,
+                              int channels, const uint16_t *depth_raw, float depth_scale, const double *timestamps,
+                              revo_pyr **pyr_out)
+{
+    if (!depth_raw) return REVO_ERR_INVALID_ARG;
+    return create_batch_impl(ctx, cfg, cam0, n, bgr, channels, nullptr, depth_raw, depth_scale, timestamps, pyr_out);
 }
 
 int revo_pyr_create(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera *cam0, const uint8_t *bgr, size_t bgr_stride,
@@ -781,7 +806,7 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     const int env_engine = getenv("REVO_TRACK_ENGINE") ? atoi(getenv("REVO_TRACK_ENGINE")) : 0;
     int engine = ctx->track_engine ? ctx->track_engine : env_engine;
     if (prm.split_world > 1) engine = 1;
-    if (engine != 2) engine = 1;
+    if (engine != 2 && engine != 3) engine = 1;
     const size_t b_q = engine == 2 ? align_up(track_queue_workspace_bytes(n, 8 * ctx->prop.multiProcessorCount, nullptr), 256) : 0;
     REVO_CUDA(ctx, cudaMallocAsync((void **)&ws, b_pairs + b_res + b_rec + b_tr + b_tc + 256 + b_q, ctx->stream));
     PairDesc *d_pairs = (PairDesc *)ws;
@@ -799,6 +824,7 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     cudaEventRecord(ctx->ev[4], ctx->stream);
     if (!rc) {
         if (engine == 2) rc = launch_track_queue(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_q, b_q);
+        else if (engine == 3) rc = launch_track_pp(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);
         else rc = launch_track(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);
     }
     cudaEventRecord(ctx->ev[5], ctx->stream);

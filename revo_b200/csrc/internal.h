@@ -80,7 +80,7 @@ struct revo_ctx {
     int stage_next;
     int track_ctas_per_pair;
     int track_threads;
-    int track_engine;        // 0 = automatic, 1 = one cluster per pair (track.cu), 2 = task queue (track_queue.cu)
+    int track_engine;        // 0 = automatic, 1 = one cluster per pair (track.cu), 2 = task queue (track_queue.cu), 3 = ping-pong clusters (track_pp.cu)
     int track_chunk_points;  // queue engine: minimum points per task (0 = automatic)
     cudaEvent_t ev[8];      // pyramid begin/end, keyframe begin/end, track kernel begin/end, upload begin/end (copy stream)
     bool ev_valid[4];
@@ -120,6 +120,7 @@ int cuda_fail(revo_ctx *ctx, cudaError_t e, const char *what);
 // All launchers are asynchronous on ctx->stream and batched over n frames (d_desc: device table).
 int launch_gray(revo_ctx *ctx, const uint8_t *d_bgr, size_t stride, int ch, size_t frame_bytes, const ImgLevel *d_desc,
                 int n, int w, int h);
+int launch_depth_u16(revo_ctx *ctx, const uint16_t *d_raw, size_t frame_px, float scale, const ImgLevel *d_desc, int n, int px);
 int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst,
                          int w_src, int h_src);
 // gray_tmap: host pointer to a CUtensorMap made by make_gray_tensor_map (nullptr = plain loads)
@@ -170,6 +171,10 @@ int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const Trac
                  int *d_work_counter);
 
 int launch_stage_in(revo_ctx *ctx, const void *src_mapped_host, void *dst, size_t bytes);
+
+// ---- track_pp.cu: cluster engine with warp-specialised CTAs working on two pairs at once ---------------
+int launch_track_pp(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, revo_track_result *d_results,
+                    double *d_records, revo_trace_entry *d_trace, int *d_trace_counts, int *d_work_counter);
 
 // ---- track_queue.cu ----------------------------------------------------------
 // Task-queue engine: device workspace size for n_pairs (ring + pair states + partial tables) and the launcher.

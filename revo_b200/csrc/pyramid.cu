@@ -71,6 +71,40 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ bgr, s
     }
 }
 
+// K0: raw 16-bit depth -> metres, float(z) * scale with one rounding: what cv::Mat::convertTo(CV_32FC1, 1.0f / DEPTH_SCALE_FACTOR)
+// computes in the reference's reader (io/iowrapperRGBD.cpp:327).  8 pixels per thread (one 128-bit load, two 128-bit stores).
+__global__ void __launch_bounds__(256) k_depth_u16(const uint16_t *__restrict__ raw, size_t frame_px, float scale,
+                                                   const ImgLevel *__restrict__ desc, int px)
+{
+    const int f = blockIdx.z;
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i0 >= px) return;
+    const uint16_t *src = raw + (size_t)f * frame_px + i0;
+    float *dst = desc[f].depth + i0;
+    if (i0 + 8 <= px && ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 15) == 0)) {
+        const uint4 v = __ldg((const uint4 *)src);
+        const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[2 * k] = __fmul_rn((float)(wv[k] & 0xffffu), scale);
+            o[2 * k + 1] = __fmul_rn((float)(wv[k] >> 16), scale);
+        }
+        *(float4 *)dst = make_float4(o[0], o[1], o[2], o[3]);
+        *(float4 *)(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+        for (int k = 0; k < 8 && i0 + k < px; ++k) dst[k] = __fmul_rn((float)src[k], scale);
+    }
+}
+
+int launch_depth_u16(revo_ctx *ctx, const uint16_t *d_raw, size_t frame_px, float scale, const ImgLevel *d_desc, int n, int px)
+{
+    dim3 grid(cdiv(cdiv(px, 8), 256), 1, n);
+    k_depth_u16<<<grid, 256, 0, ctx->stream>>>(d_raw, frame_px, scale, d_desc, px);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
 int launch_gray(revo_ctx *ctx, const uint8_t *d_bgr, size_t stride, int ch, size_t frame_bytes, const ImgLevel *d_desc,
                 int n, int w, int h)
 {
@@ -109,23 +143,25 @@ __global__ void __launch_bounds__(256) k_pyrdown(const ImgLevel *__restrict__ sr
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
         const uint8_t *__restrict__ row = in + (size_t)reflect101(2 * y - 2 + r, hs) * ws;
-        int b[16];
         if (fast) {
+            // 16-byte window (columns c0 .. c0+15) as four words; output k is centred on byte 2k+4: the bytes 2k+2 .. 2k+5
+            // times (1,4,6,4) are one DP4A on a PRMT-aligned word, plus byte 2k+6
             const uint32_t *q = (const uint32_t *)(row + c0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t v = __ldg(q + k);
-                b[4 * k] = v & 255; b[4 * k + 1] = (v >> 8) & 255; b[4 * k + 2] = (v >> 16) & 255; b[4 * k + 3] = v >> 24;
-            }
+            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
+            constexpr unsigned kW = 0x04060401u;
+            hsum[r][0] = (int)__dp4a(__byte_perm(w0, w1, 0x5432), kW, (w1 >> 16) & 255u);
+            hsum[r][1] = (int)__dp4a(w1, kW, w2 & 255u);
+            hsum[r][2] = (int)__dp4a(__byte_perm(w1, w2, 0x5432), kW, (w2 >> 16) & 255u);
+            hsum[r][3] = (int)__dp4a(w2, kW, w3 & 255u);
         } else {
+            int b[16];
 #pragma unroll
             for (int i = 2; i <= 12; ++i) b[i] = row[reflect101(c0 + i, ws)];
-            b[0] = b[1] = b[13] = b[14] = b[15] = 0;
-        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = 2 * k + 4;
-            hsum[r][k] = b[i - 2] + 4 * b[i - 1] + 6 * b[i] + 4 * b[i + 1] + b[i + 2];
+            for (int k = 0; k < 4; ++k) {
+                const int i = 2 * k + 4;
+                hsum[r][k] = b[i - 2] + 4 * b[i - 1] + 6 * b[i] + 4 * b[i + 1] + b[i + 2];
+            }
         }
     }
     uint32_t o = 0;
@@ -223,16 +259,22 @@ __global__ void __launch_bounds__(256) k_fill_in(const ImgLevel *__restrict__ de
     const int f = blockIdx.z;
     const ImgLevel L = desc[f];
     const float frac = __fdiv_rn((float)(*L.nz_patches), (float)(L.hist_w * L.hist_h));
-    if (!(frac < n_percentage)) return;
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (ox >= w || oy >= h) return;
-    const int xx = 2 * ox + 1, yy = 2 * oy + 1;
+    if (!(frac < n_percentage)) return;      // the usual case: the whole CTA leaves (few CTAs: 8 rows per thread)
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ox >= w) return;
     const int wt = top[f].w, ht = top[f].h;
-    if (xx >= wt || yy >= ht) return;
-    const int py = yy / P_low, px = xx / P_low;
-    if (py >= L.hist_h || px >= L.hist_w) return;
-    if ((double)L.hist[(size_t)py * L.hist_w + px] < (double)(P * P) * 0.05) {
-        if (top[f].edges[(size_t)yy * wt + xx]) L.edges[(size_t)oy * w + ox] = 255;
+    const int xx = 2 * ox + 1;
+    if (xx >= wt) return;
+    const int px = xx / P_low;
+    if (px >= L.hist_w) return;
+    for (int oy = (blockIdx.y * blockDim.y + threadIdx.y) * 8, k = 0; k < 8 && oy < h; ++k, ++oy) {
+        const int yy = 2 * oy + 1;
+        if (yy >= ht) break;
+        const int py = yy / P_low;
+        if (py >= L.hist_h) break;
+        if ((double)L.hist[(size_t)py * L.hist_w + px] < (double)(P * P) * 0.05) {
+            if (top[f].edges[(size_t)yy * wt + xx]) L.edges[(size_t)oy * w + ox] = 255;
+        }
     }
 }
 
@@ -243,7 +285,7 @@ int launch_hist_fill(revo_ctx *ctx, const ImgLevel *d_desc, const ImgLevel *d_to
     if (hist_w > 0 && hist_h > 0) {
         // the histogram itself is produced by the Canny output kernel (canny.cu: k_canny_final + k_hist_finalize)
         if (do_fill) {
-            dim3 block(32, 8), g2(cdiv(w, 32), cdiv(h, 8), n);
+            dim3 block(32, 8), g2(cdiv(w, 32), cdiv(h, 64), n);
             k_fill_in<<<g2, block, 0, ctx->stream>>>(d_desc, d_top, w, h, patch, patch_low, n_percentage);
             LAUNCH_CHECK(ctx);
         }

@@ -48,34 +48,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 
-// ---- mbarrier / st.async PTX (cluster exchange without a cluster-wide fence) ---------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-// 8 bytes into the shared memory of CTA `dst_rank` of this cluster (same offset as `local_ptr`), completing 8 bytes of
-// the transaction count of that CTA's mbarrier (same offset as `local_bar`): STAS.64 on sm_100a.
-__device__ __forceinline__ void st_async_b64(void *local_ptr, unsigned dst_rank, unsigned long long v, uint64_t *local_bar)
-{
-    uint32_t ra, rb;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(dst_rank));
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(dst_rank));
-    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(ra), "l"(v), "r"(rb) : "memory");
-}
-
 // ---- the kernel ---------------------------------------------------------------
 // Dynamic shared memory: the thread-private cache of the level's 3-D points, float[3][pcap][kThreads] (x, y, z planes):
 // thread t keeps the first `pcap` of ITS points of the current level there for all evaluations of the level, so an

@@ -73,6 +73,11 @@ public:
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;
     revo_ctx *handle() const { return h_; }
+    // pre-size the device memory pool for the steady state of a stream (revo_ctx_reserve)
+    void reserve(size_t bytes) const { check(revo_ctx_reserve(h_, bytes)); }
+    // 0 = automatic, 1 = one thread-block cluster per pair, 2 = chip-wide task queue (revo_ctx_set_track_engine)
+    void setTrackEngine(int engine, int chunk_points = 0) const { check(revo_ctx_set_track_engine(h_, engine, chunk_points)); }
+    void synchronize() const { check(revo_ctx_synchronize(h_)); }
     void check(int rc) const {
         if (!rc) return;
         std::string msg = revo_strerror(rc);

@@ -51,14 +51,14 @@ def main():
 
     # (name, engine, ctas_per_pair, threads, chunk_points, env)
     configs = [
-        ("cluster C8 T128 pf1", 1, 8, 128, 0, {"REVO_TRACK_PREFETCH": "1"}),
-        ("cluster C8 T128 pf0", 1, 8, 128, 0, {"REVO_TRACK_PREFETCH": "0"}),
-        ("cluster C4 T256 pf1", 1, 4, 256, 0, {"REVO_TRACK_PREFETCH": "1"}),
-        ("cluster C4 T256 pf0", 1, 4, 256, 0, {"REVO_TRACK_PREFETCH": "0"}),
-        ("cluster C4 T128 pf1", 1, 4, 128, 0, {"REVO_TRACK_PREFETCH": "1"}),
-        ("cluster C2 T256 pf1", 1, 2, 256, 0, {"REVO_TRACK_PREFETCH": "1"}),
-        ("cluster C8 T128 pf1 pcap12", 1, 8, 128, 0, {"REVO_TRACK_PREFETCH": "1", "REVO_TRACK_PCAP": "12"}),
-        ("cluster C8 T128 pf1 pcap24", 1, 8, 128, 0, {"REVO_TRACK_PREFETCH": "1", "REVO_TRACK_PCAP": "24"}),
+        ("cluster C8 T128", 1, 8, 128, 0, {}),
+        ("pingpong C8", 3, 8, 0, 0, {}),
+        ("pingpong C4", 3, 4, 0, 0, {}),
+        ("pingpong C8 pcap6", 3, 8, 0, 0, {"REVO_TRACK_PCAP": "6"}),
+        ("pingpong C8 pcap16", 3, 8, 0, 0, {"REVO_TRACK_PCAP": "16"}),
+        ("pingpong C8 max37", 3, 8, 0, 0, {"REVO_TRACK_MAX_CLUSTERS": "37"}),
+        ("pingpong C16", 3, 16, 0, 0, {}),
+        ("queue T128 s512 o2", 2, 0, 128, 0, {}),
     ]
     if args.configs:
         keep = set(int(x) for x in args.configs.split(","))
@@ -103,14 +103,14 @@ def main():
     os.environ["REVO_TRACK_PROF"] = "1"
     for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS", "REVO_TRACK_PREFETCH"):
         os.environ.pop(k, None)
-    for eng in (2, 1):
+    for eng in (1,):
         ctx.set_track_engine(eng, 0)
         ctx.set_track_shape(0, 0)
         trk.trackFramesBatch(Rs, Ts, kf, cur)
     os.environ.pop("REVO_TRACK_PROF")
     for nb in (1, 8, 32, 64, B):
         sub_k = api.PyramidBatch.__new__(api.PyramidBatch)
-        for eng in (2, 1):
+        for eng in (3, 1):
             ctx.set_track_engine(eng, 0)
             refs = [kf[i] for i in range(nb)]
             curs = [cur[i] for i in range(nb)]

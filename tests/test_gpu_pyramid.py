@@ -133,3 +133,32 @@ def test_bgra_input_and_errors(ctx, orc32):
     with pytest.raises(api.RevoError) as ei:
         pg.returnGray(5)
     assert ei.value.code == 6
+
+
+def test_uint16_depth_wire_format(ctx, orc32):
+    """16-bit raw depth (TUM wire format) converted on the device == float(raw) * (1.0f / 5000) with one rounding per
+    pixel, i.e. cv::Mat::convertTo(CV_32FC1, 1.0f / DEPTH_SCALE_FACTOR) of the reference's reader
+    (io/iowrapperRGBD.cpp:327; checked here against cv2.multiply); the pyramids are then identical."""
+    import cv2
+
+    from revo_b200 import api
+
+    ps = [synth_pair(s) for s in (1, 2)]
+    bgr = np.stack([p["key"][0] for p in ps])
+    raw = np.stack([np.round(p["key"][1].astype(np.float64) * 5000.0).astype(np.uint16) for p in ps])
+    raw[0, :7, :13] = 65535
+    st = _settings(ps[0]["cam"], 3)
+    scale = np.float32(1.0) / np.float32(5000.0)
+    depth_host = raw.astype(np.float32) * scale
+    assert np.array_equal(depth_host[0], cv2.multiply(raw[0].astype(np.float32), float(scale)))
+    b16 = api.PyramidBatch(ctx, st, bgr, raw, 2, depth_scale_factor=5000.0)
+    b32 = api.PyramidBatch(ctx, st, bgr, depth_host, 2)
+    ctx.synchronize()
+    for i in range(2):
+        for l in range(3):
+            assert np.array_equal(b16[i].returnDepth(l), b32[i].returnDepth(l)), (i, l)
+            assert np.array_equal(b16[i].returnEdges(l), b32[i].returnEdges(l))
+            assert np.array_equal(b16[i].return3DEdges(l), b32[i].return3DEdges(l))
+    assert np.array_equal(b16[0].returnDepth(0), depth_host[0])
+    b16.destroy()
+    b32.destroy()

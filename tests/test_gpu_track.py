@@ -16,10 +16,11 @@ from conftest import rot_angle, synth_pair
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["queue", "cluster"], autouse=True)
+@pytest.fixture(params=["cluster", "pingpong", "queue"], autouse=True)
 def engine(request, ctx):
-    """Every test of this file runs on both tracking engines (task queue: track_queue.cu, cluster per pair: track.cu)."""
-    ctx.set_track_engine(2 if request.param == "queue" else 1, 0)
+    """Every test of this file runs on all tracking engines (cluster per pair: track.cu, warp-specialised clusters working
+    on two pairs: track_pp.cu, task queue: track_queue.cu)."""
+    ctx.set_track_engine({"cluster": 1, "queue": 2, "pingpong": 3}[request.param], 0)
     yield request.param
     ctx.set_track_engine(0, 0)
 
