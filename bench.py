@@ -36,11 +36,11 @@ if ROOT not in sys.path:
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=128, help="independent streams (frames per step) per GPU")
-    ap.add_argument("--ref-streams", type=int, default=32, help="streams per step of the CPU reference arm / cpu_baseline")
+    ap.add_argument("--ref-streams", type=int, default=64, help="streams per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--levels", type=int, default=4)
@@ -66,7 +66,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -435,10 +435,10 @@ def main():
         import cv2
 
         S = min(args.ref_streams, B)
-        r = run_cpu(args, bgr_h.numpy(), depth16_h.numpy().view(np.uint16), cam, S, min(K, 10), 1, fidx)
+        r = run_cpu(args, bgr_h.numpy(), depth16_h.numpy().view(np.uint16), cam, S, min(K, 40), 1, fidx)
         line["cpu_baseline"] = {"value": r["frames"] / r["seconds"], "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                 "gn_iters_per_sec": r["evals"] / r["seconds"],
-                                "sample": f"{S} of the {B} streams x {min(K, 10)} frames ({r['frames']} frames, {r['seconds']:.1f} s); "
+                                "sample": f"{S} of the {B} streams x {min(K, 40)} frames ({r['frames']} frames, {r['seconds']:.1f} s); "
                                           f"cv2 {cv2.__version__} ({cv2.getNumThreads()} threads) + C port of the reference loops/tracker"}
     print(json.dumps(line))
     sys.stderr.write(f"[bench] {value:.0f} frames/s (e2e {e2e:.0f}), {line['gn_iters_per_sec']:.0f} GN-iters/s, step {dev_run['ms'] / K:.2f} ms = "

@@ -126,8 +126,15 @@ __device__ __forceinline__ int reflect101(int i, int n)
 }
 
 // Register-tiled: one thread -> 4 horizontally adjacent outputs of one row.  Per input row (5 of them) the 11 bytes it
-// needs come from four aligned 32-bit loads (columns 2x-4 .. 2x+11); the 2.5-fold vertical reuse of input rows between
-// neighbouring output rows is served by L1.  Border threads take a byte-wise path with the REFLECT_101 index map.
+// needs come from four aligned 32-bit loads (columns 2x-4 .. 2x+11); the horizontal [1 4 6 4 1] of an output is one
+// DP4A on a PRMT-aligned word plus one byte; the 2.5-fold vertical reuse of input rows between neighbouring output rows
+// is served by L1.  BORDER_REFLECT_101 without divergence: the first thread of a row synthesises its left halo word
+// from its own first word (columns -2,-1 = columns 2,1), the last one takes column ws from column ws-2.
+__device__ __forceinline__ int reflect101_near(int i, int n)   // |overshoot| <= 2 < n
+{
+    return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i);
+}
+
 __global__ void __launch_bounds__(256) k_pyrdown(const ImgLevel *__restrict__ src, const ImgLevel *__restrict__ dst, int ws,
                                                  int hs, int wd, int hd)
 {
@@ -138,22 +145,29 @@ __global__ void __launch_bounds__(256) k_pyrdown(const ImgLevel *__restrict__ sr
     const uint8_t *__restrict__ in = src[f].gray;
     uint8_t *__restrict__ out = dst[f].gray;
     const int c0 = 2 * x0 - 4;   // column of byte 0 of the 16-byte window
-    const bool fast = (c0 >= 0) && (c0 + 16 <= ws) && ((ws & 3) == 0) && ((((uintptr_t)in) & 3) == 0) && (x0 + 4 <= wd);
+    // vector path: ws a multiple of 8 (so wd = ws/2 is a multiple of 4 and every thread owns 4 outputs), >= 16, aligned
+    const bool vec = ((ws & 7) == 0) && ws >= 16 && ((((uintptr_t)in) & 3) == 0) && hs >= 4;
     int hsum[5][4];
+    if (vec) {
+        const bool left = c0 < 0, right = c0 + 16 > ws;    // at most one of them (ws >= 16)
+        constexpr unsigned kW = 0x04060401u;
 #pragma unroll
-    for (int r = 0; r < 5; ++r) {
-        const uint8_t *__restrict__ row = in + (size_t)reflect101(2 * y - 2 + r, hs) * ws;
-        if (fast) {
-            // 16-byte window (columns c0 .. c0+15) as four words; output k is centred on byte 2k+4: the bytes 2k+2 .. 2k+5
-            // times (1,4,6,4) are one DP4A on a PRMT-aligned word, plus byte 2k+6
-            const uint32_t *q = (const uint32_t *)(row + c0);
-            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
-            constexpr unsigned kW = 0x04060401u;
+        for (int r = 0; r < 5; ++r) {
+            const uint32_t *q = (const uint32_t *)(in + (size_t)reflect101_near(2 * y - 2 + r, hs) * ws + c0);
+            const uint32_t w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+            uint32_t w0, w3;
+            if (left) w0 = __byte_perm(w1, 0u, 0x1200); else w0 = __ldg(q);            // bytes 2,3 = columns 2,1
+            if (right) w3 = (w2 >> 16) & 255u; else w3 = __ldg(q + 3);                // byte 0 = column ws-2
+            // output k is centred on byte 2k+4: bytes 2k+2 .. 2k+5 times (1,4,6,4) + byte 2k+6
             hsum[r][0] = (int)__dp4a(__byte_perm(w0, w1, 0x5432), kW, (w1 >> 16) & 255u);
             hsum[r][1] = (int)__dp4a(w1, kW, w2 & 255u);
             hsum[r][2] = (int)__dp4a(__byte_perm(w1, w2, 0x5432), kW, (w2 >> 16) & 255u);
             hsum[r][3] = (int)__dp4a(w2, kW, w3 & 255u);
-        } else {
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const uint8_t *__restrict__ row = in + (size_t)reflect101(2 * y - 2 + r, hs) * ws;
             int b[16];
 #pragma unroll
             for (int i = 2; i <= 12; ++i) b[i] = row[reflect101(c0 + i, ws)];

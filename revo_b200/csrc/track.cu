@@ -140,7 +140,12 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 if (tid < world) st_release_sys(&((Mailbox *)prm.split_peers[tid])->flag[par][prm.split_rank], fl);
                 Mailbox *mine_mb = (Mailbox *)prm.split_peers[prm.split_rank];
                 if (tid < world) {
-                    while (ld_acquire_sys(&mine_mb->flag[par][tid]) < fl) { }
+                    // watchdog (~5 s): a peer that never launches must not hang this GPU; the result is then invalid
+                    // (ranks disagree), which the caller's cross-rank check catches
+                    const long long t0 = clock64();
+                    while (ld_acquire_sys(&mine_mb->flag[par][tid]) < fl) {
+                        if (clock64() - t0 > 10000000000ll) break;
+                    }
                 }
                 __syncwarp();
                 double tot = 0;
