@@ -229,6 +229,25 @@ REVO_API int revo_track(revo_ctx *ctx, const revo_tracker_config *cfg, const rev
 REVO_API int revo_track_batch(revo_ctx *ctx, const revo_tracker_config *cfg, int n, revo_pyr *const *refs,
                               revo_pyr *const *curs, const float *R9s, const float *t3s, revo_track_result *results,
                               revo_trace_entry *trace, int trace_cap, int *trace_counts);
+/* TrackerNew::assessTrackingQuality -- system/tracker.cpp:118-201 (Schenk & Fraundorfer, IROS 2017): the 3-D edge points of
+ * up to n_frames_voting past frames (their level-`hist_level` lists, tracker.cpp:173,259 of system.cpp feed
+ * return3DEdges(histogramLevel)) are projected into the current frame with  inv(estimated_pose) * past_world_pose[i];
+ * every past frame marks each pixel at most once (M_i), M = sum M_i; over the pixels of the current frame with a valid
+ * depth, histogram[M] counts pixels and overlaps[M] those that are Canny edges (returnOrigEdges).  The vote:
+ * overlap_measure = sum_{k>0} overlaps[k] * {0, 1, 1.25, 1.5}[k];  OK if overlap_measure >= overlaps[0] or fewer than 3 past
+ * frames took part, else NEW_KF.  Poses are column-major 4x4 floats (Eigen::Matrix4f::data()). */
+typedef struct revo_quality_result {
+    int32_t histogram[4];
+    int32_t overlaps[4];
+    float overlap_measure;
+    int32_t status;        /* REVO_TRACKER_STATE_OK or REVO_TRACKER_STATE_NEW_KF */
+    int32_t out_of_bounds; /* projections that left the image (the reference only logs it) */
+    int32_t n_frames;      /* past frames that took part: min(n_past, n_frames_voting) */
+} revo_quality_result;
+REVO_API int revo_track_quality(revo_ctx *ctx, const revo_pyr *cur, int hist_level, int n_past, revo_pyr *const *past,
+                                const float *past_world_poses16, const float *estimated_pose16, int n_frames_voting,
+                                revo_quality_result *out);
+
 /* Launch-shape override for revo_track_batch (0 = automatic): CTAs per pair (cluster size 1,2,4,8,16)
  * and threads per CTA. */
 REVO_API int revo_ctx_set_track_shape(revo_ctx *ctx, int ctas_per_pair, int threads_per_cta);

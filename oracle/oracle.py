@@ -442,3 +442,44 @@ def make_keyframe(orc: Oracle, pyr: Pyramid, backend: str = "cv2") -> None:
             dt = orc.edt(pyr.edges[lvl])
         pyr.dt.append(dt)
         pyr.opt.append(orc.build_opt_structure(dt))  # :245
+
+
+def assess_tracking_quality(past_pts, past_world_poses, estimated_pose, cam, depth, edges_orig, depth_min=0.1, depth_max=5.2,
+                            n_frames_voting=3):
+    """CPU restatement (numpy, float32 in the reference's operation order) of TrackerNew::assessTrackingQuality,
+    system/tracker.cpp:118-201.  past_pts: list of (N_i, 4) float32 3-D edge lists (return3DEdges(histogramLevel)),
+    past_world_poses: list of 4x4, cam = (fx, fy, cx, cy, w, h) of the histogram level, depth / edges_orig of the current frame
+    at that level.  Returns dict(histogram, overlaps, overlap_measure, status, out_of_bounds)."""
+    f32 = np.float32
+    fx, fy, cx, cy, w, h = cam
+    fx, fy, cx, cy = f32(fx), f32(fy), f32(cx), f32(cy)
+    w, h = int(w), int(h)
+    nf = min(len(past_pts), int(n_frames_voting), 3)
+    M = np.zeros((h, w), np.int32)
+    oob = 0
+    est_inv = np.linalg.inv(np.asarray(estimated_pose, np.float32).astype(np.float64))
+    for f in range(nf):
+        tr = (est_inv @ np.asarray(past_world_poses[f], np.float32).astype(np.float64)).astype(f32)      # tracker.cpp:147
+        R, T = tr[:3, :3], tr[:3, 3]
+        p = np.asarray(past_pts[f], f32)
+        x, y, z = p[:, 0], p[:, 1], p[:, 2]
+        X = ((R[0, 0] * x + R[0, 1] * y) + R[0, 2] * z) + T[0]
+        Y = ((R[1, 0] * x + R[1, 1] * y) + R[1, 2] * z) + T[1]
+        Z = ((R[2, 0] * x + R[2, 1] * y) + R[2, 2] * z) + T[2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = (fx * X) / Z + cx                                                                          # :157-158
+            v = (fy * Y) / Z + cy
+        inb = (u >= 0) & (u < f32(w)) & (v >= 0) & (v < f32(h))
+        oob += int((~inb).sum())
+        Mi = np.zeros((h, w), np.int32)
+        Mi[np.floor(v[inb]).astype(np.int64), np.floor(u[inb]).astype(np.int64)] = 1                      # one mark per frame and pixel
+        M += Mi
+    d = np.asarray(depth, f32)
+    ok = np.isfinite(d) & (d > f32(depth_min)) & (d < f32(depth_max))                                     # isPointOkDepth
+    e = np.asarray(edges_orig) > 0
+    histogram = [int((ok & (M == k)).sum()) for k in range(4)]
+    overlaps = [int((ok & e & (M == k)).sum()) for k in range(4)]
+    weights = [0.0, 1.0, 1.25, 1.5]
+    measure = float(sum(f32(overlaps[k]) * f32(weights[k]) for k in range(1, nf + 1)))
+    status = 0 if (measure >= overlaps[0] or nf + 1 < 4) else 2                                            # OK / NEW_KF
+    return dict(histogram=histogram, overlaps=overlaps, overlap_measure=measure, status=status, out_of_bounds=oob, n_frames=nf)

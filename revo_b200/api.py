@@ -68,6 +68,11 @@ class revo_track_result(C.Structure):
                 ("n_pts", C.c_int32 * MAX_LEVELS), ("used_identity_init", C.c_int32)]
 
 
+class revo_quality_result(C.Structure):
+    _fields_ = [("histogram", C.c_int32 * 4), ("overlaps", C.c_int32 * 4), ("overlap_measure", C.c_float),
+                ("status", C.c_int32), ("out_of_bounds", C.c_int32), ("n_frames", C.c_int32)]
+
+
 class revo_trace_entry(C.Structure):
     _fields_ = [("error", C.c_float), ("lam", C.c_float), ("accepted", C.c_int32), ("good", C.c_int32),
                 ("bad", C.c_int32), ("level", C.c_int32)]
@@ -92,7 +97,7 @@ EXPORTED_SYMBOLS = [
     "revo_pyr_make_keyframe_batch", "revo_pyr_destroy", "revo_pyr_destroy_batch", "revo_pyr_is_keyframe", "revo_pyr_level_camera",
     "revo_pyr_timestamp", "revo_pyr_num_edges", "revo_pyr_download", "revo_pyr_upload_level", "revo_eval",
     "revo_track_level", "revo_track", "revo_track_batch", "revo_ctx_set_track_shape", "revo_split_export",
-    "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve", "revo_ctx_last_upload_ms", "revo_pyr_create_batch_u16",
+    "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve", "revo_ctx_last_upload_ms", "revo_pyr_create_batch_u16", "revo_track_quality",
 ]
 
 
@@ -141,6 +146,7 @@ def load_library():
     lib.revo_track_batch.argtypes = [vp, C.POINTER(revo_tracker_config), i32, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp,
                                      i32, vp]
     lib.revo_ctx_set_track_shape.argtypes = [vp, i32, i32]
+    lib.revo_track_quality.argtypes = [vp, vp, i32, i32, C.POINTER(vp), vp, vp, i32, C.POINTER(revo_quality_result)]
     lib.revo_ctx_set_track_engine.argtypes = [vp, i32, i32]
     lib.revo_ctx_reserve.argtypes = [vp, C.c_size_t]
     lib.revo_ctx_last_upload_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -255,6 +261,8 @@ class TrackerSettings:
     """system/tracker.h:31-50: USE_EDGE_FILTER defaults to true here (tracker.h:46)."""
     CHECK_INIT_VALUES: bool = True
     optimizerSettings: OptimizerSettings = field(default_factory=lambda: OptimizerSettings(USE_EDGE_FILTER=True))
+    CHECK_TRACKING_RESULTS: bool = True     # tracker.h:45
+    nFramesHistogramVoting: int = 3         # tracker.h:44,47
 
 
 @dataclass
@@ -626,6 +634,9 @@ class TrackerNew:
         self.mSettings = config or TrackerSettings()
         self.mPyrConfig = pyrConfig or ImgPyramidSettings()
         self.histogramLevel = 2
+        # past frames for the tracking-quality vote: (pyramid whose level-histogramLevel 3-D edge list is used, world pose, ts)
+        self.mPastPcl: list = []
+        self.last_quality: Optional[revo_quality_result] = None
 
     def _c_cfg(self) -> revo_tracker_config:
         c = revo_tracker_config()
@@ -670,6 +681,32 @@ class TrackerNew:
                        for k in range(counts[i])] for i in range(n)]
             return out, traces
         return out
+
+    # -- tracking-quality vote (tracker.cpp:118-257) -----------------------------------
+    def addOldPclAndPose(self, pyr: ImgPyramidRGBD, worldPose, timeStamp: float = 0.0):
+        """``addOldPclAndPose(pcl, worldPose, ts)`` (tracker.cpp:209-224).  The reference copies ``return3DEdges(histogramLevel)``
+        of the frame; here the frame's pyramid is kept (its list stays on the device) -- it must outlive the vote."""
+        self.mPastPcl.append((pyr, np.asarray(worldPose, np.float32).reshape(4, 4).copy(), float(timeStamp)))
+
+    def clearUpPastLists(self):
+        """tracker.cpp:249-257"""
+        while len(self.mPastPcl) > self.mSettings.nFramesHistogramVoting:
+            self.mPastPcl.pop(0)
+
+    def assessTrackingQuality(self, estimatedPose, currFrame: ImgPyramidRGBD) -> int:
+        """``TrackerStatus assessTrackingQuality(estimatedPose, currFrame)`` (tracker.cpp:118-201); the counts are kept in
+        ``self.last_quality``."""
+        if not self.mPastPcl or not self.mSettings.CHECK_TRACKING_RESULTS:
+            return TRACKER_STATE_OK
+        n = len(self.mPastPcl)
+        arr = (C.c_void_p * n)(*[p[0].h for p in self.mPastPcl])
+        poses = np.ascontiguousarray(np.stack([p[1].T.reshape(-1) for p in self.mPastPcl]), np.float32)   # column-major
+        est = np.ascontiguousarray(np.asarray(estimatedPose, np.float32).reshape(4, 4).T.reshape(-1))
+        res = revo_quality_result()
+        self.ctx.check(self.ctx.lib.revo_track_quality(self.ctx.h, currFrame.h, self.histogramLevel, n, arr, poses.ctypes.data,
+                                                       est.ctypes.data, self.mSettings.nFramesHistogramVoting, C.byref(res)))
+        self.last_quality = res
+        return int(res.status)
 
     # -- multi-GPU split (one process per GPU) ------------------------------------
     def splitExport(self, rank: int, world: int) -> bytes:

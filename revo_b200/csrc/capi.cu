@@ -942,6 +942,97 @@ int revo_eval(revo_ctx *ctx, const revo_opt_config *cfg, const revo_pyr *ref, co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// tracking-quality vote
+// ---------------------------------------------------------------------------------------------------
+static bool invert4(const double *m /* column-major */, double *inv)
+{
+    // Gauss-Jordan with partial pivoting on [m | I]
+    double a[4][8];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) { a[r][c] = m[c * 4 + r]; a[r][4 + c] = (r == c) ? 1.0 : 0.0; }
+    for (int k = 0; k < 4; ++k) {
+        int piv = k;
+        for (int r = k + 1; r < 4; ++r)
+            if (fabs(a[r][k]) > fabs(a[piv][k])) piv = r;
+        if (fabs(a[piv][k]) < 1e-300) return false;
+        if (piv != k)
+            for (int c = 0; c < 8; ++c) std::swap(a[piv][c], a[k][c]);
+        const double d = 1.0 / a[k][k];
+        for (int c = 0; c < 8; ++c) a[k][c] *= d;
+        for (int r = 0; r < 4; ++r) {
+            if (r == k) continue;
+            const double f = a[r][k];
+            if (f != 0.0)
+                for (int c = 0; c < 8; ++c) a[r][c] -= f * a[k][c];
+        }
+    }
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) inv[c * 4 + r] = a[r][4 + c];
+    return true;
+}
+
+int revo_track_quality(revo_ctx *ctx, const revo_pyr *cur, int hist_level, int n_past, revo_pyr *const *past,
+                       const float *past_world_poses16, const float *estimated_pose16, int n_frames_voting, revo_quality_result *out)
+{
+    if (!ctx || !cur || !out || n_past < 0 || (n_past > 0 && (!past || !past_world_poses16)) || !estimated_pose16)
+        return REVO_ERR_INVALID_ARG;
+    if (hist_level < 0 || hist_level >= cur->n_levels) return REVO_ERR_BAD_LEVEL;
+    memset(out, 0, sizeof(*out));
+    out->status = REVO_TRACKER_STATE_OK;
+    int nf = n_past < n_frames_voting ? n_past : n_frames_voting;
+    if (nf > 3) nf = 3;                        // histWeights has four entries (tracker.cpp:231-234)
+    out->n_frames = nf > 0 ? nf : 0;
+    if (nf <= 0) return REVO_OK;               // tracker.cpp:121: nothing to vote with
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const ImgLevel &L = cur->lv[hist_level];
+    QualityArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_frames = nf; a.fx = L.fx; a.fy = L.fy; a.cx = L.cx; a.cy = L.cy; a.w = L.w; a.h = L.h;
+    double est[16], est_inv[16];
+    for (int i = 0; i < 16; ++i) est[i] = estimated_pose16[i];
+    if (!invert4(est, est_inv)) return REVO_ERR_INVALID_ARG;
+    for (int f = 0; f < nf; ++f) {
+        if (!past[f] || hist_level >= past[f]->n_levels) return REVO_ERR_INVALID_ARG;
+        const float *pw = past_world_poses16 + 16 * (size_t)f;
+        double tr[16];                          // inv(estimatedPose) * pastWorldPose   (tracker.cpp:147)
+        for (int c = 0; c < 4; ++c)
+            for (int r = 0; r < 4; ++r) {
+                double s = 0;
+                for (int k = 0; k < 4; ++k) s += est_inv[k * 4 + r] * (double)pw[c * 4 + k];
+                tr[c * 4 + r] = s;
+            }
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) a.fr[f].R[c * 3 + r] = (float)tr[c * 4 + r];
+        for (int r = 0; r < 3; ++r) a.fr[f].T[r] = (float)tr[12 + r];
+        a.fr[f].pts = past[f]->lv[hist_level].pts;
+        a.fr[f].n_pts = past[f]->lv[hist_level].n_pts;
+        wait_for_build(ctx, past[f]);
+    }
+    wait_for_build(ctx, cur);
+    const size_t words = ((size_t)L.w * L.h + 3) / 4;
+    int rc = ensure_scratch(ctx, words * 4 + 256);
+    if (rc) return rc;
+    unsigned *d_mbits = (unsigned *)ctx->scratch;
+    int *d_counters = (int *)((uint8_t *)ctx->scratch + align_up(words * 4, 64));
+    // returnOrigEdges(histogramLevel): the Canny output before the fill-in (imgpyramidrgbd.h:69-77)
+    const uint8_t *d_edges = (cur->cfg.use_edge_hist && hist_level > 0) ? L.edges_orig : L.edges;
+    rc = launch_quality(ctx, a, L.depth, d_edges, cur->cfg.depth_min, cur->cfg.depth_max, d_mbits, d_counters);
+    if (rc) return rc;
+    int c[16];
+    REVO_CUDA(ctx, cudaMemcpyAsync(c, d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    static const float kHistWeights[4] = {0.f, 1.f, 1.25f, 1.5f};
+    float measure = 0.f;
+    for (int k = 0; k < 4; ++k) { out->histogram[k] = c[k]; out->overlaps[k] = c[4 + k]; }
+    for (int k = 1; k <= nf; ++k) measure += (float)c[4 + k] * kHistWeights[k];     // tracker.cpp:176-181
+    out->overlap_measure = measure;
+    out->out_of_bounds = c[8];
+    // tracker.cpp:183: histogram.size() = 1 + frames that took part
+    out->status = (measure >= (float)c[4] || nf + 1 < 4) ? REVO_TRACKER_STATE_OK : REVO_TRACKER_STATE_NEW_KF;
+    return REVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // multi-GPU split of one pair (one process per GPU; mailboxes exchanged as CUDA IPC handles)
 // ---------------------------------------------------------------------------------------------------
 struct SplitBlob {

@@ -135,6 +135,21 @@ int launch_hist_fill(revo_ctx *ctx, const ImgLevel *d_desc, const ImgLevel *d_to
                      int patch_low, bool do_fill, float n_percentage);
 int launch_compact(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, float dmin, float dmax);
 int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h);
+// tracking-quality vote (revo_track_quality): the past frames' 3-D lists with the transform into the current frame
+struct QualityFrame {
+    const float4 *pts;
+    const int *n_pts;
+    float R[9], T[3];     // column-major R, as Eigen::Matrix3f
+};
+struct QualityArgs {
+    QualityFrame fr[4];
+    int n_frames;
+    float fx, fy, cx, cy;
+    int w, h;
+};
+// d_counters: 16 ints = histogram[4], overlaps[4], out_of_bounds, ...
+int launch_quality(revo_ctx *ctx, const QualityArgs &args, const float *d_depth, const uint8_t *d_edges, float dmin, float dmax,
+                   unsigned *d_mbits, int *d_counters);
 int launch_opt_struct_f4(revo_ctx *ctx, const float *d_dt, int w, int h, float4 *d_out);
 int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uint4 *d_out);
 // reference-order (column-major scan) 3-D edge list into d_out (capacity w*h float4); *d_n receives the count

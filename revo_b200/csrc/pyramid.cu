@@ -701,6 +701,72 @@ int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uin
     return REVO_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Tracking-quality vote (TrackerNew::assessTrackingQuality, system/tracker.cpp:118-201).
+//  k_quality_scatter: one thread per (past frame, 3-D point): newPt = R pt + T, u = fx x / z + cx, v = fy y / z + cy in the
+//      reference's float operation order; in-bounds projections set bit `frame` of the pixel's byte (atomicOr on the
+//      containing word: "prevent coinciding reprojections" -- a frame counts a pixel once), M = popcount.
+//  k_quality_hist: one thread per pixel of the current frame: valid depth -> histogram[M]++, and overlaps[M]++ if the pixel
+//      is a Canny edge; block-level shared counters, one global atomic per counter and block.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_quality_scatter(const QualityArgs a, unsigned *__restrict__ mbits, int *__restrict__ counters)
+{
+    const QualityFrame &F = a.fr[blockIdx.y];
+    const int n = *F.n_pts;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(F.pts + i);
+        // Eigen: R * pt + T (column-major accumulation order), then tracker.cpp:157-158
+        const float X = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.R[0], p.x), __fmul_rn(F.R[3], p.y)), __fmul_rn(F.R[6], p.z)), F.T[0]);
+        const float Y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.R[1], p.x), __fmul_rn(F.R[4], p.y)), __fmul_rn(F.R[7], p.z)), F.T[1]);
+        const float Z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.R[2], p.x), __fmul_rn(F.R[5], p.y)), __fmul_rn(F.R[8], p.z)), F.T[2]);
+        const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.fx, X), Z), a.cx);
+        const float v = __fadd_rn(__fdiv_rn(__fmul_rn(a.fy, Y), Z), a.cy);
+        if (u >= 0.f && u < (float)a.w && v >= 0.f && v < (float)a.h) {
+            const int px = (int)floorf(v) * a.w + (int)floorf(u);
+            atomicOr(mbits + (px >> 2), 1u << ((px & 3) * 8 + blockIdx.y));
+        } else {
+            atomicAdd(counters + 8, 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_quality_hist(const float *__restrict__ depth, const uint8_t *__restrict__ edges,
+                                                      const unsigned *__restrict__ mbits, int n_px, float dmin, float dmax,
+                                                      int *__restrict__ counters)
+{
+    __shared__ int sc[8];
+    if (threadIdx.x < 8) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_px) {
+        const float Z = depth[i];
+        if (isfinite(Z) && Z > dmin && Z < dmax) {     // ImgPyramidRGBD::isPointOkDepth
+            const int val = __popc((mbits[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+            atomicAdd(&sc[val & 3], 1);
+            if (edges[i]) atomicAdd(&sc[4 + (val & 3)], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && sc[threadIdx.x]) atomicAdd(counters + threadIdx.x, sc[threadIdx.x]);
+}
+
+int launch_quality(revo_ctx *ctx, const QualityArgs &a, const float *d_depth, const uint8_t *d_edges, float dmin, float dmax,
+                   unsigned *d_mbits, int *d_counters)
+{
+    const int w = a.w, h = a.h;
+    const size_t words = ((size_t)w * h + 3) / 4;
+    REVO_CUDA(ctx, cudaMemsetAsync(d_mbits, 0, words * 4, ctx->stream));
+    REVO_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 16 * sizeof(int), ctx->stream));
+    if (a.n_frames > 0) {
+        dim3 grid(64, a.n_frames);
+        k_quality_scatter<<<grid, 256, 0, ctx->stream>>>(a, d_mbits, d_counters);
+        LAUNCH_CHECK(ctx);
+    }
+    k_quality_hist<<<cdiv(w * h, 256), 256, 0, ctx->stream>>>(d_depth, d_edges, d_mbits, w * h, dmin, dmax, d_counters);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
 int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h)
 {
     {

@@ -17,6 +17,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -361,8 +362,48 @@ public:
         return s;
     }
 #endif
+    // void addOldPclAndPose(pcl, worldPose, timeStamp)   tracker.h:77 / tracker.cpp:209-224.  The reference copies
+    // return3DEdges(histogramLevel) of the frame; here the frame itself is kept (its list stays on the device).
+    // worldPose: column-major 4x4 (Eigen::Matrix4f::data()).
+    void addOldPclAndPose(const std::shared_ptr<ImgPyramidRGBD> &frame, const float *worldPose16, double timeStamp) {
+        Past p;
+        p.frame = frame; p.ts = timeStamp;
+        std::memcpy(p.pose, worldPose16, sizeof(p.pose));
+        mPast.push_back(p);
+    }
+    void clearUpPastLists() {   // tracker.cpp:249-257
+        while ((int)mPast.size() > mSettings.nFramesHistogramVoting) mPast.pop_front();
+    }
+    // TrackerStatus assessTrackingQuality(estimatedPose, currFrame)   tracker.h:74 / tracker.cpp:118-201
+    TrackerStatus assessTrackingQuality(const float *estimatedPose16, const std::shared_ptr<ImgPyramidRGBD> &currFrame) {
+        if (mPast.empty() || !mSettings.CHECK_TRACKING_RESULTS) return TRACKER_STATE_OK;
+        std::vector<revo_pyr *> hs;
+        std::vector<float> poses;
+        for (const Past &p : mPast) {
+            hs.push_back(p.frame->handle());
+            poses.insert(poses.end(), p.pose, p.pose + 16);
+        }
+        ctx_->check(revo_track_quality(ctx_->handle(), currFrame->handle(), histogramLevel, (int)hs.size(), hs.data(), poses.data(),
+                                       estimatedPose16, mSettings.nFramesHistogramVoting, &lastQuality));
+        return (TrackerStatus)lastQuality.status;
+    }
+#ifdef REVO_HOST_WITH_EIGEN
+    void addOldPclAndPose(const std::shared_ptr<ImgPyramidRGBD> &frame, const Eigen::Matrix4f &worldPose, double timeStamp) {
+        addOldPclAndPose(frame, worldPose.data(), timeStamp);
+    }
+    TrackerStatus assessTrackingQuality(const Eigen::Matrix4f &estimatedPose, const std::shared_ptr<ImgPyramidRGBD> &currFrame) {
+        return assessTrackingQuality(estimatedPose.data(), currFrame);
+    }
+#endif
     revo_track_result lastResult{};
+    revo_quality_result lastQuality{};
 private:
+    struct Past {
+        std::shared_ptr<ImgPyramidRGBD> frame;
+        float pose[16];
+        double ts;
+    };
+    std::deque<Past> mPast;
     std::shared_ptr<revo::Context> ctx_;
     const TrackerSettings mSettings;
     const ImgPyramidSettings mPyrConfig;

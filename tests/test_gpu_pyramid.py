@@ -162,3 +162,20 @@ def test_uint16_depth_wire_format(ctx, orc32):
     assert np.array_equal(b16[0].returnDepth(0), depth_host[0])
     b16.destroy()
     b32.destroy()
+
+
+def test_canny_tile_fallback_path(ctx, orc32):
+    """Widths that are not a multiple of 4 take the tile / union-find Canny (TMA tile load when the width allows it, plain
+    loads otherwise) instead of the bit-mask pipeline: same bit-exact result (single-level pyramid: odd sizes allowed)."""
+    from revo_b200 import api
+
+    p = synth_pair(3, 640, 480)
+    bgr, depth = p["key"]
+    for w, h in ((322, 242), (250, 200)):
+        b, d = np.ascontiguousarray(bgr[:h, :w]), np.ascontiguousarray(depth[:h, :w])
+        cam = (300.0, 300.0, w / 2.0, h / 2.0, w, h)
+        st = _settings(cam, 1)
+        pg = api.ImgPyramidRGBD(ctx, st, None, b, d)
+        pg.makeKeyframe()
+        po = _oracle_pyr(orc32, cam, 1, b, d)
+        _compare(pg, po, 1)

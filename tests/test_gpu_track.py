@@ -237,3 +237,38 @@ def test_end_to_end_gpu_pyramids_track_to_ground_truth(ctx, orc64):
     assert status == api.TRACKER_STATE_OK
     assert rot_angle(R, Tgt[:3, :3]) < 1.5e-3 and np.linalg.norm(T - Tgt[:3, 3]) < 3e-3
     assert sum(trk.last_result.n_evals) >= 6
+
+
+def test_tracking_quality_vote(ctx, orc64):
+    """TrackerNew::assessTrackingQuality (tracker.cpp:118-201) on the device vs the numpy restatement: exact counts."""
+    from oracle import oracle as O
+    from revo_b200 import api, synth
+
+    seeds = (1, 23, 24)
+    ps = [synth_pair(s) for s in seeds]
+    st = _settings(ps[0]["cam"], 3)
+    pyrs = [api.ImgPyramidRGBD(ctx, st, None, *p["key"]) for p in ps]
+    cur = api.ImgPyramidRGBD(ctx, st, None, *ps[0]["cur"])
+    trk = api.TrackerNew(ctx, api.TrackerSettings(), st)
+    rng = np.random.default_rng(3)
+    poses = [synth.se3_exp(rng.normal(0, 0.01, 6)) for _ in seeds]
+    est = synth.se3_exp(rng.normal(0, 0.01, 6))
+    assert trk.assessTrackingQuality(est, cur) == api.TRACKER_STATE_OK and trk.last_quality is None     # nothing to vote with
+    lvl = trk.histogramLevel
+    cam2 = cur._cam(lvl)
+    cam = (cam2.fx, cam2.fy, cam2.cx, cam2.cy, cam2.width, cam2.height)
+    depth, edges = cur.returnDepth(lvl), cur.returnOrigEdges(lvl)
+    for k, (p, T) in enumerate(zip(pyrs, poses)):
+        trk.addOldPclAndPose(p, T, float(k))
+        status = trk.assessTrackingQuality(est, cur)
+        q = trk.last_quality
+        o = O.assess_tracking_quality([x.return3DEdges(lvl) for x in pyrs[:k + 1]], poses[:k + 1], est, cam, depth, edges)
+        assert list(q.histogram) == o["histogram"] and list(q.overlaps) == o["overlaps"], (k, list(q.histogram), o)
+        assert q.out_of_bounds == o["out_of_bounds"] and q.n_frames == o["n_frames"] == k + 1
+        assert abs(q.overlap_measure - o["overlap_measure"]) < 1e-3 and status == o["status"]
+    # a fourth frame: only the first nFramesHistogramVoting of the list vote until clearUpPastLists() trims it (tracker.cpp:143)
+    trk.addOldPclAndPose(pyrs[0], poses[1], 3.0)
+    trk.assessTrackingQuality(est, cur)
+    assert trk.last_quality.n_frames == 3 and list(trk.last_quality.histogram) == o["histogram"]
+    trk.clearUpPastLists()
+    assert len(trk.mPastPcl) == 3 and trk.mPastPcl[0][2] == 1.0
