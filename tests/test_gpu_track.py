@@ -272,3 +272,43 @@ def test_tracking_quality_vote(ctx, orc64):
     assert trk.last_quality.n_frames == 3 and list(trk.last_quality.histogram) == o["histogram"]
     trk.clearUpPastLists()
     assert len(trk.mPastPcl) == 3 and trk.mPastPcl[0][2] == 1.0
+
+
+def test_config3_1280x960_five_levels(ctx, orc32, orc64, engine):
+    """BASELINE.json configs[2]: one 1280x960 pair, 5-level pyramid, Huber weights (always on, optimizer.h:75,156-160).
+    Pyramids built by the CUDA path are bit-exact against the oracle on all five levels (level 3 and 4 never run the edge
+    fill-in) and the full coarse-to-fine track agrees with the oracle like at VGA."""
+    from oracle import oracle as O
+    from revo_b200 import api
+
+    if engine == "queue":
+        pytest.skip("same arithmetic as the other engines; keeps the suite short")
+    p = synth_pair(3, 1280, 960)
+    st = _settings(p["cam"], 5)
+    gk = api.ImgPyramidRGBD(ctx, st, None, *p["key"])
+    gc = api.ImgPyramidRGBD(ctx, st, None, *p["cur"])
+    gk.makeKeyframe()
+    cfg = O.PyrCfg(n_levels=5)
+    ok = O.build_pyramid(orc64, cfg, p["cam"], *p["key"], backend="cv2")
+    O.make_keyframe(orc64, ok, backend="cv2")
+    oc = O.build_pyramid(orc64, cfg, p["cam"], *p["cur"], backend="cv2")
+    for l in range(5):
+        assert np.array_equal(gk.returnEdges(l), ok.edges[l]), f"edges L{l}"
+        assert np.array_equal(gk.returnDistTransform(l), ok.dt[l]), f"dt L{l}"
+        assert np.array_equal(gc.return3DEdges(l), oc.edges3d[l]), f"edges3d L{l}"
+    trk = api.TrackerNew(ctx, api.TrackerSettings(), st)
+    status, Rg, Tg, err = trk.trackFrames(np.eye(3), np.zeros(3), gk, gc)
+    r32 = orc32.track_frames(ok, oc, np.eye(3), np.zeros(3), orc32.default_cfg(), 4, 0, True)
+    r64 = orc64.track_frames(ok, oc, np.eye(3), np.zeros(3), orc64.default_cfg(), 4, 0, True)
+    spread_r = rot_angle(r32["R"], r64["R"])
+    spread_t = np.linalg.norm(r32["T"].astype(np.float64) - r64["T"])
+    d_r = min(rot_angle(Rg, r32["R"]), rot_angle(Rg, r64["R"]))
+    d_t = min(np.linalg.norm(Tg - r32["T"]), np.linalg.norm(Tg - r64["T"]))
+    Tgt = p["T_kf_cur"]
+    print(f"1280x960: gpu evals {list(trk.last_result.n_evals)[:5]} f64 {r64['evals'][:5]} d_r {d_r:.2e} d_t {d_t:.2e} "
+          f"spread {spread_r:.2e}/{spread_t:.2e} gt {rot_angle(Rg, Tgt[:3, :3]):.2e}/{np.linalg.norm(Tg - Tgt[:3, 3]):.2e}")
+    assert status == r64["status"]
+    assert d_r <= max(2e-4, 1.5 * spread_r) and d_t <= max(2e-4, 1.5 * spread_t)
+    assert rot_angle(Rg, Tgt[:3, :3]) <= rot_angle(r64["R"], Tgt[:3, :3]) + 3e-4
+    assert np.linalg.norm(Tg - Tgt[:3, 3]) <= np.linalg.norm(r64["T"] - Tgt[:3, 3]) + 1e-3
+    assert list(trk.last_result.n_pts)[:5] == [len(oc.edges3d[l]) for l in range(5)]
