@@ -51,13 +51,11 @@ def main():
 
     # (name, engine, ctas_per_pair, threads, chunk_points, env)
     configs = [
-        ("cluster C8 T128", 1, 8, 128, 0, {}),
+        ("cluster C8 T128 (default for > 37 pairs)", 1, 8, 128, 0, {}),
+        ("cluster C4 T256", 1, 4, 256, 0, {}),
+        ("cluster C8 T256", 1, 8, 256, 0, {}),
+        ("cluster C8 T128 pcap8", 1, 8, 128, 0, {"REVO_TRACK_PCAP": "8"}),
         ("pingpong C8", 3, 8, 0, 0, {}),
-        ("pingpong C4", 3, 4, 0, 0, {}),
-        ("pingpong C8 pcap6", 3, 8, 0, 0, {"REVO_TRACK_PCAP": "6"}),
-        ("pingpong C8 pcap16", 3, 8, 0, 0, {"REVO_TRACK_PCAP": "16"}),
-        ("pingpong C8 max37", 3, 8, 0, 0, {"REVO_TRACK_MAX_CLUSTERS": "37"}),
-        ("pingpong C16", 3, 16, 0, 0, {}),
         ("queue T128 s512 o2", 2, 0, 128, 0, {}),
     ]
     if args.configs:
@@ -65,7 +63,7 @@ def main():
         configs = [c for i, c in enumerate(configs) if i in keep]
     base = None
     for name, eng, C, T, chunk, env in configs:
-        for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS", "REVO_TRACK_PREFETCH"):
+        for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS"):
             os.environ.pop(k, None)
         os.environ.update(env)
         ctx.set_track_engine(eng, chunk)
@@ -101,7 +99,7 @@ def main():
     print("evals per pair: min %d p50 %d p90 %d max %d" % (tot.min(), np.median(tot), np.percentile(tot, 90), tot.max()))
     # profile pass (phase cycle counters; slows the kernel slightly) + sub-batches (critical path vs throughput)
     os.environ["REVO_TRACK_PROF"] = "1"
-    for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS", "REVO_TRACK_PREFETCH"):
+    for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS"):
         os.environ.pop(k, None)
     for eng in (1,):
         ctx.set_track_engine(eng, 0)
