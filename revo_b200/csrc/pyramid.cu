@@ -238,33 +238,9 @@ int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d
 // K2 (Canny) lives in canny.cu.
 
 // ---------------------------------------------------------------------------
-// K5: patch histogram (u8 counts wrap like cv::Mat_<uchar>::operator++) + count of
-// non-empty patches; fill-in from the level above.  One CTA per patch row.
+// K5: fill-in from the level above (the patch histogram itself -- u8 counts that wrap like cv::Mat_<uchar>::operator++,
+// number of non-empty patches -- is accumulated by the Canny output kernels and finalised by k_hist_finalize, canny.cu).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_hist(const ImgLevel *__restrict__ desc, int w, int h, int P)
-{
-    extern __shared__ int cnt[];
-    const int f = blockIdx.z;
-    const ImgLevel L = desc[f];
-    const int py = blockIdx.x;
-    for (int i = threadIdx.x; i < L.hist_w; i += blockDim.x) cnt[i] = 0;
-    __syncthreads();
-    const int band_w = L.hist_w * P;
-    for (int i = threadIdx.x; i < band_w * P; i += blockDim.x) {
-        const int r = i / band_w, c = i - r * band_w;
-        if (L.edges[(size_t)(py * P + r) * w + c]) atomicAdd(&cnt[c / P], 1);
-    }
-    __syncthreads();
-    int nz = 0;
-    for (int i = threadIdx.x; i < L.hist_w; i += blockDim.x) {
-        const uint8_t v = (uint8_t)(cnt[i] & 255);
-        L.hist[(size_t)py * L.hist_w + i] = v;
-        nz += v != 0;
-    }
-    nz = __reduce_add_sync(0xffffffffu, nz);
-    if ((threadIdx.x & 31) == 0 && nz) atomicAdd(L.nz_patches, nz);
-}
-
 // fillInEdges: this-level pixel (ox,oy) <- top pixel (2ox+1, 2oy+1) when the patch of the top pixel has
 // fewer than 0.05 P^2 edge pixels AT THIS LEVEL and the whole level has < n_percentage non-empty patches.
 __global__ void __launch_bounds__(256) k_fill_in(const ImgLevel *__restrict__ desc, const ImgLevel *__restrict__ top, int w, int h,

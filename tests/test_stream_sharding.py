@@ -55,3 +55,46 @@ def test_two_rank_gloo_sharding_equals_single_process(tmp_path):
     both = np.concatenate([ranks[0]["T_w_c"], ranks[1]["T_w_c"]])
     assert np.array_equal(both, st.T_w_c)                        # same streams, same poses, bit for bit
     assert int(ranks[0]["evals"]) + int(ranks[1]["evals"]) == st.total_evals
+
+
+def test_pipelined_stepping_equals_sequential():
+    """step_pipelined() with two frames in flight (prefetch, prefetch, then one new frame per step) tracks the same frames
+    in the same order as step(): identical poses with the (deterministic) oracle backend, and close() releases what is
+    still in flight."""
+    sys.path.insert(0, ROOT)
+    from bench import OracleBackend
+    from revo_b200 import synth
+    from revo_b200.stream import StreamTracker
+
+    w, h, n_frames = 160, 120, 6
+    cam = synth.intrinsics(w, h)
+    streams = [synth.make_stream(sd, n_frames, w, h) for sd in (310, 311)]
+    frame = lambda i: (np.stack([s["frames"][i][0] for s in streams]), np.stack([s["frames"][i][1] for s in streams]))
+
+    class CountingBackend(OracleBackend):
+        created = destroyed = 0
+
+        def create(self, bgr, depth, n):
+            CountingBackend.created += 1
+            return super().create(bgr, depth, n)
+
+        def destroy(self, handles):
+            CountingBackend.destroyed += 1
+
+    seq = StreamTracker(OracleBackend(cam, 3), 2, kf_interval=3)
+    seq.start(*frame(0))
+    for i in range(1, n_frames):
+        seq.step(*frame(i))
+
+    pip = StreamTracker(CountingBackend(cam, 3), 2, kf_interval=3)
+    pip.start(*frame(0))
+    pip.prefetch(*frame(1))
+    pip.prefetch(*frame(2))
+    for i in range(1, n_frames):
+        nxt = frame(i + 2) if i + 2 < n_frames else (None, None)
+        pip.step_pipelined(*nxt)
+    assert pip.frame == seq.frame == n_frames - 1
+    assert np.array_equal(pip.T_w_c, seq.T_w_c) and pip.total_evals == seq.total_evals
+    assert len(pip._pending) == 0
+    pip.close()
+    assert CountingBackend.created == n_frames and CountingBackend.destroyed >= 3
