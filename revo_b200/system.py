@@ -1,0 +1,127 @@
+"""Host-side mirror of the per-frame body of ``REVO::start`` (system/system.cpp:128-283) and of ``REVO::Pose``
+(system/system.h:89-150): motion-model initialisation, the tracking-quality vote and the "take the previous frame as
+keyframe and track again" policy, pose-graph bookkeeping.  It is the caller of the hot path, not part of it: pure host
+logic over objects with the reference's interface
+
+    pyramid:  makeKeyframe(), setTwf(T), getTransKFtoWorld(), returnTimestamp(), frameId
+    tracker:  trackFrames(R, T, ref, cur) -> (status, R, T, error), assessTrackingQuality(T_w_c, cur) -> status,
+              addOldPclAndPose(pyr, T_w_c, ts), clearUpPastLists(), histogramLevel
+
+so the same code drives the CUDA classes of :mod:`revo_b200.api` and, in the CPU tests, oracle-backed stand-ins.
+IO, viewer, logging and pose output of the reference loop are out of scope.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+TRACKER_STATE_OK, TRACKER_STATE_LOST, TRACKER_STATE_NEW_KF, TRACKER_STATE_UNKNOWN = range(4)
+
+
+def transformFromRT(R, T) -> np.ndarray:
+    M = np.eye(4, dtype=np.float32)
+    M[:3, :3] = np.asarray(R, np.float32).reshape(3, 3)
+    M[:3, 3] = np.asarray(T, np.float32).reshape(3)
+    return M
+
+
+def _inv(T: np.ndarray) -> np.ndarray:
+    return np.linalg.inv(T.astype(np.float64)).astype(np.float32)
+
+
+class Pose:
+    """``REVO::Pose`` (system/system.h:89-150): pose of a frame relative to its parent keyframe."""
+
+    def __init__(self, T_kf_curr, timestamp: float, kfFrame):
+        self.T_kf_curr = np.asarray(T_kf_curr, np.float32).reshape(4, 4).copy()
+        self.timestamp = float(timestamp)
+        self.kfFrame = kfFrame
+
+    def getCurrToWorld(self) -> np.ndarray:          # T_W_curr = T_W_KF * T_KF_CURR  (system.h:131-134)
+        return (self.kfFrame.getTransKFtoWorld().astype(np.float32) @ self.T_kf_curr).astype(np.float32)
+
+    def T_W_N(self) -> np.ndarray:
+        return self.getCurrToWorld()
+
+    def T_N_W(self) -> np.ndarray:
+        return _inv(self.getCurrToWorld())
+
+    def T_kf_N(self) -> np.ndarray:
+        return self.T_kf_curr
+
+    def setKfFrame(self, kfFrame):                   # only called when the "previous frame" becomes keyframe (system.h:140-146)
+        self.kfFrame = kfFrame
+        self.T_kf_curr = np.eye(4, dtype=np.float32)
+
+    def returnTimestamp(self) -> float:
+        return self.timestamp
+
+
+class REVO:
+    """The tracking part of ``REVO::start`` for one stream: feed pyramids in order with :meth:`processFrame`."""
+
+    def __init__(self, tracker):
+        self.mTracker = tracker
+        self.mPoseGraph: List[Pose] = []
+        self.kfPyr = None
+        self.prevPyr = None
+        self.noFrames = 0
+        self.nKeyFrames = 0
+        self.justAddedNewKeyframe = False
+        self.R = np.eye(3, dtype=np.float32)        # initial guess of the next frame relative to the keyframe
+        self.T = np.zeros(3, dtype=np.float32)
+        self.T_NM1_N = np.eye(4, dtype=np.float32)
+        self.trackerStatus = TRACKER_STATE_UNKNOWN
+        self.error = 0.0
+        self.retracked: List[int] = []               # frame ids at which the previous frame was promoted and tracking repeated
+
+    def processFrame(self, currPyr) -> np.ndarray:
+        """One iteration of the ``while`` loop (system.cpp:147-275). Returns the frame's pose in the world."""
+        trk = self.mTracker
+        currPyr.frameId = self.noFrames
+        if self.noFrames == 0:                       # first frame -> keyframe (system.cpp:151-175)
+            self.kfPyr = self.prevPyr = currPyr
+            currPyr.makeKeyframe()
+            currPyr.setTwf(np.eye(4, dtype=np.float32))
+            self.mPoseGraph.append(Pose(np.eye(4), currPyr.returnTimestamp(), currPyr))
+            self.nKeyFrames += 1
+            self.noFrames += 1
+            self.justAddedNewKeyframe = True
+            trk.addOldPclAndPose(currPyr, np.eye(4, dtype=np.float32), currPyr.returnTimestamp())
+            return np.eye(4, dtype=np.float32)
+        self.noFrames += 1
+        status, R, T, self.error = trk.trackFrames(self.R, self.T, self.kfPyr, currPyr)                  # :188
+        T_KF_N = transformFromRT(R, T)
+        currPoseInWorld = (self.kfPyr.getTransKFtoWorld().astype(np.float32) @ T_KF_N).astype(np.float32)   # :192
+        status = trk.assessTrackingQuality(currPoseInWorld, currPyr)                                     # :199
+        if status == TRACKER_STATE_NEW_KF and not self.justAddedNewKeyframe:
+            # tracking gets inaccurate: take the previous frame as keyframe and optimise again (:203-239)
+            self.kfPyr = self.prevPyr
+            self.kfPyr.setTwf(self.mPoseGraph[-1].getCurrToWorld())
+            self.kfPyr.makeKeyframe()
+            self.mPoseGraph[-1].setKfFrame(self.kfPyr)
+            self.nKeyFrames += 1
+            trk.clearUpPastLists()
+            _, R, T, self.error = trk.trackFrames(self.T_NM1_N[:3, :3], self.T_NM1_N[:3, 3], self.kfPyr, currPyr)   # :225
+            T_KF_N = transformFromRT(R, T)
+            currPoseInWorld = (self.kfPyr.getTransKFtoWorld().astype(np.float32) @ T_KF_N).astype(np.float32)
+            status = trk.assessTrackingQuality(currPoseInWorld, currPyr)
+            self.justAddedNewKeyframe = True
+            self.retracked.append(currPyr.frameId)
+        else:
+            self.justAddedNewKeyframe = False
+        self.trackerStatus = status
+        # add the frame to the pose graph, remember its edge cloud for the vote (:253-254)
+        self.mPoseGraph.append(Pose(T_KF_N, currPyr.returnTimestamp(), self.kfPyr))
+        trk.addOldPclAndPose(currPyr, currPoseInWorld, currPyr.returnTimestamp())
+        # relative motion N-1 -> N and the constant-velocity guess for the next frame (:262-271)
+        self.T_NM1_N = (self.mPoseGraph[-2].T_N_W() @ self.mPoseGraph[-1].T_W_N()).astype(np.float32)
+        T_init = (self.mPoseGraph[-1].T_kf_N() @ self.T_NM1_N).astype(np.float32)
+        self.R, self.T = T_init[:3, :3].copy(), T_init[:3, 3].copy()
+        self.prevPyr = currPyr
+        return self.mPoseGraph[-1].getCurrToWorld()
+
+    def trajectory(self) -> np.ndarray:
+        """(n_frames, 4, 4) world poses of all frames processed so far."""
+        return np.stack([p.getCurrToWorld() for p in self.mPoseGraph])

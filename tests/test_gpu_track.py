@@ -312,3 +312,36 @@ def test_config3_1280x960_five_levels(ctx, orc32, orc64, engine):
     assert rot_angle(Rg, Tgt[:3, :3]) <= rot_angle(r64["R"], Tgt[:3, :3]) + 3e-4
     assert np.linalg.norm(Tg - Tgt[:3, 3]) <= np.linalg.norm(r64["T"] - Tgt[:3, 3]) + 1e-3
     assert list(trk.last_result.n_pts)[:5] == [len(oc.edges3d[l]) for l in range(5)]
+
+
+def test_revo_main_loop_on_gpu(ctx, orc32, engine):
+    """revo_b200/system.py (REVO::start mirror: motion model, quality vote, keyframe switch) driving the CUDA classes over a
+    short synthetic stream: follows the ground truth and agrees with the same loop over the oracle-backed stand-ins."""
+    from _oracle_system import OraclePyr, OracleTracker
+    from oracle import oracle as O
+    from revo_b200 import api, synth
+    from revo_b200.system import REVO
+
+    if engine != "cluster":
+        pytest.skip("host logic: one engine is enough")
+    w, h, n = 320, 240, 7
+    s = synth.make_stream(77, n, w, h, max_trans=0.03, max_rot_deg=1.5)
+    cam = synth.intrinsics(w, h)
+    st = _settings(cam, 3)
+    g = REVO(api.TrackerNew(ctx, api.TrackerSettings(), st))
+    o = REVO(OracleTracker(orc32, 3))
+    cfg = O.PyrCfg(n_levels=3)
+    for i in range(n):
+        bgr, depth = s["frames"][i]
+        g.processFrame(api.ImgPyramidRGBD(ctx, st, None, bgr, depth, 0.033 * i))
+        o.processFrame(OraclePyr(orc32, cfg, cam, bgr, depth, 0.033 * i))
+    tg, to = g.trajectory(), o.trajectory()
+    assert g.retracked == o.retracked and g.nKeyFrames == o.nKeyFrames
+    for i in range(1, n):
+        D = np.linalg.inv(to[i].astype(np.float64)) @ tg[i].astype(np.float64)
+        assert rot_angle(np.eye(3), D[:3, :3]) < 1e-3 and np.linalg.norm(D[:3, 3]) < 2e-3, (i, D)
+        T_gt = np.linalg.inv(s["T_w_c"][0]) @ s["T_w_c"][i]
+        E = np.linalg.inv(T_gt) @ tg[i].astype(np.float64)
+        assert rot_angle(np.eye(3), E[:3, :3]) < 8e-3 and np.linalg.norm(E[:3, 3]) < 2e-2
+    q = g.mTracker.last_quality
+    assert q is not None and q.n_frames == 3 and sum(q.histogram) > 0
