@@ -1,0 +1,58 @@
+"""TUM wire formats (revo_b200/tum_io.py): association list parsing like the reference's reader
+(io/iowrapperRGBD.cpp:301-333), 8-bit colour + raw 16-bit depth round trip through PNG files, and the trajectory format of
+REVO::writePose (system/system.cpp:75-79)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def test_association_list_and_frames(tmp_path):
+    import cv2
+
+    from revo_b200 import synth, tum_io
+
+    p = synth.make_pair(4, 160, 120)
+    os.makedirs(tmp_path / "rgb")
+    os.makedirs(tmp_path / "depth")
+    lines = ["# comment", ""]
+    raws = []
+    for i, (bgr, depth) in enumerate((p["key"], p["cur"])):
+        raw = np.round(depth.astype(np.float64) * 5000.0).astype(np.uint16)
+        raws.append(raw)
+        cv2.imwrite(str(tmp_path / "rgb" / f"{i}.png"), bgr)
+        cv2.imwrite(str(tmp_path / "depth" / f"{i}.png"), raw)
+        lines.append(f"{1305031102.175304 + i:.6f} rgb/{i}.png {1305031102.160407 + i:.6f} depth/{i}.png")
+    (tmp_path / "associate.txt").write_text("\n".join(lines) + "\n")
+    assoc = tum_io.read_associations(str(tmp_path / "associate.txt"))
+    assert len(assoc) == 2 and assoc[0][1] == "rgb/0.png" and assoc[1][3] == "depth/1.png"
+    assert len(tum_io.read_associations(str(tmp_path / "associate.txt"), skip_first_n=1)) == 1
+    frames = list(tum_io.iter_frames(str(tmp_path)))
+    assert len(frames) == 2 and abs(frames[1][0] - 1305031103.160407) < 1e-6
+    for (ts, bgr, raw), ref_raw, (ref_bgr, ref_depth) in zip(frames, raws, (p["key"], p["cur"])):
+        assert bgr.dtype == np.uint8 and np.array_equal(bgr, ref_bgr)
+        assert raw.dtype == np.uint16 and np.array_equal(raw, ref_raw)
+        # the reader's conversion reproduces the float depth the synthetic scene was quantised from
+        assert np.array_equal(raw.astype(np.float32) * (np.float32(1.0) / np.float32(5000.0)), ref_depth)
+
+
+def test_trajectory_round_trip(tmp_path):
+    from revo_b200 import synth, tum_io
+
+    rng = np.random.default_rng(1)
+    poses = [synth.se3_exp(rng.normal(0, 0.5, 6)) for _ in range(5)]
+    poses.append(np.diag([-1.0, -1.0, 1.0, 1.0]))            # trace <= 0: the other branch of the quaternion conversion
+    ts = [1305031102.175304 + 0.033 * i for i in range(len(poses))]
+    tum_io.write_trajectory(str(tmp_path / "traj.txt"), ts, poses)
+    first = (tmp_path / "traj.txt").read_text().splitlines()[0].split()
+    assert len(first) == 8 and first[0] == "1305031102.175304" and all(len(v.split(".")[1]) == 9 for v in first[1:])
+    t2, p2 = tum_io.read_trajectory(str(tmp_path / "traj.txt"))
+    assert np.allclose(t2, ts, atol=1e-6)
+    for a, b in zip(poses, p2):
+        assert np.allclose(a, b, atol=2e-8 * 10)
+    q = tum_io.quaternion_from_R(np.eye(3))
+    assert np.array_equal(q, [0, 0, 0, 1])
