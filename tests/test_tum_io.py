@@ -56,3 +56,30 @@ def test_trajectory_round_trip(tmp_path):
         assert np.allclose(a, b, atol=2e-8 * 10)
     q = tum_io.quaternion_from_R(np.eye(3))
     assert np.array_equal(q, [0, 0, 0, 1])
+
+
+def test_ate_rpe_on_transformed_noisy_trajectory(tmp_path):
+    """ATE is invariant to a rigid transform of the estimate and measures the added noise; RPE of an exact copy is 0."""
+    from revo_b200 import evaluate, synth, tum_io
+
+    rng = np.random.default_rng(3)
+    gt = [np.eye(4)]
+    for _ in range(59):
+        gt.append(gt[-1] @ synth.se3_exp(np.r_[rng.normal(0, 0.01, 3), rng.normal(0, 0.01, 3)]))
+    gt = np.array(gt)
+    ts = 100.0 + 0.033 * np.arange(len(gt))
+    G = synth.se3_exp(np.array([0.3, -0.2, 0.5, 0.2, -0.4, 0.9]))
+    est = np.array([G @ T for T in gt])
+    a = evaluate.ate(gt, est)
+    assert a["rmse"] < 1e-9
+    assert evaluate.rpe(gt, est)["trans_rmse"] < 1e-9 and evaluate.rpe(gt, est, delta=5)["rot_rmse"] < 1e-6
+    noisy = est.copy()
+    noisy[:, :3, 3] += rng.normal(0, 0.01, (len(gt), 3))
+    a = evaluate.ate(gt, noisy)
+    assert 0.01 < a["rmse"] < 0.025                       # sigma * sqrt(3) = 0.017
+    # through the files, with the estimate's timestamps shifted by a few milliseconds and one frame dropped
+    tum_io.write_trajectory(str(tmp_path / "gt.txt"), ts, gt)
+    keep = [i for i in range(len(gt)) if i != 7]
+    tum_io.write_trajectory(str(tmp_path / "est.txt"), ts[keep] + 0.004, noisy[keep])
+    r = evaluate.evaluate_files(str(tmp_path / "gt.txt"), str(tmp_path / "est.txt"))
+    assert r["n"] == len(gt) - 1 and abs(r["ate"]["rmse"] - a["rmse"]) < 2e-3
