@@ -57,18 +57,22 @@ def main():
         ("cluster C8 T128 pcap8", 1, 8, 128, 0, {"REVO_TRACK_PCAP": "8"}),
         ("pingpong C8", 3, 8, 0, 0, {}),
         ("queue T128 s512 o2", 2, 0, 128, 0, {}),
+        # engine 4 exists only after scratch/experiments/enable_lean_engine.patch (otherwise these lines print FAILED)
+        ("lean C8 T128", 4, 8, 128, 0, {}),
+        ("lean C8 T128 packed", 4, 8, 128, 0, {"REVO_LEAN_PACK": "1"}),
+        ("lean C8 T128 packed no-L1", 4, 8, 128, 0, {"REVO_LEAN_PACK": "1", "REVO_LEAN_HINT": "3"}),
     ]
     if args.configs:
         keep = set(int(x) for x in args.configs.split(","))
         configs = [c for i, c in enumerate(configs) if i in keep]
     base = None
     for name, eng, C, T, chunk, env in configs:
-        for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS"):
+        for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS", "REVO_LEAN_PACK", "REVO_LEAN_HINT"):
             os.environ.pop(k, None)
         os.environ.update(env)
-        ctx.set_track_engine(eng, chunk)
-        ctx.set_track_shape(C, T)
         try:
+            ctx.set_track_engine(eng, chunk)
+            ctx.set_track_shape(C, T)
             ms = []
             for r in range(args.reps + 2):
                 t0 = time.perf_counter()
@@ -99,7 +103,7 @@ def main():
     print("evals per pair: min %d p50 %d p90 %d max %d" % (tot.min(), np.median(tot), np.percentile(tot, 90), tot.max()))
     # profile pass (phase cycle counters; slows the kernel slightly) + sub-batches (critical path vs throughput)
     os.environ["REVO_TRACK_PROF"] = "1"
-    for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS"):
+    for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS", "REVO_LEAN_PACK", "REVO_LEAN_HINT"):
         os.environ.pop(k, None)
     for eng in (1,):
         ctx.set_track_engine(eng, 0)
