@@ -251,13 +251,22 @@ REVO_API int revo_track_quality(revo_ctx *ctx, const revo_pyr *cur, int hist_lev
 /* Launch-shape override for revo_track_batch (0 = automatic): CTAs per pair (cluster size 1,2,4,8,16)
  * and threads per CTA. */
 REVO_API int revo_ctx_set_track_shape(revo_ctx *ctx, int ctas_per_pair, int threads_per_cta);
-/* Tracking engine: 0 = automatic, 1 = one thread-block cluster per pair (lowest single-pair latency; the only
- * engine of revo_track_split), 2 = chip-wide task queue (every evaluation is cut into chunk tasks that any CTA of the
- * persistent grid may run; highest batch throughput).  chunk_points: minimum points per task (0 = automatic). */
+/* Tracking engine: 0 = automatic (= 1), 1 = one thread-block cluster per pair (track.cu; fastest at every batch size
+ * measured and the only engine of revo_track_split), 2 = chip-wide task queue (track_queue.cu: every evaluation is cut into
+ * chunk tasks that any CTA of the persistent grid may run), 3 = warp-specialised clusters working on two pairs
+ * (track_pp.cu).  chunk_points: minimum points per task of engine 2 (0 = automatic). */
 REVO_API int revo_ctx_set_track_engine(revo_ctx *ctx, int engine, int chunk_points);
 /* Pre-size the device memory pool: later stream-ordered slab allocations up to `bytes` in total are served
  * from cached memory instead of the driver (call once before a steady-state stream starts). */
 REVO_API int revo_ctx_reserve(revo_ctx *ctx, size_t bytes);
+
+/* ---- pose helpers for a Sophus::SE3f adapter (host arithmetic, no device needed) ------------- */
+/* Unit quaternion (x, y, z, w: Eigen / Sophus coefficient order) <-> column-major 3x3 rotation as the tracking calls take
+ * it.  revo_quat_to_R9 normalises q (REVO_ERR_INVALID_ARG for a zero or non-finite quaternion); revo_R9_to_quat applies
+ * the tracker's own test (||R R^T - I||_F < 1e-5, det > 0: the Sophus ENSUREs of so3.hpp:419-424) and returns
+ * REVO_ERR_NOT_ORTHOGONAL otherwise; the conversion is Eigen's (Shepperd), as SO3(Matrix3) does. */
+REVO_API int revo_quat_to_R9(const float *q_xyzw, float *R9_out);
+REVO_API int revo_R9_to_quat(const float *R9, float *q_xyzw_out);
 
 /* ---- single pair split over several GPUs (BASELINE config 5) ------------- */
 /* One process per GPU.  Every rank builds the same pyramids; rank r evaluates the r-th contiguous

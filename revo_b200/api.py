@@ -97,7 +97,7 @@ EXPORTED_SYMBOLS = [
     "revo_pyr_make_keyframe_batch", "revo_pyr_destroy", "revo_pyr_destroy_batch", "revo_pyr_is_keyframe", "revo_pyr_level_camera",
     "revo_pyr_timestamp", "revo_pyr_num_edges", "revo_pyr_download", "revo_pyr_upload_level", "revo_eval",
     "revo_track_level", "revo_track", "revo_track_batch", "revo_ctx_set_track_shape", "revo_split_export",
-    "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve", "revo_ctx_last_upload_ms", "revo_pyr_create_batch_u16", "revo_track_quality",
+    "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve", "revo_ctx_last_upload_ms", "revo_pyr_create_batch_u16", "revo_track_quality", "revo_quat_to_R9", "revo_R9_to_quat",
 ]
 
 
@@ -150,6 +150,8 @@ def load_library():
     lib.revo_ctx_set_track_engine.argtypes = [vp, i32, i32]
     lib.revo_ctx_reserve.argtypes = [vp, C.c_size_t]
     lib.revo_ctx_last_upload_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.revo_quat_to_R9.argtypes = [vp, vp]
+    lib.revo_R9_to_quat.argtypes = [vp, vp]
     lib.revo_split_export.argtypes = [vp, i32, i32, vp]
     lib.revo_split_open.argtypes = [vp, vp]
     lib.revo_track_split.argtypes = [vp, C.POINTER(revo_tracker_config), vp, vp, vp, vp, C.POINTER(revo_track_result)]
@@ -577,6 +579,29 @@ def _handles(frames):
         return frames.n, frames.arr
     n = len(frames)
     return n, (C.c_void_p * n)(*[p.h for p in frames])
+
+
+def quat_to_R(q_xyzw) -> np.ndarray:
+    """Unit quaternion (x, y, z, w; normalised by the library) -> 3x3 rotation (``revo_quat_to_R9``; host arithmetic)."""
+    lib = load_library()
+    q = np.ascontiguousarray(q_xyzw, np.float32).reshape(4)
+    r9 = np.zeros(9, np.float32)
+    rc = lib.revo_quat_to_R9(q.ctypes.data, r9.ctypes.data)
+    if rc:
+        raise RevoError(rc, lib.revo_strerror(rc).decode())
+    return _R_from_c(r9)
+
+
+def R_to_quat(R) -> np.ndarray:
+    """3x3 rotation -> (x, y, z, w) like ``Sophus::SO3f(R).unit_quaternion()``; raises RevoError(REVO_ERR_NOT_ORTHOGONAL)
+    where Sophus would abort (``revo_R9_to_quat``; host arithmetic)."""
+    lib = load_library()
+    r9 = _R_to_c(R)
+    q = np.zeros(4, np.float32)
+    rc = lib.revo_R9_to_quat(r9.ctypes.data, q.ctypes.data)
+    if rc:
+        raise RevoError(rc, lib.revo_strerror(rc).decode())
+    return q
 
 
 def _R_to_c(R) -> np.ndarray:

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -123,6 +124,63 @@ const char *revo_strerror(int code)
         case REVO_ERR_COMM: return "multi-GPU setup error";
         default: return "unknown error";
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pose helpers (host arithmetic)
+// ---------------------------------------------------------------------------------------------------
+int revo_quat_to_R9(const float *q, float *R)
+{
+    if (!q || !R) return REVO_ERR_INVALID_ARG;
+    const double n2 = (double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2] + (double)q[3] * q[3];
+    if (!(n2 > 0.0) || !std::isfinite(n2)) return REVO_ERR_INVALID_ARG;
+    const double s = 1.0 / std::sqrt(n2);
+    const double x = q[0] * s, y = q[1] * s, z = q[2] * s, w = q[3] * s;
+    R[0] = (float)(1 - 2 * (y * y + z * z)); R[3] = (float)(2 * (x * y - z * w));     R[6] = (float)(2 * (x * z + y * w));
+    R[1] = (float)(2 * (x * y + z * w));     R[4] = (float)(1 - 2 * (x * x + z * z)); R[7] = (float)(2 * (y * z - x * w));
+    R[2] = (float)(2 * (x * z - y * w));     R[5] = (float)(2 * (y * z + x * w));     R[8] = (float)(1 - 2 * (x * x + y * y));
+    return REVO_OK;
+}
+
+int revo_R9_to_quat(const float *Rf, float *q)
+{
+    if (!Rf || !q) return REVO_ERR_INVALID_ARG;
+    double R[9];
+    for (int i = 0; i < 9; ++i) R[i] = Rf[i];
+    auto M = [&](int i, int j) { return R[j * 3 + i]; };
+    double n2 = 0;   // ||R^T R - I||_F^2
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double d = -(i == j ? 1.0 : 0.0);
+            for (int k = 0; k < 3; ++k) d += M(k, i) * M(k, j);
+            n2 += d * d;
+        }
+    const double det = M(0, 0) * (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) - M(0, 1) * (M(1, 0) * M(2, 2) - M(1, 2) * M(2, 0)) +
+                       M(0, 2) * (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0));
+    if (!(std::sqrt(n2) < 1e-5) || !(det > 0)) return REVO_ERR_NOT_ORTHOGONAL;
+    double o[4];
+    double t = M(0, 0) + M(1, 1) + M(2, 2);
+    if (t > 0) {
+        t = std::sqrt(t + 1.0);
+        o[3] = 0.5 * t;
+        t = 0.5 / t;
+        o[0] = (M(2, 1) - M(1, 2)) * t;
+        o[1] = (M(0, 2) - M(2, 0)) * t;
+        o[2] = (M(1, 0) - M(0, 1)) * t;
+    } else {
+        int i = 0;
+        if (M(1, 1) > M(0, 0)) i = 1;
+        if (M(2, 2) > M(i, i)) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(M(i, i) - M(j, j) - M(k, k) + 1.0);
+        o[i] = 0.5 * t;
+        t = 0.5 / t;
+        o[3] = (M(k, j) - M(j, k)) * t;
+        o[j] = (M(j, i) + M(i, j)) * t;
+        o[k] = (M(k, i) + M(i, k)) * t;
+    }
+    for (int c = 0; c < 4; ++c) q[c] = (float)o[c];
+    return REVO_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

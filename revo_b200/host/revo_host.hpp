@@ -11,7 +11,7 @@
 //    C-ABI status code (REVO_ERR_NOT_KEYFRAME, REVO_ERR_BAD_LEVEL, REVO_ERR_NOT_ORTHOGONAL, ...);
 //  * images live in HBM: the cv::Mat / Eigen accessors return host COPIES (revo_pyr_download);
 //  * Eigen / OpenCV are optional: without them the POD types revo::Mat3f / revo::Vec3f / revo::Image are used
-//    (this image has neither Eigen nor OpenCV C++ headers).  Define REVO_HOST_WITH_EIGEN / REVO_HOST_WITH_OPENCV
+//    (this image has neither Eigen nor OpenCV C++ headers).  Define REVO_HOST_WITH_EIGEN / REVO_HOST_WITH_SOPHUS / REVO_HOST_WITH_OPENCV
 //    to get the reference's exact signatures (Eigen::Matrix3f&, cv::Mat) as overloads.
 #pragma once
 
@@ -27,6 +27,9 @@
 
 #ifdef REVO_HOST_WITH_EIGEN
 #include <Eigen/Core>
+#endif
+#ifdef REVO_HOST_WITH_SOPHUS   // implies REVO_HOST_WITH_EIGEN
+#include <sophus/se3.hpp>
 #endif
 #ifdef REVO_HOST_WITH_OPENCV
 #include <opencv2/core.hpp>
@@ -55,6 +58,14 @@ struct Vec3f {
     float operator[](int i) const { return v[i]; }
     float *data() { return v; }
     const float *data() const { return v; }
+};
+// Pose as Sophus::SE3f stores it (se3.hpp: unit quaternion in Eigen coefficient order x, y, z, w + translation).  The
+// conversions run in the C ABI (revo_quat_to_R9 / revo_R9_to_quat); a matrix that is not a rotation throws
+// revo::Error(REVO_ERR_NOT_ORTHOGONAL) where Sophus' constructor would abort() (so3.hpp:419-424).
+struct SE3f {
+    float q[4];
+    float t[3];
+    static SE3f Identity() { return SE3f{{0.f, 0.f, 0.f, 1.f}, {0.f, 0.f, 0.f}}; }
 };
 template <typename T>
 struct Image {   // minimal stand-in for cv::Mat_<T> (row-major, tight)
@@ -359,6 +370,30 @@ public:
         std::memcpy(r.m, R.data(), sizeof(r.m)); std::memcpy(t.v, T.data(), sizeof(t.v));
         const TrackerStatus s = trackFrames(r, t, error, refFrame, currFrame);
         std::memcpy(R.data(), r.m, sizeof(r.m)); std::memcpy(T.data(), t.v, sizeof(t.v));
+        return s;
+    }
+#endif
+    // the same call with the pose in Sophus::SE3f form (the reference converts R, T <-> SE3f inside Optimizer::trackFrames,
+    // optimizer.cpp:240,308-309)
+    TrackerStatus trackFrames(revo::SE3f &T_ref_cur, float &error, const std::shared_ptr<ImgPyramidRGBD> &refFrame,
+                              const std::shared_ptr<ImgPyramidRGBD> &currFrame) {
+        revo::Mat3f r; revo::Vec3f t;
+        ctx_->check(revo_quat_to_R9(T_ref_cur.q, r.data()));
+        std::memcpy(t.v, T_ref_cur.t, sizeof(t.v));
+        const TrackerStatus s = trackFrames(r, t, error, refFrame, currFrame);
+        ctx_->check(revo_R9_to_quat(r.data(), T_ref_cur.q));
+        std::memcpy(T_ref_cur.t, t.v, sizeof(t.v));
+        return s;
+    }
+#ifdef REVO_HOST_WITH_SOPHUS
+    TrackerStatus trackFrames(Sophus::SE3f &T_ref_cur, float &error, const std::shared_ptr<ImgPyramidRGBD> &refFrame,
+                              const std::shared_ptr<ImgPyramidRGBD> &currFrame) {
+        revo::SE3f p;
+        const Eigen::Quaternionf uq = T_ref_cur.unit_quaternion();
+        p.q[0] = uq.x(); p.q[1] = uq.y(); p.q[2] = uq.z(); p.q[3] = uq.w();
+        for (int i = 0; i < 3; ++i) p.t[i] = T_ref_cur.translation()[i];
+        const TrackerStatus s = trackFrames(p, error, refFrame, currFrame);
+        T_ref_cur = Sophus::SE3f(Eigen::Quaternionf(p.q[3], p.q[0], p.q[1], p.q[2]), Eigen::Vector3f(p.t[0], p.t[1], p.t[2]));
         return s;
     }
 #endif

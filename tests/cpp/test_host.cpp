@@ -24,6 +24,17 @@ static int selftest()
     if (!t.optimizerSettings.USE_EDGE_FILTER || !t.CHECK_INIT_VALUES) return 5;
     revo_opt_config c = t.optimizerSettings.c_config();
     if (c.use_edge_filter != 1 || c.convergence_eps[2] != 0.999f) return 6;
+    // pose helpers of the C ABI (host arithmetic): quaternion <-> column-major rotation, Sophus-style error instead of abort()
+    const float q[4] = {0.1f, -0.2f, 0.3f, 0.9f};
+    float R[9], q2[4];
+    if (revo_quat_to_R9(q, R) != REVO_OK || revo_R9_to_quat(R, q2) != REVO_OK) return 7;
+    const float n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i)
+        if (std::fabs(q2[i] - q[i] / n) > 1e-6f) return 8;
+    R[0] *= 1.01f;
+    if (revo_R9_to_quat(R, q2) != REVO_ERR_NOT_ORTHOGONAL) return 9;
+    revo::SE3f id = revo::SE3f::Identity();
+    if (id.q[3] != 1.f || id.t[0] != 0.f) return 10;
     return 0;
 }
 

@@ -6,6 +6,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -107,3 +108,27 @@ def test_camera_pyramid_rule():
     assert cp.size() == st.nLevels() + 1 == 5
     assert (cp.at(3).width, cp.at(3).height) == (80, 60)
     assert abs(cp.at(2).fx - 517.3 / 4) < 1e-4 and abs(cp.at(1).cy - 255.3 / 2) < 1e-4
+
+
+def test_pose_helpers_quaternion_round_trip():
+    """revo_quat_to_R9 / revo_R9_to_quat (host arithmetic in the C ABI, the Sophus::SE3f side of the adapter): round trip,
+    Eigen's branch for trace <= 0, and the tracker's own not-a-rotation error instead of Sophus' abort()."""
+    from revo_b200 import api, synth, tum_io
+
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        R = synth.se3_exp(np.r_[np.zeros(3), rng.normal(0, 1.5, 3)])[:3, :3]
+        q = api.R_to_quat(R)
+        assert abs(np.linalg.norm(q) - 1) < 1e-6
+        assert np.allclose(q, tum_io.quaternion_from_R(R), atol=1e-6)
+        assert np.allclose(api.quat_to_R(q), R, atol=2e-6)
+        assert np.allclose(api.quat_to_R(3.0 * q), R, atol=2e-6)          # normalised by the library
+    q = api.R_to_quat(np.diag([-1.0, -1.0, 1.0]))                            # trace <= 0 branch
+    assert np.allclose(np.abs(q), [0, 0, 1, 0], atol=1e-7)
+    with pytest.raises(api.RevoError) as e:
+        api.R_to_quat(np.diag([1.0, 1.0, 1.01]))
+    assert e.value.code == 5                                                 # REVO_ERR_NOT_ORTHOGONAL
+    with pytest.raises(api.RevoError):
+        api.R_to_quat(np.diag([1.0, 1.0, -1.0]))                             # det < 0
+    with pytest.raises(api.RevoError):
+        api.quat_to_R(np.zeros(4))
