@@ -76,8 +76,10 @@ class REVO:
         self.error = 0.0
         self.retracked: List[int] = []               # frame ids at which the previous frame was promoted and tracking repeated
 
-    def processFrame(self, currPyr) -> np.ndarray:
-        """One iteration of the ``while`` loop (system.cpp:147-275). Returns the frame's pose in the world."""
+    def _frame(self, currPyr):
+        """One iteration of the ``while`` loop (system.cpp:147-275) as a coroutine: it YIELDS every ``trackFrames`` request
+        ``(R_init, T_init, refPyr, currPyr)`` and is sent the result ``(status, R, T, error)``, so that a driver can
+        batch the requests of many streams into one launch (:class:`MultiStreamREVO`).  Returns the frame's world pose."""
         trk = self.mTracker
         currPyr.frameId = self.noFrames
         if self.noFrames == 0:                       # first frame -> keyframe (system.cpp:151-175)
@@ -91,7 +93,7 @@ class REVO:
             trk.addOldPclAndPose(currPyr, np.eye(4, dtype=np.float32), currPyr.returnTimestamp())
             return np.eye(4, dtype=np.float32)
         self.noFrames += 1
-        status, R, T, self.error = trk.trackFrames(self.R, self.T, self.kfPyr, currPyr)                  # :188
+        status, R, T, self.error = yield (self.R, self.T, self.kfPyr, currPyr)                           # :188
         T_KF_N = transformFromRT(R, T)
         currPoseInWorld = (self.kfPyr.getTransKFtoWorld().astype(np.float32) @ T_KF_N).astype(np.float32)   # :192
         status = trk.assessTrackingQuality(currPoseInWorld, currPyr)                                     # :199
@@ -103,7 +105,7 @@ class REVO:
             self.mPoseGraph[-1].setKfFrame(self.kfPyr)
             self.nKeyFrames += 1
             trk.clearUpPastLists()
-            _, R, T, self.error = trk.trackFrames(self.T_NM1_N[:3, :3], self.T_NM1_N[:3, 3], self.kfPyr, currPyr)   # :225
+            _, R, T, self.error = yield (self.T_NM1_N[:3, :3], self.T_NM1_N[:3, 3], self.kfPyr, currPyr)   # :225
             T_KF_N = transformFromRT(R, T)
             currPoseInWorld = (self.kfPyr.getTransKFtoWorld().astype(np.float32) @ T_KF_N).astype(np.float32)
             status = trk.assessTrackingQuality(currPoseInWorld, currPyr)
@@ -122,6 +124,73 @@ class REVO:
         self.prevPyr = currPyr
         return self.mPoseGraph[-1].getCurrToWorld()
 
+    def processFrame(self, currPyr) -> np.ndarray:
+        """One iteration of the ``while`` loop (system.cpp:147-275). Returns the frame's pose in the world."""
+        g = self._frame(currPyr)
+        try:
+            req = next(g)
+            while True:
+                req = g.send(self.mTracker.trackFrames(*req))
+        except StopIteration as done:
+            return done.value
+
     def trajectory(self) -> np.ndarray:
         """(n_frames, 4, 4) world poses of all frames processed so far."""
         return np.stack([p.getCurrToWorld() for p in self.mPoseGraph])
+
+
+class MultiStreamREVO:
+    """B independent streams, each with the per-frame logic of :class:`REVO` (its own pose graph, motion model and vote
+    history), advancing one frame per call with the ``trackFrames`` requests of all streams batched: one launch for the
+    first alignment of every stream, one more for the streams whose vote asked for a new keyframe.  By construction the
+    result equals B separate :class:`REVO` runs (same coroutine), which is what the tests check.
+
+    trackers:    one tracker object per stream (vote state: ``assessTrackingQuality`` / ``addOldPclAndPose`` /
+                 ``clearUpPastLists``)
+    track_batch: ``f(requests) -> results`` with ``requests = [(R, T, refPyr, currPyr), ...]`` and
+                 ``results = [(status, R, T, error), ...]`` in the same order
+    """
+
+    def __init__(self, trackers, track_batch):
+        self.streams: List[REVO] = [REVO(t) for t in trackers]
+        self.track_batch = track_batch
+        self.batch_sizes: List[int] = []             # requests per launch, for tests / diagnostics
+
+    def processFrames(self, currPyrs) -> List[np.ndarray]:
+        assert len(currPyrs) == len(self.streams)
+        gens = [s._frame(p) for s, p in zip(self.streams, currPyrs)]
+        poses: List[Optional[np.ndarray]] = [None] * len(gens)
+        pending = {}
+        for i, g in enumerate(gens):
+            try:
+                pending[i] = next(g)
+            except StopIteration as done:
+                poses[i] = done.value
+        while pending:
+            idx = sorted(pending)
+            results = self.track_batch([pending[i] for i in idx])
+            self.batch_sizes.append(len(idx))
+            pending = {}
+            for i, r in zip(idx, results):
+                try:
+                    pending[i] = gens[i].send(r)
+                except StopIteration as done:
+                    poses[i] = done.value
+        return poses
+
+    def trajectories(self) -> List[np.ndarray]:
+        return [s.trajectory() for s in self.streams]
+
+
+def cuda_track_batch(tracker):
+    """``track_batch`` for :class:`MultiStreamREVO` over ``revo_b200.api.TrackerNew.trackFramesBatch``."""
+
+    def run(requests):
+        n = len(requests)
+        Rs = np.stack([np.asarray(r[0], np.float32).reshape(3, 3) for r in requests])
+        Ts = np.stack([np.asarray(r[1], np.float32).reshape(3) for r in requests])
+        out = tracker.trackFramesBatch(Rs, Ts, [r[2] for r in requests], [r[3] for r in requests])
+        return [(int(out["status"][i]), out["R"][i].reshape(3, 3).T.copy(), out["t"][i].copy(), float(out["error"][i]))
+                for i in range(n)]
+
+    return run

@@ -115,3 +115,48 @@ def test_forced_keyframe_switch():
     assert sysm.retracked == [2, 4] and Trk.cleared == 2 and sysm.nKeyFrames == 3
     # the fake tracker always reports 1 cm relative to the keyframe in use: world x = keyframe x + 1 cm
     assert np.allclose(sysm.trajectory()[:, 0, 3], [0.0, 0.01, 0.02, 0.02, 0.03, 0.03], atol=1e-6)
+
+
+def test_multi_stream_driver_equals_independent_runs():
+    """MultiStreamREVO batches the trackFrames requests of B streams (first alignment of all streams in one call, the
+    re-tracks after a keyframe switch in a second one) and must reproduce B separate REVO runs exactly."""
+    from _oracle_system import OraclePyr, OracleTracker
+    from oracle import oracle as O
+    from revo_b200 import synth
+    from revo_b200.system import REVO, MultiStreamREVO
+
+    w, h, n, B = 160, 120, 7, 3
+    cam = synth.intrinsics(w, h)
+    orc = O.Oracle("f32")
+    cfg = O.PyrCfg(n_levels=3)
+    # stream 1 moves fast, so that its vote asks for keyframes while the others keep theirs
+    streams = [synth.make_stream(300 + b, n, w, h, max_trans=0.01 + 0.04 * (b == 1), max_rot_deg=0.5 + 2.5 * (b == 1)) for b in range(B)]
+
+    def pyr(b, i):
+        return OraclePyr(orc, cfg, cam, *streams[b]["frames"][i], timestamp=0.033 * i)
+
+    single = [REVO(OracleTracker(orc, 3)) for _ in range(B)]
+    for b in range(B):
+        for i in range(n):
+            single[b].processFrame(pyr(b, i))
+
+    trackers = [OracleTracker(orc, 3) for _ in range(B)]
+    calls = []
+
+    def track_batch(requests):
+        calls.append(len(requests))
+        return [trackers[0].trackFrames(*r) for r in requests]       # trackFrames itself is stateless
+
+    multi = MultiStreamREVO(trackers, track_batch)
+    for i in range(n):
+        poses = multi.processFrames([pyr(b, i) for b in range(B)])
+        assert len(poses) == B and all(p.shape == (4, 4) for p in poses)
+    for b in range(B):
+        assert np.array_equal(multi.trajectories()[b], single[b].trajectory())
+        assert multi.streams[b].retracked == single[b].retracked
+        assert multi.streams[b].nKeyFrames == single[b].nKeyFrames
+    # the first frame needs no tracking; afterwards one call with all B streams, plus one per frame for the re-tracks
+    n_retracks = sum(len(s.retracked) for s in single)
+    assert n_retracks >= 1                                          # the second, smaller batch is exercised
+    assert calls.count(B) >= n - 1 and sum(calls) == B * (n - 1) + n_retracks
+    assert multi.batch_sizes == calls
