@@ -301,34 +301,6 @@ __device__ __forceinline__ bool lm_step(LMState &lm, const double *rec, const re
 }
 
 // ---- per-point work: PASS A + PASS B fused ---------------------------------------
-struct Proj {
-    float Wx, Wy, iz, dx, dy;
-    const uint4 *bp;
-    int state;   // 0 = no point, 1 = in bounds (texels wanted), 2 = out of bounds
-};
-
-// optimizer.cpp:93-100: warp, project, bounds test
-__device__ __forceinline__ Proj project(bool exists, const float4 p, const LevelIn &L, const float *__restrict__ R,
-                                        const float *__restrict__ t)
-{
-    Proj o;
-    o.Wx = R[0] * p.x + R[3] * p.y + R[6] * p.z + t[0];
-    o.Wy = R[1] * p.x + R[4] * p.y + R[7] * p.z + t[1];
-    const float Wz = R[2] * p.x + R[5] * p.y + R[8] * p.z + t[2];
-    // the reference divides (Wx/Wz*fx+cx); one correctly rounded reciprocal is shared by u, v and the Jacobian
-    // (differs from the quotient by <= 1 ulp, far inside the float tolerance of this path)
-    o.iz = __frcp_rn(Wz);
-    const float u = o.Wx * o.iz * L.fx + L.cx;
-    const float v = o.Wy * o.iz * L.fy + L.cy;
-    const bool inb = (u > 1.f && v > 1.f && u < (float)(L.w - 2) && v < (float)(L.h - 2));   // NaN-safe (:100)
-    const int ix = inb ? (int)u : 0, iy = inb ? (int)v : 0;
-    o.dx = u - (float)ix;
-    o.dy = v - (float)iy;
-    o.bp = L.opt + 2u * (unsigned)(iy * L.w + ix);
-    o.state = exists ? (inb ? 1 : 2) : 0;
-    return o;
-}
-
 // One 256-bit load (LDG.E.ENL2.256 on sm_100a) of the 32-byte QUAD record of pixel (ix,iy): the four distance-transform
 // values and the four packed gradients the bilinear fetch of optimizer.h:173-185 needs.  Returned as the two row
 // records r0 = {dt(x,y), dt(x+1,y), g(x,y), g(x+1,y)}, r1 = the same for row y+1.  One warp-wide gather touches at
@@ -348,59 +320,8 @@ __device__ __forceinline__ void unpack_grad(uint32_t g, float &gx, float &gy)
     gy = (float)((int)g >> 16);
 }
 
-// r0 = pair record of row iy (texels (ix,iy),(ix+1,iy)), r1 = pair record of row iy+1
-__device__ __forceinline__ void finish_point(const Proj &P, const uint4 r0, const uint4 r1, const LevelIn &L, float edge_dist,
-                                             bool use_filter, float huber, float (&acc)[32])
-{
-    if (P.state == 0) return;
-    if (P.state == 2) { acc[kRecBad] += 1.f; return; }
-    // getInterpolatedElement43, optimizer.h:173-185
-    const float dxdy = P.dx * P.dy;
-    const float w11 = dxdy, w01 = P.dy - dxdy, w10 = P.dx - dxdy, w00 = 1.f - P.dx - P.dy + dxdy;
-    float gx00, gy00, gx10, gy10, gx01, gy01, gx11, gy11;
-    unpack_grad(r0.z, gx00, gy00); unpack_grad(r0.w, gx10, gy10);
-    unpack_grad(r1.z, gx01, gy01); unpack_grad(r1.w, gx11, gy11);
-    constexpr float kq = 1.0f / 32764.0f;
-    const float gxi = (w11 * gx11 + w01 * gx01 + w10 * gx10 + w00 * gx00) * kq;
-    const float gyi = (w11 * gy11 + w01 * gy01 + w10 * gy10 + w00 * gy00) * kq;
-    const float r = w11 * __uint_as_float(r1.y) + w01 * __uint_as_float(r1.x) + w10 * __uint_as_float(r0.y) + w00 * __uint_as_float(r0.x);
-    if (use_filter && r > edge_dist) {                                             // optimizer.cpp:112
-        acc[kRecBad] += 1.f;
-        return;
-    }
-    const float wr = (r <= huber) ? 1.f : __fdividef(huber, r);                    // optimizer.h:159
-    const float gx = L.fx * gxi, gy = L.fy * gyi;                                  // optimizer.cpp:119-120
-    // calculateWarpUpdate, optimizer.cpp:204-228
-    // Same six entries, factored through a = x/z, b = y/z, t = a gx + b gy (12 flops instead of ~30):
-    //   v2 = -(a gx + b gy)/z, v3 = -(b t + gy), v4 = a t + gx, v5 = a gy - b gx.
-    const float z = P.iz;
-    const float a = P.Wx * z, b = P.Wy * z;
-    const float t = a * gx + b * gy;
-    float J[6];
-    J[0] = z * gx;
-    J[1] = z * gy;
-    J[2] = -(t * z);
-    J[3] = -(b * t + gy);
-    J[4] = a * t + gx;
-    J[5] = a * gy - b * gx;
-    // LGS6::update, LGSX.h:392-398 (upper triangle only; A is symmetric)
-    int s = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const float wi = wr * J[i];
-#pragma unroll
-        for (int j = i; j < 6; ++j) acc[s++] += wi * J[j];
-    }
-    const float rw = r * wr;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) acc[kRecB + i] += rw * J[i];
-    acc[kRecSW] += rw * r;     // optimizer.cpp:131
-    acc[kRecSU] += r * r;
-    acc[kRecGood] += 1.f;
-}
-
-// ---- branch-free variant of the per-point work (used by the task-queue engine) -----------------------------------
-// Same arithmetic as project()/finish_point(), but a point that does not exist, projects out of bounds or fails the
+// ---- branch-free per-point work (all engines) -------------------------------------------------------------------
+// optimizer.cpp:93-131 + calculateWarpUpdate (:204-228) + LGS6::update (LGSX.h:392-398).  A point that does not exist, projects out of bounds or fails the
 // edge filter runs through the same straight-line code with weight 0 (its texel fetch is redirected to texel 0 and
 // its projection is zeroed so that no inf/NaN can reach the sums).  Straight-line code lets the compiler interleave
 // the arithmetic of one point with the address computation and gathers of the next, and no lane ever waits for a
