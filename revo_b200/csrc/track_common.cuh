@@ -303,9 +303,9 @@ __device__ __forceinline__ bool lm_step(LMState &lm, const double *rec, const re
 // ---- per-point work: PASS A + PASS B fused ---------------------------------------
 // One 256-bit load (LDG.E.ENL2.256 on sm_100a) of the 32-byte QUAD record of pixel (ix,iy): the four distance-transform
 // values and the four packed gradients the bilinear fetch of optimizer.h:173-185 needs.  Returned as the two row
-// records r0 = {dt(x,y), dt(x+1,y), g(x,y), g(x+1,y)}, r1 = the same for row y+1.  One warp-wide gather touches at
-// most 32 cache lines; the L1 tag stage processes a gather line by line, so halving the number of gathers per point
-// (this layout vs one record per image row) halves the cost that actually bounds the evaluation.
+// records r0 = {dt(x,y), dt(x+1,y), g(x,y), g(x+1,y)}, r1 = the same for row y+1.  One gather and one address per point
+// instead of two (or four texel fetches); on its own this measured neutral -- the gather phase is bound neither by L1
+// wavefronts nor by per-thread memory parallelism (profiles/r1_k_track_v6_hotspots.txt) -- but it is the cheapest fetch.
 __device__ __forceinline__ void ldg_quad(const uint4 *p, uint4 &r0, uint4 &r1)
 {
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -321,8 +321,8 @@ __device__ __forceinline__ void unpack_grad(uint32_t g, float &gx, float &gy)
 }
 
 // ---- branch-free per-point work (all engines) -------------------------------------------------------------------
-// optimizer.cpp:93-131 + calculateWarpUpdate (:204-228) + LGS6::update (LGSX.h:392-398).  A point that does not exist, projects out of bounds or fails the
-// edge filter runs through the same straight-line code with weight 0 (its texel fetch is redirected to texel 0 and
+// optimizer.cpp:93-131 + calculateWarpUpdate (:204-228) + LGS6::update (LGSX.h:392-398).  A point that does not exist,
+// projects out of bounds or fails the edge filter runs through the same straight-line code with weight 0 (its texel fetch is redirected to texel 0 and
 // its projection is zeroed so that no inf/NaN can reach the sums).  Straight-line code lets the compiler interleave
 // the arithmetic of one point with the address computation and gathers of the next, and no lane ever waits for a
 // divergent neighbour.  The two divisions are single MUFU.RCP (<= 1 ulp, far inside the float tolerance of the path).
