@@ -160,3 +160,28 @@ def test_multi_stream_driver_equals_independent_runs():
     assert n_retracks >= 1                                          # the second, smaller batch is exercised
     assert calls.count(B) >= n - 1 and sum(calls) == B * (n - 1) + n_retracks
     assert multi.batch_sizes == calls
+
+
+def test_cuda_track_batch_adapter_conventions():
+    """cuda_track_batch: requests -> one trackFramesBatch call; the column-major R of the result record comes back as a
+    row-major 3x3 (what REVO._frame composes poses with)."""
+    from revo_b200 import api
+    from revo_b200.system import cuda_track_batch
+
+    R_true = np.arange(9, dtype=np.float32).reshape(3, 3)
+
+    class FakeTracker:
+        def trackFramesBatch(self, Rs, Ts, refs, curs):
+            assert Rs.shape == (2, 3, 3) and Ts.shape == (2, 3) and refs == ["k0", "k1"] and curs == ["c0", "c1"]
+            out = np.zeros(2, api.TRACK_RESULT_DTYPE)
+            for i in range(2):
+                out["R"][i] = api._R_to_c(R_true + i)            # column-major, as the C ABI returns it
+                out["t"][i] = Ts[i] + 1
+                out["status"][i] = 2 * i
+                out["error"][i] = 0.5 + i
+            return out
+
+    res = cuda_track_batch(FakeTracker())([(np.eye(3), np.zeros(3), "k0", "c0"), (np.eye(3), np.ones(3), "k1", "c1")])
+    assert [r[0] for r in res] == [0, 2] and [r[3] for r in res] == [0.5, 1.5]
+    assert np.array_equal(res[0][1], R_true) and np.array_equal(res[1][1], R_true + 1)
+    assert np.array_equal(res[1][2], [2, 2, 2])
