@@ -483,3 +483,22 @@ def assess_tracking_quality(past_pts, past_world_poses, estimated_pose, cam, dep
     measure = float(sum(f32(overlaps[k]) * f32(weights[k]) for k in range(1, nf + 1)))
     status = 0 if (measure >= overlaps[0] or nf + 1 < 4) else 2                                            # OK / NEW_KF
     return dict(histogram=histogram, overlaps=overlaps, overlap_measure=measure, status=status, out_of_bounds=oob, n_frames=nf)
+
+
+def generate_colored_pcl(bgr, depth, edges, cam, depth_min=0.1, depth_max=5.2, dense=False):
+    """``ImgPyramidRGBD::generateColoredPcl`` loop (datastructures/imgpyramidrgbd.cpp:300-323) restated literally (pure
+    Python loops: small cases only).  cam = (fx, fy, cx, cy, w, h); bgr is the colour image already reduced to the level
+    (:287-296).  Returns (8, N) float32 columns (X, Y, Z, 1, r, g, b, 1) in the reference's scan order (x outer, y inner)."""
+    fx, fy, cx, cy = (np.float32(v) for v in cam[:4])
+    cols = []
+    h, w = depth.shape
+    for xx in range(w):
+        for yy in range(h):
+            Z = np.float32(depth[yy, xx])
+            if np.isfinite(Z) and Z > np.float32(depth_min) and Z < np.float32(depth_max):     # isPointOkDepth, imgpyramidrgbd.h:170-173
+                if dense or edges[yy, xx] > 0:
+                    b, g, r = (np.float32(v) for v in bgr[yy, xx][:3])
+                    X = Z * (np.float32(xx) - cx) / fx
+                    Y = Z * (np.float32(yy) - cy) / fy
+                    cols.append([X, Y, Z, 1.0, r / np.float32(255.0), g / np.float32(255.0), b / np.float32(255.0), 1.0])
+    return np.asarray(cols, np.float32).reshape(-1, 8).T.copy()

@@ -88,6 +88,8 @@ assert TRACK_RESULT_DTYPE.itemsize == C.sizeof(revo_track_result)
 GRAY, DEPTH, EDGES, EDGES_ORIG, HIST, EDGES3D, DT, OPTSTRUCT, EDGES3D_DEVICE_ORDER = range(9)
 # TrackerNew::TrackerStatus, system/tracker.h:60-65
 TRACKER_STATE_OK, TRACKER_STATE_LOST, TRACKER_STATE_NEW_KF, TRACKER_STATE_UNKNOWN = range(4)
+(REVO_OK, REVO_ERR_INVALID_ARG, REVO_ERR_NO_DEVICE, REVO_ERR_CUDA, REVO_ERR_NOT_KEYFRAME, REVO_ERR_NOT_ORTHOGONAL, REVO_ERR_BAD_LEVEL,
+ REVO_ERR_BUFFER_TOO_SMALL, REVO_ERR_UNSUPPORTED, REVO_ERR_COMM) = range(10)
 SPLIT_HANDLE_BYTES = 128
 
 EXPORTED_SYMBOLS = [
@@ -357,6 +359,28 @@ def _ptr(a) -> int:
 # ---------------------------------------------------------------------------
 # ImgPyramidRGBD
 # ---------------------------------------------------------------------------
+def colored_pcl_from_arrays(bgr, depth, edges, fx, fy, cx, cy, depth_min, depth_max, dense: bool) -> np.ndarray:
+    """The loop of ``ImgPyramidRGBD::generateColoredPcl`` (imgpyramidrgbd.cpp:300-323) vectorised: pixels in the reference's
+    column-major scan order (x outer, y inner) with finite ``depth_min < Z < depth_max`` and -- unless ``dense`` -- an edge
+    label; column = ``(Z(x-cx)/fx, Z(y-cy)/fy, Z, 1, R/255, G/255, B/255, 1)`` in float32 arithmetic."""
+    depth = np.asarray(depth, np.float32)
+    with np.errstate(invalid="ignore"):
+        ok = np.isfinite(depth) & (depth > np.float32(depth_min)) & (depth < np.float32(depth_max))
+    if not dense:
+        ok &= np.asarray(edges) > 0
+    xs, ys = np.nonzero(ok.T)                        # transposed: x-major order
+    Z = depth[ys, xs]
+    out = np.empty((8, len(xs)), np.float32)
+    out[0] = Z * (xs.astype(np.float32) - np.float32(cx)) / np.float32(fx)
+    out[1] = Z * (ys.astype(np.float32) - np.float32(cy)) / np.float32(fy)
+    out[2] = Z
+    out[3] = 1.0
+    clr = np.asarray(bgr)[ys, xs].astype(np.float32) / np.float32(255.0)
+    out[4], out[5], out[6] = clr[:, 2], clr[:, 1], clr[:, 0]
+    out[7] = 1.0
+    return out
+
+
 class ImgPyramidRGBD:
     """``ImgPyramidRGBD(settings, cameraPyr, fullResRgb, fullResDepth, timestamp)`` --
     datastructures/imgpyramidrgbd.h:39-41.  ``rgb`` is HxWx3|4 uint8 in OpenCV BGR order,
@@ -369,11 +393,13 @@ class ImgPyramidRGBD:
         self.cameraPyr = cameraPyr or CameraPyr(settings)
         self.frameId = 0
         self._T_w_f = np.eye(4, dtype=np.float32)
+        self.rgbFullSize = None
         if _handle is not None:
             self.h = _handle
             return
         rgb = np.ascontiguousarray(rgb, np.uint8)
         depth = np.ascontiguousarray(depth, np.float32)
+        self.rgbFullSize = rgb                      # imgpyramidrgbd.cpp:51 keeps a clone for generateColoredPcl (viewer)
         assert rgb.ndim == 3 and rgb.shape[2] in (3, 4) and rgb.shape[:2] == (settings.height, settings.width)
         assert depth.shape == (settings.height, settings.width)
         cfg, cam = settings._c_cfg(), settings._c_cam()
@@ -496,6 +522,23 @@ class ImgPyramidRGBD:
 
     def isPointOkDepth(self, z) -> bool:
         return bool(np.isfinite(z) and self.mSettings.DEPTH_MIN < z < self.mSettings.DEPTH_MAX)
+
+    def generateColoredPcl(self, lvl: int, densePcl: bool = False) -> np.ndarray:
+        """``generateColoredPcl(lvl, clrPcl, densePcl)`` (imgpyramidrgbd.cpp:279-327): the viewer's coloured cloud, an
+        (8, N) float32 matrix of columns ``(X, Y, Z, 1, r, g, b, 1)``.  Host-side like the reference (not on the hot path):
+        depth and edges come from the device through the accessors, the colour image is the one kept at construction."""
+        if self.rgbFullSize is None:
+            raise RevoError(REVO_ERR_UNSUPPORTED, "generateColoredPcl needs the colour image (pyramid built from a batch handle)")
+        import cv2
+
+        rgb = self.rgbFullSize[:, :, :3]
+        if lvl > 2:                                  # the reference only fills `rgb` for levels 0..2: empty cloud
+            return np.zeros((8, 0), np.float32)
+        for _ in range(lvl):
+            rgb = cv2.pyrDown(rgb)
+        c = self._cam(lvl)
+        return colored_pcl_from_arrays(rgb, self.returnDepth(lvl), self.returnEdges(lvl), c.fx, c.fy, c.cx, c.cy,
+                                       self.mSettings.DEPTH_MIN, self.mSettings.DEPTH_MAX, densePcl)
 
     # -- test hook -----------------------------------------------------------
     def uploadLevel(self, lvl, pts4=None, dt=None, opt4=None):

@@ -179,3 +179,29 @@ def test_canny_tile_fallback_path(ctx, orc32):
         pg.makeKeyframe()
         po = _oracle_pyr(orc32, cam, 1, b, d)
         _compare(pg, po, 1)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("REVO_RUN_UNVALIDATED") != "1",
+                    reason="written after the round-1 GPU budget was spent: not yet run on hardware (set REVO_RUN_UNVALIDATED=1)")
+def test_colored_point_cloud_from_device_arrays(ctx, orc32):
+    """ImgPyramidRGBD.generateColoredPcl (viewer export, imgpyramidrgbd.cpp:279-327) over the device's depth / edge arrays
+    against the loop restatement over the oracle pyramid, levels 0..2 (colour reduced with pyrDown like the reference)."""
+    import cv2
+
+    from oracle import oracle as O
+    from revo_b200 import api
+
+    p = synth_pair(4, 320, 240)
+    bgr, depth = p["key"]
+    st = _settings(p["cam"], 3)
+    pg = api.ImgPyramidRGBD(ctx, st, None, bgr, depth)
+    po = _oracle_pyr(orc32, p["cam"], 3, bgr, depth, keyframe=False)
+    rgb = bgr
+    for lvl in range(3):
+        if lvl:
+            rgb = cv2.pyrDown(rgb)
+        c = po.cams[lvl]
+        for dense in (False, True):
+            want = O.generate_colored_pcl(rgb, po.depth[lvl], po.edges[lvl], (c.fx, c.fy, c.cx, c.cy, c.w, c.h), 0.1, 5.2, dense)
+            assert np.array_equal(pg.generateColoredPcl(lvl, dense), want)
+    assert pg.generateColoredPcl(3).shape == (8, 0)
