@@ -1,0 +1,166 @@
+// revo_system.hpp -- C++ mirror of the per-frame body of REVO::start (system/system.cpp:128-283) and of REVO::Pose
+// (system/system.h:89-150) over the classes of revo_host.hpp: motion-model initialisation, the tracking-quality vote,
+// "take the previous frame as keyframe and track again", pose-graph bookkeeping.  Header only.  It is the caller of the
+// hot path, not part of it: plain host logic, templated on the pyramid / tracker types so that the CPU test
+// (tests/cpp/test_host.cpp --selftest) can run it over fakes; `revo::REVOLoop` is the instantiation over the CUDA classes.
+// The same logic in Python: revo_b200/system.py.  IO, viewer, logging and pose output of the reference loop are out of scope.
+//
+// Required of PyrT:      void makeKeyframe(); void setTwf(const float T[16]); const float *getTransKFtoWorld() const;
+//                        double returnTimestamp() const; int frameId;
+// Required of TrackerT:  TrackerStatus-like int trackFrames(revo::Mat3f &R, revo::Vec3f &T, float &error, ref, cur);
+//                        int assessTrackingQuality(const float *pose16, cur); void addOldPclAndPose(cur, const float *pose16, double ts);
+//                        void clearUpPastLists();
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "revo_host.hpp"
+
+namespace revo {
+
+// Column-major 4x4, exactly Eigen::Matrix4f's storage.
+struct Mat4f {
+    float m[16];
+    static Mat4f Identity() { Mat4f r{}; r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.f; return r; }
+    static Mat4f fromPtr(const float *p) { Mat4f r; std::memcpy(r.m, p, sizeof(r.m)); return r; }
+    // transformFromRT (utils/...: [R T; 0 1])
+    static Mat4f fromRT(const Mat3f &R, const Vec3f &T) {
+        Mat4f r = Identity();
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i) r(i, j) = R(i, j);
+        for (int i = 0; i < 3; ++i) r(i, 3) = T[i];
+        return r;
+    }
+    float &operator()(int i, int j) { return m[j * 4 + i]; }
+    float operator()(int i, int j) const { return m[j * 4 + i]; }
+    const float *data() const { return m; }
+    Mat3f rotation() const { Mat3f R; for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) R(i, j) = (*this)(i, j); return R; }
+    Vec3f translation() const { return Vec3f{{(*this)(0, 3), (*this)(1, 3), (*this)(2, 3)}}; }
+    friend Mat4f operator*(const Mat4f &a, const Mat4f &b) {
+        Mat4f c{};
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) {
+                float s = 0.f;
+                for (int k = 0; k < 4; ++k) s += a(i, k) * b(k, j);
+                c(i, j) = s;
+            }
+        return c;
+    }
+    // inverse of a rigid transform (the reference calls Eigen's general .inverse() on SE3 matrices)
+    Mat4f inverseRigid() const {
+        Mat4f r = Identity();
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i) r(i, j) = (*this)(j, i);
+        for (int i = 0; i < 3; ++i) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += (double)(*this)(k, i) * (*this)(k, 3);
+            r(i, 3) = (float)-s;
+        }
+        return r;
+    }
+};
+
+enum { STATE_OK = 0, STATE_LOST = 1, STATE_NEW_KF = 2, STATE_UNKNOWN = 3 };   // TrackerNew::TrackerStatus, tracker.h:60-65
+
+// REVO::Pose (system/system.h:89-150): pose of a frame relative to its parent keyframe.
+template <class PyrT>
+class PoseT {
+public:
+    PoseT(const Mat4f &T_kf_curr, double timestamp, const std::shared_ptr<PyrT> &kfFrame)
+        : T_kf_curr_(T_kf_curr), timestamp_(timestamp), kfFrame_(kfFrame) {}
+    Mat4f getCurrToWorld() const { return Mat4f::fromPtr(kfFrame_->getTransKFtoWorld()) * T_kf_curr_; }   // T_W_KF * T_KF_CURR (:131-134)
+    Mat4f T_W_N() const { return getCurrToWorld(); }
+    Mat4f T_N_W() const { return getCurrToWorld().inverseRigid(); }
+    const Mat4f &T_kf_N() const { return T_kf_curr_; }
+    // only called when the "previous frame" becomes keyframe (system.h:140-146)
+    void setKfFrame(const std::shared_ptr<PyrT> &kfFrame) { kfFrame_ = kfFrame; T_kf_curr_ = Mat4f::Identity(); }
+    double returnTimestamp() const { return timestamp_; }
+    const std::shared_ptr<PyrT> &kfFrame() const { return kfFrame_; }
+
+private:
+    Mat4f T_kf_curr_;
+    double timestamp_;
+    std::shared_ptr<PyrT> kfFrame_;
+};
+
+// The tracking part of REVO::start for one stream: feed pyramids in order with processFrame().
+template <class PyrT, class TrackerT>
+class REVOLoopT {
+public:
+    explicit REVOLoopT(const std::shared_ptr<TrackerT> &tracker) : mTracker(tracker) {}
+
+    // One iteration of the while loop (system.cpp:147-275).  Returns the frame's pose in the world.
+    Mat4f processFrame(const std::shared_ptr<PyrT> &currPyr) {
+        TrackerT &trk = *mTracker;
+        currPyr->frameId = noFrames;
+        if (noFrames == 0) {                                    // first frame -> keyframe (system.cpp:151-175)
+            kfPyr = prevPyr = currPyr;
+            currPyr->makeKeyframe();
+            const Mat4f I = Mat4f::Identity();
+            currPyr->setTwf(I.data());
+            mPoseGraph.emplace_back(I, currPyr->returnTimestamp(), currPyr);
+            ++nKeyFrames; ++noFrames;
+            justAddedNewKeyframe = true;
+            trk.addOldPclAndPose(currPyr, I.data(), currPyr->returnTimestamp());
+            return I;
+        }
+        ++noFrames;
+        Mat3f r = R; Vec3f t = T;
+        (void)trk.trackFrames(r, t, error, kfPyr, currPyr);                                            // :188
+        Mat4f T_KF_N = Mat4f::fromRT(r, t);
+        Mat4f currPoseInWorld = Mat4f::fromPtr(kfPyr->getTransKFtoWorld()) * T_KF_N;                  // :192
+        int status = (int)trk.assessTrackingQuality(currPoseInWorld.data(), currPyr);                 // :199
+        if (status == STATE_NEW_KF && !justAddedNewKeyframe) {
+            // tracking gets inaccurate: take the previous frame as keyframe and optimise again (:203-239)
+            kfPyr = prevPyr;
+            const Mat4f T_w_prev = mPoseGraph.back().getCurrToWorld();
+            kfPyr->setTwf(T_w_prev.data());
+            kfPyr->makeKeyframe();
+            mPoseGraph.back().setKfFrame(kfPyr);
+            ++nKeyFrames;
+            trk.clearUpPastLists();
+            r = T_NM1_N.rotation(); t = T_NM1_N.translation();
+            (void)trk.trackFrames(r, t, error, kfPyr, currPyr);                                        // :225
+            T_KF_N = Mat4f::fromRT(r, t);
+            currPoseInWorld = Mat4f::fromPtr(kfPyr->getTransKFtoWorld()) * T_KF_N;
+            status = (int)trk.assessTrackingQuality(currPoseInWorld.data(), currPyr);
+            justAddedNewKeyframe = true;
+            retracked.push_back(currPyr->frameId);
+        } else {
+            justAddedNewKeyframe = false;
+        }
+        trackerStatus = status;
+        // add the frame to the pose graph, remember its edge cloud for the vote (:253-254)
+        mPoseGraph.emplace_back(T_KF_N, currPyr->returnTimestamp(), kfPyr);
+        trk.addOldPclAndPose(currPyr, currPoseInWorld.data(), currPyr->returnTimestamp());
+        // relative motion N-1 -> N and the constant-velocity guess for the next frame (:262-271)
+        const size_t n = mPoseGraph.size();
+        T_NM1_N = mPoseGraph[n - 2].T_N_W() * mPoseGraph[n - 1].T_W_N();
+        const Mat4f T_init = mPoseGraph[n - 1].T_kf_N() * T_NM1_N;
+        R = T_init.rotation(); T = T_init.translation();
+        prevPyr = currPyr;
+        return mPoseGraph.back().getCurrToWorld();
+    }
+
+    std::vector<Mat4f> trajectory() const {
+        std::vector<Mat4f> out;
+        for (const auto &p : mPoseGraph) out.push_back(p.getCurrToWorld());
+        return out;
+    }
+
+    std::shared_ptr<TrackerT> mTracker;
+    std::vector<PoseT<PyrT>> mPoseGraph;
+    std::shared_ptr<PyrT> kfPyr, prevPyr;
+    int noFrames = 0, nKeyFrames = 0, trackerStatus = STATE_UNKNOWN;
+    bool justAddedNewKeyframe = false;
+    Mat3f R = Mat3f::Identity();          // initial guess of the next frame relative to the keyframe
+    Vec3f T = Vec3f::Zero();
+    Mat4f T_NM1_N = Mat4f::Identity();
+    float error = 0.f;
+    std::vector<int> retracked;           // frame ids at which the previous frame was promoted and tracking repeated
+};
+
+}  // namespace revo
+
+// the instantiation over the CUDA classes of revo_host.hpp
+using REVOLoop = revo::REVOLoopT<ImgPyramidRGBD, TrackerNew>;

@@ -9,6 +9,71 @@
 #include <vector>
 
 #include "../../revo_b200/host/revo_host.hpp"
+#include "../../revo_b200/host/revo_system.hpp"
+
+// ---- fakes for the main-loop mirror (revo_system.hpp): a tracker that always reports 1 cm along x relative to the keyframe in
+// use and whose vote always asks for a new keyframe (the scenario of tests/test_system_host.py::test_forced_keyframe_switch)
+struct FakePyr {
+    explicit FakePyr(double ts) : ts_(ts) { const revo::Mat4f I = revo::Mat4f::Identity(); std::memcpy(T_, I.data(), sizeof(T_)); }
+    void makeKeyframe() { kf = true; }
+    void setTwf(const float T[16]) { std::memcpy(T_, T, sizeof(T_)); }
+    const float *getTransKFtoWorld() const { return T_; }
+    double returnTimestamp() const { return ts_; }
+    int frameId = 0;
+    bool kf = false;
+    double ts_;
+    float T_[16];
+};
+struct FakeTracker {
+    int cleared = 0, votes = 0, bad_ref = 0;
+    int trackFrames(revo::Mat3f &R, revo::Vec3f &T, float &error, const std::shared_ptr<FakePyr> &ref, const std::shared_ptr<FakePyr> &) {
+        if (!ref->kf) ++bad_ref;
+        R = revo::Mat3f::Identity(); T = revo::Vec3f{{0.01f, 0.f, 0.f}}; error = 0.1f;
+        return revo::STATE_OK;
+    }
+    int assessTrackingQuality(const float *, const std::shared_ptr<FakePyr> &) { ++votes; return revo::STATE_NEW_KF; }
+    void addOldPclAndPose(const std::shared_ptr<FakePyr> &, const float *, double) {}
+    void clearUpPastLists() { ++cleared; }
+};
+
+// compile check of the instantiation over the CUDA classes (never called here: it needs a device)
+__attribute__((unused)) static revo::Mat4f instantiate_real_loop(const std::shared_ptr<TrackerNew> &t, const std::shared_ptr<ImgPyramidRGBD> &p)
+{
+    REVOLoop loop(t);
+    return loop.processFrame(p);
+}
+
+static int selftest_main_loop()
+{
+    auto trk = std::make_shared<FakeTracker>();
+    revo::REVOLoopT<FakePyr, FakeTracker> sys(trk);
+    std::vector<std::shared_ptr<FakePyr>> frames;
+    for (int i = 0; i < 6; ++i) {
+        frames.push_back(std::make_shared<FakePyr>(0.033 * i));
+        sys.processFrame(frames.back());
+    }
+    // frame 0 is a keyframe; frame 1: vote NEW_KF but justAdded -> no switch; frame 2: switch to frame 1; 3: no; 4: switch to 3
+    const bool want_kf[6] = {true, true, false, true, false, false};
+    for (int i = 0; i < 6; ++i)
+        if (frames[i]->kf != want_kf[i]) return 30 + i;
+    if (sys.retracked != std::vector<int>{2, 4} || trk->cleared != 2 || sys.nKeyFrames != 3 || trk->bad_ref) return 40;
+    const float want_x[6] = {0.f, 0.01f, 0.02f, 0.02f, 0.03f, 0.03f};
+    const std::vector<revo::Mat4f> traj = sys.trajectory();
+    if (traj.size() != 6) return 41;
+    for (int i = 0; i < 6; ++i)
+        if (std::fabs(traj[i](0, 3) - want_x[i]) > 1e-6f) return 50 + i;
+    // motion model: the guess of the next frame is T_kf_N * T_NM1_N (system.cpp:268)
+    const revo::Mat4f T_init = sys.mPoseGraph.back().T_kf_N() * sys.T_NM1_N;
+    if (std::fabs(T_init(0, 3) - sys.T[0]) > 1e-6f || std::fabs(sys.R(0, 0) - 1.f) > 1e-6f) return 60;
+    // rigid inverse
+    revo::Mat4f A = revo::Mat4f::Identity();
+    A(0, 0) = 0.f; A(0, 1) = -1.f; A(1, 0) = 1.f; A(1, 1) = 0.f; A(0, 3) = 1.f; A(1, 3) = 2.f; A(2, 3) = 3.f;
+    const revo::Mat4f P = A * A.inverseRigid();
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (std::fabs(P(i, j) - (i == j ? 1.f : 0.f)) > 1e-6f) return 61;
+    return 0;
+}
 
 static int selftest()
 {
@@ -42,6 +107,7 @@ int main(int argc, char **argv)
 {
     if (argc >= 2 && !std::strcmp(argv[1], "--selftest")) {
         int rc = selftest();
+        if (!rc) rc = selftest_main_loop();
         if (rc) { std::printf("selftest failed: %d\n", rc); return rc; }
         try {
             revo::Context ctx(0);
