@@ -11,7 +11,11 @@
 //                        int assessTrackingQuality(const float *pose16, cur); void addOldPclAndPose(cur, const float *pose16, double ts);
 //                        void clearUpPastLists();
 #pragma once
+#include <cstdio>
+#include <fstream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include "revo_host.hpp"
@@ -159,6 +163,43 @@ public:
     float error = 0.f;
     std::vector<int> retracked;           // frame ids at which the previous frame was promoted and tracking repeated
 };
+
+// ---- dataset wire formats ------------------------------------------------------------------------
+// One line of a TUM association file, "rgb_ts rgb_file depth_ts depth_file" (io/iowrapperRGBD.cpp:301-333).
+struct Association {
+    double rgbTs, depthTs;
+    std::string rgbFile, depthFile;
+};
+// '#' comments and empty lines are ignored; the first skipFirstN data lines are skipped (SKIP_FIRST_N_FRAMES).
+inline std::vector<Association> readAssociations(const std::string &path, int skipFirstN = 0) {
+    std::vector<Association> out;
+    std::ifstream f(path);
+    if (!f) throw Error(REVO_ERR_INVALID_ARG, "cannot open " + path);
+    std::string line;
+    int n = 0;
+    while (std::getline(f, line)) {
+        const size_t b = line.find_first_not_of(" \t\r");
+        if (b == std::string::npos || line[b] == '#') continue;
+        if (++n <= skipFirstN) continue;
+        std::istringstream is(line);
+        Association a;
+        if (!(is >> a.rgbTs >> a.rgbFile >> a.depthTs >> a.depthFile)) throw Error(REVO_ERR_INVALID_ARG, "malformed association line: " + line);
+        out.push_back(a);
+    }
+    return out;
+}
+// "timestamp tx ty tz qx qy qz qw" as REVO::writePose formats it (system/system.cpp:75-79: std::fixed, 6 decimals for the
+// timestamp, setprecision(9) afterwards; quaternion = Eigen::Quaternionf(R)).
+inline std::string poseToTUMString(const Mat4f &T_w_c, double timestamp) {
+    float q[4];
+    const Mat3f R = T_w_c.rotation();
+    const int rc = revo_R9_to_quat(R.data(), q);
+    if (rc) throw Error(rc, revo_strerror(rc));
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "%.6f %.9f %.9f %.9f %.9f %.9f %.9f %.9f", timestamp, (double)T_w_c(0, 3), (double)T_w_c(1, 3),
+                  (double)T_w_c(2, 3), (double)q[0], (double)q[1], (double)q[2], (double)q[3]);
+    return buf;
+}
 
 }  // namespace revo
 

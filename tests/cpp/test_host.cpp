@@ -43,7 +43,7 @@ __attribute__((unused)) static revo::Mat4f instantiate_real_loop(const std::shar
     return loop.processFrame(p);
 }
 
-static int selftest_main_loop()
+static int selftest_main_loop(const char *self)
 {
     auto trk = std::make_shared<FakeTracker>();
     revo::REVOLoopT<FakePyr, FakeTracker> sys(trk);
@@ -65,6 +65,23 @@ static int selftest_main_loop()
     // motion model: the guess of the next frame is T_kf_N * T_NM1_N (system.cpp:268)
     const revo::Mat4f T_init = sys.mPoseGraph.back().T_kf_N() * sys.T_NM1_N;
     if (std::fabs(T_init(0, 3) - sys.T[0]) > 1e-6f || std::fabs(sys.R(0, 0) - 1.f) > 1e-6f) return 60;
+    // TUM wire formats: trajectory line and association list
+    revo::Mat4f W = revo::Mat4f::Identity();
+    W(0, 0) = 0.f; W(0, 1) = -1.f; W(1, 0) = 1.f; W(1, 1) = 0.f; W(0, 3) = 1.5f; W(1, 3) = -2.f; W(2, 3) = 0.25f;   // 90 deg about z
+    if (revo::poseToTUMString(W, 1305031102.175304) != "1305031102.175304 1.500000000 -2.000000000 0.250000000 0.000000000 0.000000000 0.707106769 0.707106769")
+        return 62;
+    {
+        const std::string path_s = std::string(self) + ".assoc_selftest.txt";   // next to the binary, removed below
+        const char *path = path_s.c_str();
+        FILE *f = std::fopen(path, "w");
+        if (!f) return 63;
+        std::fputs("# comment\n\n1.5 rgb/a.png 1.25 depth/a.png\n2.5 rgb/b.png 2.25 depth/b.png\n", f);
+        std::fclose(f);
+        const std::vector<revo::Association> a = revo::readAssociations(path);
+        if (a.size() != 2 || a[1].rgbFile != "rgb/b.png" || a[0].depthTs != 1.25 || a[1].depthFile != "depth/b.png") return 64;
+        if (revo::readAssociations(path, 1).size() != 1) return 65;
+        std::remove(path);
+    }
     // rigid inverse
     revo::Mat4f A = revo::Mat4f::Identity();
     A(0, 0) = 0.f; A(0, 1) = -1.f; A(1, 0) = 1.f; A(1, 1) = 0.f; A(0, 3) = 1.f; A(1, 3) = 2.f; A(2, 3) = 3.f;
@@ -107,7 +124,7 @@ int main(int argc, char **argv)
 {
     if (argc >= 2 && !std::strcmp(argv[1], "--selftest")) {
         int rc = selftest();
-        if (!rc) rc = selftest_main_loop();
+        if (!rc) rc = selftest_main_loop(argv[0]);
         if (rc) { std::printf("selftest failed: %d\n", rc); return rc; }
         try {
             revo::Context ctx(0);
