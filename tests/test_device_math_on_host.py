@@ -1,0 +1,144 @@
+"""The device source text of the per-point tracking arithmetic, compiled for the HOST and checked against the oracle -- a CPU
+test of what the GPU executes per edge point (the `-m gpu` tests check the same through the kernels).
+
+Taken verbatim from the CUDA sources (function text, extracted at test time): ``opt_texel`` / ``pack_grad`` / ``store_quad``
+(pyramid.cu: the 32-byte quad record with snorm16 gradients) and ``project_b`` / ``unpack_grad`` / ``finish_point_b``
+(track_common.cuh: warp, project, bounds, bilinear fetch, edge filter, Huber weight, Jacobian, normal-equation terms;
+optimizer.cpp:93-131, 204-228, LGSX.h:392-398).  Host shims replace the intrinsics (``rcp.approx`` -> 1/x, ``__float2int_rn``
+-> lrintf, ...); g++ fuses ``a * b + c`` like nvcc does (-mfma -ffp-contract=fast).  The summed record must agree with the
+float64 oracle to the tolerance of the GPU test (2e-5 per block, counts exact up to one border flip)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import synth_pair
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SHIM = r'''
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+struct uint4 { uint32_t x, y, z, w; };
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline int __float2int_rn(float a) { return (int)lrintf(a); }
+static inline float rcp_approx(float x) { return 1.0f / x; }
+constexpr int kRecA = 0, kRecB = 21, kRecSW = 27, kRecSU = 28, kRecGood = 29, kRecBad = 30;
+'''
+
+DRIVER = r'''
+extern "C" int host_eval_record(const float *pts4, int n, const float *dt, int w, int h, float fx, float fy, float cx, float cy,
+                                const float *R9, const float *t3, float ed, int use_filter, float huber, double *rec32)
+{
+    const size_t npx = (size_t)w * h;
+    std::vector<uint4> opt(2 * npx);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = 0; i < npx; ++i) {                      // k_opt_struct, pyramid.cu
+        const float4 a = opt_texel(dt, i, w, h);
+        const float4 b = (i + 1 < npx) ? opt_texel(dt, i + 1, w, h) : z;
+        const float4 c = (i + w < npx) ? opt_texel(dt, i + w, w, h) : z;
+        const float4 d = (i + w + 1 < npx) ? opt_texel(dt, i + w + 1, w, h) : z;
+        store_quad(opt.data(), i, a, b, c, d);
+    }
+    LevelConst L;
+    L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.umax = (float)(w - 2); L.vmax = (float)(h - 2); L.w = w; L.opt = opt.data();
+    for (int i = 0; i < 32; ++i) rec32[i] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const float4 p = make_float4(pts4[4 * i], pts4[4 * i + 1], pts4[4 * i + 2], 1.f);
+        const ProjB P = project_b(true, p, L, R9, t3);
+        const uint32_t *q = (const uint32_t *)P.bp;        // ldg_quad: one 32-byte record -> the two row records
+        const uint4 r0 = make_uint4(q[0], q[1], q[4], q[5]), r1 = make_uint4(q[2], q[3], q[6], q[7]);
+        float acc[32] = {0};
+        finish_point_b(P, r0, r1, L, ed, use_filter != 0, huber, acc);
+        for (int k = 0; k < 32; ++k) rec32[k] += acc[k];
+    }
+    return 0;
+}
+'''
+
+
+def _grab(text, start_pat):
+    m = re.search(start_pat, text, re.M)
+    assert m, start_pat
+    j = text.index("\n}", m.start())
+    return text[m.start():text.index("\n", j + 1) + 1]
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    common = open(os.path.join(ROOT, "revo_b200", "csrc", "track_common.cuh")).read()
+    pyr = open(os.path.join(ROOT, "revo_b200", "csrc", "pyramid.cu")).read()
+    parts = [_grab(pyr, r"^__device__ __forceinline__ float4 opt_texel"), _grab(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
+             _grab(pyr, r"^__device__ __forceinline__ void store_quad"), _grab(common, r"^__device__ __forceinline__ void unpack_grad"),
+             _grab(common, r"^struct ProjB \{"), _grab(common, r"^struct LevelConst \{"),
+             _grab(common, r"^__device__ __forceinline__ ProjB project_b"), _grab(common, r"^__device__ __forceinline__ void finish_point_b")]
+    d = tmp_path_factory.mktemp("host_math")
+    src, lib = str(d / "device_math.cpp"), str(d / "libdevice_math.so")
+    open(src, "w").write(SHIM + "\n".join(parts) + DRIVER)
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", src, "-o", lib], check=True)
+    return C.CDLL(lib)
+
+
+def _host_record(lib, pts4, dt, cam, R, T, ed, use_filter, huber):
+    pts4 = np.ascontiguousarray(pts4, np.float32)
+    dt = np.ascontiguousarray(dt, np.float32)
+    R9 = np.ascontiguousarray(np.asarray(R, np.float32).T.reshape(-1))      # column-major, as the C ABI takes it
+    t3 = np.ascontiguousarray(T, np.float32)
+    rec = np.zeros(32, np.float64)
+    f = C.c_float
+    lib.host_eval_record(pts4.ctypes.data_as(C.c_void_p), C.c_int(len(pts4)), dt.ctypes.data_as(C.c_void_p), C.c_int(cam.w), C.c_int(cam.h),
+                         f(cam.fx), f(cam.fy), f(cam.cx), f(cam.cy), R9.ctypes.data_as(C.c_void_p), t3.ctypes.data_as(C.c_void_p),
+                         f(ed), C.c_int(int(use_filter)), f(huber), rec.ctypes.data_as(C.c_void_p))
+    return rec
+
+
+def _rec_close(g, o, tol=2e-5, max_flips=1):
+    flips = abs(g[29] - o[29])
+    assert flips <= max_flips and g[29] + g[30] == o[29] + o[30], (g[29:31], o[29:31])
+    if flips:
+        tol = max(tol, 3.0 * flips / max(o[29], 1.0))
+    sA = np.abs(o[:21]).max() + 1e-30
+    sb = np.abs(o[:21]).max() ** 0.5 * np.abs(o[27]) ** 0.5 + 1e-30
+    assert np.abs(g[:21] - o[:21]).max() <= tol * sA
+    assert np.abs(g[21:27] - o[21:27]).max() <= tol * sb
+    assert abs(g[27] - o[27]) <= tol * abs(o[27]) + 1e-12
+    assert abs(g[28] - o[28]) <= tol * abs(o[28]) + 1e-12
+
+
+@pytest.mark.parametrize("seed", [1, 21])
+def test_device_point_math_matches_oracle_record(host_lib, orc64, seed):
+    from oracle import oracle as O
+    from revo_b200 import synth
+
+    p = synth_pair(seed, 320, 240)
+    cfg = O.PyrCfg(n_levels=3)
+    kf = O.build_pyramid(orc64, cfg, p["cam"], *p["key"])
+    O.make_keyframe(orc64, kf)
+    cur = O.build_pyramid(orc64, cfg, p["cam"], *p["cur"])
+    ocfg = orc64.default_cfg()
+    near = synth.se3_exp([0.002, -0.001, 0.0015, 0.001, -0.0005, 0.0007])
+    far = synth.se3_exp([0.05, -0.03, 0.02, 0.02, -0.03, 0.01])
+    for lvl in range(3):
+        for M in (near, p["T_kf_cur"], far):
+            R32, T32 = np.asarray(M[:3, :3], np.float32), np.asarray(M[:3, 3], np.float32)
+            for use_filter in (1, 0):
+                ocfg.use_edge_filter = use_filter
+                o = orc64.eval_record(cur.edges3d[lvl], kf.opt[lvl], cur.cams[lvl], R32, T32, ocfg, lvl)
+                g = _host_record(host_lib, cur.edges3d[lvl], kf.dt[lvl], cur.cams[lvl], R32, T32, ocfg.edge_distance_lvl[lvl],
+                                 use_filter, ocfg.huber_edge)
+                assert o[29] > 100
+                _rec_close(g, o)
