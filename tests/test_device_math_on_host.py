@@ -37,6 +37,8 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline int __float2int_rn(float a) { return (int)lrintf(a); }
 static inline float rcp_approx(float x) { return 1.0f / x; }
+static inline double __drcp_rn(double x) { return 1.0 / x; }
+#include "revo_b200.h"
 constexpr int kRecA = 0, kRecB = 21, kRecSW = 27, kRecSU = 28, kRecGood = 29, kRecBad = 30;
 '''
 
@@ -68,6 +70,37 @@ extern "C" int host_eval_record(const float *pts4, int n, const float *dt, int w
     }
     return 0;
 }
+
+// The level loop of k_track (track.cu) on one host thread: evaluate, lm_step, repeat until the level is done.
+extern "C" int host_track_level(const float *pts4, int n, const float *dt, int w, int h, float fx, float fy, float cx, float cy,
+                                float *R9_inout, float *t3_inout, const revo_opt_config *oc, int lvl, float *err_out, int *n_evals_out,
+                                double *last_rec32)
+{
+    LMState lm;
+    std::memset(&lm, 0, sizeof(lm));
+    float R[9], t[3];
+    std::memcpy(R, R9_inout, sizeof(R));
+    std::memcpy(t, t3_inout, sizeof(t));
+    quat_from_R(R, lm.q);
+    for (int i = 0; i < 3; ++i) lm.t[i] = t[i];
+    lm.last_residual = INFINITY;
+    bool first = true;
+    int evals = 0;
+    while (true) {
+        host_eval_record(pts4, n, dt, w, h, fx, fy, cx, cy, R, t, oc->edge_distance_lvl[lvl], oc->use_edge_filter, oc->huber_edge, last_rec32);
+        ++evals;
+        revo_trace_entry te;
+        bool traced;
+        const bool done = lm_step(lm, last_rec32, *oc, lvl, first, R, t, &te, &traced);
+        first = false;
+        if (done || evals > 10000) break;
+    }
+    std::memcpy(R9_inout, R, sizeof(R));
+    std::memcpy(t3_inout, t, sizeof(t));
+    *err_out = lm.last_residual;
+    *n_evals_out = evals;
+    return 0;
+}
 '''
 
 
@@ -85,11 +118,16 @@ def host_lib(tmp_path_factory):
     parts = [_grab(pyr, r"^__device__ __forceinline__ float4 opt_texel"), _grab(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
              _grab(pyr, r"^__device__ __forceinline__ void store_quad"), _grab(common, r"^__device__ __forceinline__ void unpack_grad"),
              _grab(common, r"^struct ProjB \{"), _grab(common, r"^struct LevelConst \{"),
-             _grab(common, r"^__device__ __forceinline__ ProjB project_b"), _grab(common, r"^__device__ __forceinline__ void finish_point_b")]
+             _grab(common, r"^__device__ __forceinline__ ProjB project_b"), _grab(common, r"^__device__ __forceinline__ void finish_point_b"),
+             _grab(common, r"^struct LMState \{"), _grab(common, r"^__device__ __forceinline__ void quat_to_R"),
+             _grab(common, r"^__device__ inline void quat_from_R"), _grab(common, r"^__device__ __forceinline__ void se3_exp"),
+             _grab(common, r"^__device__ __forceinline__ void se3_mul"), _grab(common, r"^__device__ __forceinline__ void solve6"),
+             _grab(common, r"^__device__ __forceinline__ bool lm_step")]
     d = tmp_path_factory.mktemp("host_math")
     src, lib = str(d / "device_math.cpp"), str(d / "libdevice_math.so")
     open(src, "w").write(SHIM + "\n".join(parts) + DRIVER)
-    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", src, "-o", lib], check=True)
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                    src, "-o", lib], check=True)
     return C.CDLL(lib)
 
 
@@ -142,3 +180,46 @@ def test_device_point_math_matches_oracle_record(host_lib, orc64, seed):
                                  use_filter, ocfg.huber_edge)
                 assert o[29] > 100
                 _rec_close(g, o)
+
+
+@pytest.mark.parametrize("seed,n_tries", [(1, 8), (22, 5)])
+def test_device_lm_loop_matches_oracle_after_same_iterations(host_lib, orc64, seed, n_tries):
+    """The level loop of k_track on one host thread -- per-point arithmetic + ``lm_step`` (6x6 LDL^T, SE3 exp / product,
+    accept / reject, lambda schedule) from the device source text -- against the oracle's ``Optimizer::trackFrames`` after
+    the SAME number of LM tries: <= 1e-4 rad / 1e-4 m (the tolerance of the path), same evaluation count."""
+    from oracle import oracle as O
+    from revo_b200 import api, synth
+    from conftest import rot_angle
+
+    p = synth_pair(seed, 320, 240)
+    cfg = O.PyrCfg(n_levels=3)
+    kf = O.build_pyramid(orc64, cfg, p["cam"], *p["key"])
+    O.make_keyframe(orc64, kf)
+    cur = O.build_pyramid(orc64, cfg, p["cam"], *p["cur"])
+    T0 = synth.se3_exp([0.002, -0.001, 0.0015, 0.001, -0.0005, 0.0007])
+    R, T = np.asarray(T0[:3, :3], np.float32), np.asarray(T0[:3, 3], np.float32)
+    Ro, To = R.copy(), T.copy()
+    s = api.OptimizerSettings(USE_EDGE_FILTER=True, max_lm_tries=n_tries, convergenceEps=[2.0] * 6)
+    oc = s._c()
+    f = C.c_float
+    for lvl in (2, 1, 0):
+        ocfg = orc64.default_cfg()
+        for l in range(6):
+            ocfg.convergence_eps[l] = 2.0
+        r = orc64.track_level(cur.edges3d[lvl], kf.opt[lvl], cur.cams[lvl], Ro, To, ocfg, lvl, max_tries=n_tries)
+        Ro, To = r["R"].astype(np.float32), r["T"].astype(np.float32)
+        cam = cur.cams[lvl]
+        pts4 = np.ascontiguousarray(cur.edges3d[lvl], np.float32)
+        dt = np.ascontiguousarray(kf.dt[lvl], np.float32)
+        R9 = np.ascontiguousarray(R.T.reshape(-1))
+        t3 = np.ascontiguousarray(T)
+        err, n_evals, rec = C.c_float(0), C.c_int(0), np.zeros(32, np.float64)
+        host_lib.host_track_level(pts4.ctypes.data_as(C.c_void_p), C.c_int(len(pts4)), dt.ctypes.data_as(C.c_void_p), C.c_int(cam.w),
+                                  C.c_int(cam.h), f(cam.fx), f(cam.fy), f(cam.cx), f(cam.cy), R9.ctypes.data_as(C.c_void_p),
+                                  t3.ctypes.data_as(C.c_void_p), C.byref(oc), C.c_int(lvl), C.byref(err), C.byref(n_evals),
+                                  rec.ctypes.data_as(C.c_void_p))
+        R, T = R9.reshape(3, 3).T.copy(), t3.copy()
+        assert n_evals.value == r["n_evals"], (lvl, n_evals.value, r["n_evals"])
+        assert rot_angle(R, Ro) <= 1e-4 and np.linalg.norm(T - To) <= 1e-4, (lvl, rot_angle(R, Ro), np.linalg.norm(T - To))
+        assert abs(err.value - r["error"]) <= 1e-4 * max(1.0, abs(r["error"]))
+        assert int(rec[29]) == r["good"] and int(rec[30]) == r["bad"]
