@@ -40,6 +40,8 @@ static inline float rcp_approx(float x) { return 1.0f / x; }
 static inline double __drcp_rn(double x) { return 1.0 / x; }
 #include "revo_b200.h"
 constexpr int kRecA = 0, kRecB = 21, kRecSW = 27, kRecSU = 28, kRecGood = 29, kRecBad = 30;
+struct LevelIn { float fx, fy, cx, cy; int w, h; };   // the fields of internal.h's LevelIn that cost_point reads
+static inline float __ldg(const float *p) { return *p; }
 '''
 
 DRIVER = r'''
@@ -69,6 +71,22 @@ extern "C" int host_eval_record(const float *pts4, int n, const float *dt, int w
         for (int k = 0; k < 32; ++k) rec32[k] += acc[k];
     }
     return 0;
+}
+
+// checkInitializationValues / evalCostFunction (tracker.cpp:265-283, 357-393): the cost sum of k_track's init check
+extern "C" double host_cost(const float *pts4, int n, const float *dt, int w, int h, float fx, float fy, float cx, float cy,
+                            const float *R9, const float *t3, float ed, int use_filter)
+{
+    LevelIn L{fx, fy, cx, cy, w, h};
+    double s = 0;
+    for (int i = 0; i < n; ++i) {
+        const float x = pts4[4 * i], y = pts4[4 * i + 1], z = pts4[4 * i + 2];
+        const float X = R9[0] * x + R9[3] * y + R9[6] * z + t3[0];
+        const float Y = R9[1] * x + R9[4] * y + R9[7] * z + t3[1];
+        const float Z = R9[2] * x + R9[5] * y + R9[8] * z + t3[2];
+        s += cost_point(X, Y, Z, L, dt, ed, use_filter != 0);
+    }
+    return s;
 }
 
 // The level loop of k_track (track.cu) on one host thread: evaluate, lm_step, repeat until the level is done.
@@ -122,7 +140,7 @@ def host_lib(tmp_path_factory):
              _grab(common, r"^struct LMState \{"), _grab(common, r"^__device__ __forceinline__ void quat_to_R"),
              _grab(common, r"^__device__ inline void quat_from_R"), _grab(common, r"^__device__ __forceinline__ void se3_exp"),
              _grab(common, r"^__device__ __forceinline__ void se3_mul"), _grab(common, r"^__device__ __forceinline__ void solve6"),
-             _grab(common, r"^__device__ __forceinline__ bool lm_step")]
+             _grab(common, r"^__device__ __forceinline__ bool lm_step"), _grab(common, r"^__device__ __forceinline__ float cost_point")]
     d = tmp_path_factory.mktemp("host_math")
     src, lib = str(d / "device_math.cpp"), str(d / "libdevice_math.so")
     open(src, "w").write(SHIM + "\n".join(parts) + DRIVER)
@@ -223,3 +241,33 @@ def test_device_lm_loop_matches_oracle_after_same_iterations(host_lib, orc64, se
         assert rot_angle(R, Ro) <= 1e-4 and np.linalg.norm(T - To) <= 1e-4, (lvl, rot_angle(R, Ro), np.linalg.norm(T - To))
         assert abs(err.value - r["error"]) <= 1e-4 * max(1.0, abs(r["error"]))
         assert int(rec[29]) == r["good"] and int(rec[30]) == r["bad"]
+
+
+def test_device_init_check_cost_matches_oracle(host_lib, orc32, orc64):
+    """``cost_point`` (the init check of k_track: evalCostFunction, tracker.cpp:357-393) summed on the host vs the oracle."""
+    from oracle import oracle as O
+    from revo_b200 import synth
+
+    p = synth_pair(3, 320, 240)
+    cfg = O.PyrCfg(n_levels=3)
+    kf = O.build_pyramid(orc64, cfg, p["cam"], *p["key"])
+    O.make_keyframe(orc64, kf)
+    cur = O.build_pyramid(orc64, cfg, p["cam"], *p["cur"])
+    ocfg = orc64.default_cfg()
+    host_lib.host_cost.restype = C.c_double
+    f = C.c_float
+    lvl = 2
+    cam = cur.cams[lvl]
+    pts4 = np.ascontiguousarray(cur.edges3d[lvl], np.float32)
+    dt = np.ascontiguousarray(kf.dt[lvl], np.float32)
+    for M in (np.eye(4), p["T_kf_cur"], synth.se3_exp([0.05, -0.03, 0.02, 0.02, -0.03, 0.01])):
+        R32, T32 = np.asarray(M[:3, :3], np.float32), np.asarray(M[:3, 3], np.float32)
+        R9 = np.ascontiguousarray(R32.T.reshape(-1))
+        # at the identity every point projects exactly onto a pixel corner and float32 / float64 floor differently (the two
+        # oracle precisions disagree there as well): compare with the float32 oracle, which does the device's operations
+        ident = np.array_equal(M, np.eye(4))
+        want = (orc32 if ident else orc64).eval_cost_function(pts4, dt, cam, R32, T32, (orc32 if ident else orc64).default_cfg(), lvl)
+        got = host_lib.host_cost(pts4.ctypes.data_as(C.c_void_p), C.c_int(len(pts4)), dt.ctypes.data_as(C.c_void_p), C.c_int(cam.w),
+                                 C.c_int(cam.h), f(cam.fx), f(cam.fy), f(cam.cx), f(cam.cy), R9.ctypes.data_as(C.c_void_p),
+                                 T32.ctypes.data_as(C.c_void_p), f(ocfg.edge_distance_lvl[lvl]), C.c_int(1))
+        assert want > 0 and abs(got - want) <= 2e-3 * want, (ident, got, want)      # a point on a pixel border may flip its texel
