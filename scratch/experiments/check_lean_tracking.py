@@ -32,18 +32,9 @@ extern "C" void host_select_lean(int on) { g_lean = on != 0; }
 
 
 def main():
-    common = open(os.path.join(ROOT, "revo_b200", "csrc", "track_common.cuh")).read()
-    pyr = open(os.path.join(ROOT, "revo_b200", "csrc", "pyramid.cu")).read()
     lean = open(os.path.join(ROOT, "scratch", "experiments", "track_lean.cu")).read()
     g = H._grab
-    parts = [g(pyr, r"^__device__ __forceinline__ float4 opt_texel"), g(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
-             g(pyr, r"^__device__ __forceinline__ void store_quad"), g(common, r"^__device__ __forceinline__ void unpack_grad"),
-             g(common, r"^struct ProjB \{"), g(common, r"^struct LevelConst \{"),
-             g(common, r"^__device__ __forceinline__ ProjB project_b"), g(common, r"^__device__ __forceinline__ void finish_point_b"),
-             g(common, r"^struct LMState \{"), g(common, r"^__device__ __forceinline__ void quat_to_R"),
-             g(common, r"^__device__ inline void quat_from_R"), g(common, r"^__device__ __forceinline__ void se3_exp"),
-             g(common, r"^__device__ __forceinline__ void se3_mul"), g(common, r"^__device__ __forceinline__ void solve6"),
-             g(common, r"^__device__ __forceinline__ bool lm_step")]
+    parts = H.device_parts()
     lean_parts = [g(lean, r"^__device__ __forceinline__ ProjB project_l"), g(lean, r"^struct PackedAcc \{"),
                   g(lean, r"^__device__ __forceinline__ void finish_point_p")]
     driver = H.DRIVER.replace(

@@ -129,18 +129,23 @@ def _grab(text, start_pat):
     return text[m.start():text.index("\n", j + 1) + 1]
 
 
-@pytest.fixture(scope="module")
-def host_lib(tmp_path_factory):
+def device_parts():
+    """The function / struct texts taken from the CUDA sources, in dependency order."""
     common = open(os.path.join(ROOT, "revo_b200", "csrc", "track_common.cuh")).read()
     pyr = open(os.path.join(ROOT, "revo_b200", "csrc", "pyramid.cu")).read()
-    parts = [_grab(pyr, r"^__device__ __forceinline__ float4 opt_texel"), _grab(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
-             _grab(pyr, r"^__device__ __forceinline__ void store_quad"), _grab(common, r"^__device__ __forceinline__ void unpack_grad"),
-             _grab(common, r"^struct ProjB \{"), _grab(common, r"^struct LevelConst \{"),
-             _grab(common, r"^__device__ __forceinline__ ProjB project_b"), _grab(common, r"^__device__ __forceinline__ void finish_point_b"),
-             _grab(common, r"^struct LMState \{"), _grab(common, r"^__device__ __forceinline__ void quat_to_R"),
-             _grab(common, r"^__device__ inline void quat_from_R"), _grab(common, r"^__device__ __forceinline__ void se3_exp"),
-             _grab(common, r"^__device__ __forceinline__ void se3_mul"), _grab(common, r"^__device__ __forceinline__ void solve6"),
-             _grab(common, r"^__device__ __forceinline__ bool lm_step"), _grab(common, r"^__device__ __forceinline__ float cost_point")]
+    return [_grab(pyr, r"^__device__ __forceinline__ float4 opt_texel"), _grab(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
+            _grab(pyr, r"^__device__ __forceinline__ void store_quad"), _grab(common, r"^__device__ __forceinline__ void unpack_grad"),
+            _grab(common, r"^struct ProjB \{"), _grab(common, r"^struct LevelConst \{"),
+            _grab(common, r"^__device__ __forceinline__ ProjB project_b"), _grab(common, r"^__device__ __forceinline__ void finish_point_b"),
+            _grab(common, r"^struct LMState \{"), _grab(common, r"^__device__ __forceinline__ void quat_to_R"),
+            _grab(common, r"^__device__ inline void quat_from_R"), _grab(common, r"^__device__ __forceinline__ void se3_exp"),
+            _grab(common, r"^__device__ __forceinline__ void se3_mul"), _grab(common, r"^__device__ __forceinline__ void solve6"),
+            _grab(common, r"^__device__ __forceinline__ bool lm_step"), _grab(common, r"^__device__ __forceinline__ float cost_point")]
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    parts = device_parts()
     d = tmp_path_factory.mktemp("host_math")
     src, lib = str(d / "device_math.cpp"), str(d / "libdevice_math.so")
     open(src, "w").write(SHIM + "\n".join(parts) + DRIVER)
