@@ -3,7 +3,7 @@
 the kernel emulation layer of tests/_cuda_emu.py, against the library kernel k_track on the same layer and against the
 float64 oracle after the same number of LM tries.  Covers what the static checks cannot: the two pipelined segments
 (cached points / uncached tail, pcap 18 and 2), the per-thread trip counts, the shared-memory addressing, the reduction
-and the level loop.  Clusters of one CTA only (the multi-CTA exchange is unchanged from track.cu and needs the hardware).
+the level loop and the one-sided exchange of multi-CTA clusters (emulated distributed shared memory + transaction barriers).
 
   python scratch/experiments/check_lean_kernel.py
 """
@@ -34,8 +34,8 @@ def main():
         for n_tries in (5,):
             ref = {}
             for variant, name in ((0, "k_track"), (1, "k_track_lean"), (2, "k_track_lean packed")):
-                for n_ctas, pcap in ((1, 18), (2, 2), (1, 0)):
-                    out, _ = TK.run_kernel(lib, variant, pairs, TK.tracker_cfg(n_tries), n_ctas=n_ctas, pcap=pcap)
+                for n_ctas, pcap, cpp in ((1, 18, 1), (2, 2, 1), (1, 0, 1), (1, 3, 2), (1, 18, 4)):
+                    out, _ = TK.run_kernel(lib, variant, pairs, TK.tracker_cfg(n_tries), n_ctas=n_ctas, pcap=pcap, ctas_per_pair=cpp)
                     for i, (kf, cur, _, _) in enumerate(pairs):
                         Ro, To, evals, last = TK.oracle_chain(orc, kf, cur, R0, t0, n_tries)
                         R = out["R"][i].reshape(3, 3).T
@@ -45,11 +45,11 @@ def main():
                         assert dr <= 1e-4 and dt <= 1e-4, (name, dr, dt)
                         worst = max(worst, dr, dt)
                         if variant == 0:
-                            ref[(n_ctas, pcap, i)] = out[i].copy()
+                            ref[(n_ctas, pcap, cpp, i)] = out[i].copy()
                         else:
-                            b = ref[(n_ctas, pcap, i)]
+                            b = ref[(n_ctas, pcap, cpp, i)]
                             assert np.abs(out["R"][i] - b["R"]).max() < 1e-6 and np.abs(out["t"][i] - b["t"]).max() < 1e-6
-                print(f"{name:22s} ok (pcap 18 / 2 / 0, one and two CTAs, {n_tries} LM tries per level)")
+                print(f"{name:22s} ok (pcap 18 / 2 / 0, clusters of 1, 2 and 4 CTAs, {n_tries} LM tries per level)")
         # default termination rules and the init check: same decisions as the library kernel
         cfg = TK.tracker_cfg(0, check_init=1)
         for l in range(6):

@@ -2,11 +2,12 @@
 
 The kernel source text (track.cu: k_track; optionally scratch/experiments/track_lean.cu: k_track_lean) and the device helpers
 (track_common.cuh, the quad-record packing of pyramid.cu) are extracted from the CUDA files at test time and compiled with g++
-against a small emulation layer: one OS thread per CUDA thread of a CTA, pthread barriers for __syncthreads / the warp
-shuffles, `static` storage for __shared__, a one-CTA "cluster", host versions of the few PTX helpers (256-bit gather,
-rcp.approx, shared-memory loads of the experiment).  CTAs run one after the other (the persistent kernels pull pairs from a
-work counter, so that is a valid schedule for clusters of one CTA).  What this does NOT cover: the distributed-shared-memory
-exchange of clusters with more than one CTA and the multi-GPU mailboxes -- those paths need the hardware.
+against a small emulation layer: one OS thread per CUDA thread, pthread barriers for __syncthreads / the warp shuffles /
+cluster.sync(), a per-CTA arena for the __shared__ variables (same offsets in every CTA, so that distributed shared memory is
+an offset into the peer's arena), mbarriers with transaction counts as 64-bit atomics, st.async as store + complete_tx, host
+versions of the other PTX helpers (256-bit gather, rcp.approx, shared-memory loads of the experiment).  The CTAs of a cluster
+run concurrently, clusters one after the other (the persistent kernels pull pairs from a work counter, so that is a valid
+schedule).  What this does NOT cover: the multi-GPU mailboxes, and of course timing.
 """
 import ctypes as C
 import os
@@ -17,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 PRELUDE = r'''
 #include <pthread.h>
+#include <sched.h>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -36,32 +38,73 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 
 namespace emu {
 struct D3 { unsigned x, y, z; };
+constexpr int kMaxWarps = 32, kArenaBytes = 64 * 1024, kMaxSlots = 32;
+struct Cluster;
+struct Cta {                        // one thread block: its barriers, shuffle slots and "shared memory"
+    int rank;
+    Cluster *cluster;
+    D3 bidx;
+    pthread_barrier_t bar, warp_bar[kMaxWarps];
+    float shfl_slot[kMaxWarps][32];
+    alignas(64) char arena[kArenaBytes];      // the __shared__ variables of the kernel, same offsets in every CTA
+    std::vector<float> dyn;                   // dynamic shared memory
+};
+struct Cluster {
+    int n_ctas;
+    std::vector<Cta *> cta;
+    pthread_barrier_t bar;                    // cluster.sync()
+    pthread_mutex_t mu;
+    size_t slot_off[kMaxSlots];
+    bool slot_set[kMaxSlots];
+    size_t used;
+};
 static thread_local D3 tidx;
-static D3 bidx, bdim, gdim;
-static float *dyn_smem;
-static pthread_barrier_t cta_bar, warp_bar[32];
-static float shfl_slot[32][32];
+static thread_local Cta *cta;
+static D3 bdim, gdim;
+// storage of the k-th __shared__ declaration of the kernel (first caller of the cluster fixes the offset)
+static inline void *smem_slot(int k, size_t bytes, size_t align)
+{
+    Cluster *cl = cta->cluster;
+    pthread_mutex_lock(&cl->mu);
+    if (!cl->slot_set[k]) {
+        cl->used = (cl->used + align - 1) / align * align;
+        cl->slot_off[k] = cl->used;
+        cl->used += bytes;
+        cl->slot_set[k] = true;
+        if (cl->used > (size_t)kArenaBytes) std::abort();
+    }
+    const size_t off = cl->slot_off[k];
+    pthread_mutex_unlock(&cl->mu);
+    return cta->arena + off;
+}
+// the same shared-memory address in CTA `rank` of the cluster (distributed shared memory)
+template <class T> static inline T *map_rank(T *p, unsigned rank)
+{
+    const char *base = cta->arena;
+    const ptrdiff_t off = (const char *)p - base;
+    if (off < 0 || off >= (ptrdiff_t)kArenaBytes) std::abort();
+    return (T *)(cta->cluster->cta[rank]->arena + off);
+}
 }
 #define threadIdx emu::tidx
-#define blockIdx emu::bidx
+#define blockIdx emu::cta->bidx
 #define blockDim emu::bdim
 #define gridDim emu::gdim
 #define __global__
 #define __device__
 #define __forceinline__ inline
 #define __restrict__
-#define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 #define __launch_bounds__(...)
-static inline void __syncthreads() { pthread_barrier_wait(&emu::cta_bar); }
-static inline void __syncwarp() { pthread_barrier_wait(&emu::warp_bar[emu::tidx.x >> 5]); }
+static inline void __syncthreads() { pthread_barrier_wait(&emu::cta->bar); }
+static inline void __syncwarp() { pthread_barrier_wait(&emu::cta->warp_bar[emu::tidx.x >> 5]); }
 static inline float __shfl_xor_sync(unsigned, float v, int m)
 {
     const int lane = emu::tidx.x & 31, w = emu::tidx.x >> 5;
-    emu::shfl_slot[w][lane] = v;
-    pthread_barrier_wait(&emu::warp_bar[w]);
-    const float r = emu::shfl_slot[w][lane ^ m];
-    pthread_barrier_wait(&emu::warp_bar[w]);
+    emu::cta->shfl_slot[w][lane] = v;
+    pthread_barrier_wait(&emu::cta->warp_bar[w]);
+    const float r = emu::cta->shfl_slot[w][lane ^ m];
+    pthread_barrier_wait(&emu::cta->warp_bar[w]);
     return r;
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
@@ -78,10 +121,10 @@ static inline double __drcp_rn(double x) { return 1.0 / x; }
 static inline float __fdividef(float a, float b) { return a / b; }
 namespace cooperative_groups {
 struct cluster_group {
-    unsigned num_blocks() const { return 1; }
-    unsigned block_rank() const { return 0; }
-    void sync() const { __syncthreads(); }
-    template <class T> T *map_shared_rank(T *p, int) const { return p; }
+    unsigned num_blocks() const { return (unsigned)emu::cta->cluster->n_ctas; }
+    unsigned block_rank() const { return (unsigned)emu::cta->rank; }
+    void sync() const { pthread_barrier_wait(&emu::cta->cluster->bar); }
+    template <class T> T *map_shared_rank(T *p, int r) const { return emu::map_rank(p, (unsigned)r); }
 };
 static inline cluster_group this_cluster() { return cluster_group(); }
 }
@@ -97,22 +140,43 @@ static inline void ldg_quad(const uint4 *p, uint4 &r0, uint4 &r1)
 }
 template <int kHint> static inline void ldg_quad_h(const uint4 *p, uint4 &r0, uint4 &r1) { ldg_quad(p, r0, r1); }
 static inline float rcp_approx(float x) { return 1.0f / x; }
-static inline uint32_t smem_u32(const void *p) { return (uint32_t)((const char *)p - (const char *)emu::dyn_smem); }   // only meaningful for the dynamic buffer
-static inline void mbar_init(uint64_t *, uint32_t) {}
-static inline void mbar_expect_tx(uint64_t *, uint32_t) {}
-static inline void mbar_wait(uint64_t *, uint32_t) { std::abort(); }                       // clusters of one CTA never exchange
-static inline void st_async_b64(void *, unsigned, unsigned long long, uint64_t *) { std::abort(); }
+static inline uint32_t smem_u32(const void *p) { return (uint32_t)((const char *)p - (const char *)emu::cta->dyn.data()); }   // only meaningful for the dynamic buffer
+// mbarrier with transaction count in one 64-bit word: [31:0] pending transaction bytes (signed: completions may come before the
+// expectation), [39:32] pending arrivals, [47:40] arrival count of a phase, [48] phase parity
+static inline uint64_t mb_pack(int32_t tx, unsigned pend, unsigned cnt, unsigned ph) { return (uint32_t)tx | ((uint64_t)pend << 32) | ((uint64_t)cnt << 40) | ((uint64_t)ph << 48); }
+static inline void mb_update(uint64_t *bar, int32_t dtx, int darrive)
+{
+    uint64_t o = __atomic_load_n(bar, __ATOMIC_SEQ_CST), n;
+    do {
+        int32_t tx = (int32_t)(uint32_t)o + dtx;
+        unsigned pend = (unsigned)((o >> 32) & 0xff) - (unsigned)darrive, cnt = (unsigned)((o >> 40) & 0xff), ph = (unsigned)((o >> 48) & 1);
+        if (pend == 0 && tx == 0) { ph ^= 1; pend = cnt; }
+        n = mb_pack(tx, pend, cnt, ph);
+    } while (!__atomic_compare_exchange_n(bar, &o, n, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+}
+static inline void mbar_init(uint64_t *bar, uint32_t count) { __atomic_store_n(bar, mb_pack(0, count, count, 0), __ATOMIC_SEQ_CST); }
+static inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { mb_update(bar, (int32_t)bytes, 1); }       // arrive.expect_tx
+static inline void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (((__atomic_load_n(bar, __ATOMIC_SEQ_CST) >> 48) & 1) == parity) sched_yield();
+}
+// st.async...mbarrier::complete_tx::bytes.b64: 8 bytes into CTA dst_rank, then 8 bytes of its barrier's transaction count
+static inline void st_async_b64(void *local_ptr, unsigned dst_rank, unsigned long long v, uint64_t *local_bar)
+{
+    __atomic_store_n((unsigned long long *)emu::map_rank((char *)local_ptr, dst_rank), v, __ATOMIC_SEQ_CST);
+    mb_update(emu::map_rank(local_bar, dst_rank), -8, 0);
+}
 static inline void st_release_sys(unsigned long long *, unsigned long long) { std::abort(); }   // multi-GPU split: not emulated
 static inline unsigned long long ld_acquire_sys(const unsigned long long *) { std::abort(); }
 static inline void __threadfence_system() {}
 template <int kThreads> static inline void lds3(uint32_t addr, float &x, float &y, float &z)
 {
-    const char *b = (const char *)emu::dyn_smem + addr;
+    const char *b = (const char *)emu::cta->dyn.data() + addr;
     std::memcpy(&x, b, 4); std::memcpy(&y, b + kThreads * 4, 4); std::memcpy(&z, b + kThreads * 8, 4);
 }
 template <int kThreads> static inline void sts3(uint32_t addr, float x, float y, float z)
 {
-    char *b = (char *)emu::dyn_smem + addr;
+    char *b = (char *)emu::cta->dyn.data() + addr;
     std::memcpy(b, &x, 4); std::memcpy(b + kThreads * 4, &y, 4); std::memcpy(b + kThreads * 8, &z, 4);
 }
 static inline float2 ffma2(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
@@ -123,29 +187,47 @@ static inline float pin(float x) { return x; }
 
 RUNNER = r'''
 namespace emu {
-template <class F> static void run_grid(int n_ctas, int threads, size_t dyn_bytes, F kernel)
+// Clusters run one after the other; the CTAs of a cluster run concurrently (one OS thread per CUDA thread).
+template <class F> static void run_grid(int n_clusters, int ctas_per_cluster, int threads, size_t dyn_bytes, F kernel)
 {
-    std::vector<float> smem(dyn_bytes / 4 + 64);
-    dyn_smem = smem.data();
     bdim = D3{(unsigned)threads, 1, 1};
-    gdim = D3{(unsigned)n_ctas, 1, 1};
-    for (int c = 0; c < n_ctas; ++c) {
-        bidx = D3{(unsigned)c, 0, 0};
-        pthread_barrier_init(&cta_bar, nullptr, threads);
-        for (int w = 0; w < threads / 32; ++w) pthread_barrier_init(&warp_bar[w], nullptr, 32);
+    gdim = D3{(unsigned)(n_clusters * ctas_per_cluster), 1, 1};
+    for (int c = 0; c < n_clusters; ++c) {
+        Cluster cl;
+        cl.n_ctas = ctas_per_cluster; cl.used = 0;
+        std::memset(cl.slot_set, 0, sizeof(cl.slot_set));
+        pthread_mutex_init(&cl.mu, nullptr);
+        pthread_barrier_init(&cl.bar, nullptr, threads * ctas_per_cluster);
+        std::vector<Cta *> ctas;
+        for (int r = 0; r < ctas_per_cluster; ++r) {
+            Cta *b = new Cta();
+            b->rank = r; b->cluster = &cl; b->bidx = D3{(unsigned)(c * ctas_per_cluster + r), 0, 0};
+            std::memset(b->arena, 0, sizeof(b->arena));
+            b->dyn.assign(dyn_bytes / 4 + 64, 0.f);
+            pthread_barrier_init(&b->bar, nullptr, threads);
+            for (int w = 0; w < threads / 32; ++w) pthread_barrier_init(&b->warp_bar[w], nullptr, 32);
+            ctas.push_back(b);
+        }
+        cl.cta = ctas;
         std::vector<std::thread> th;
-        for (int t = 0; t < threads; ++t)
-            th.emplace_back([=]() { tidx = D3{(unsigned)t, 0, 0}; kernel(); });
+        for (int r = 0; r < ctas_per_cluster; ++r)
+            for (int t = 0; t < threads; ++t)
+                th.emplace_back([=]() { cta = ctas[r]; tidx = D3{(unsigned)t, 0, 0}; kernel(); });
         for (auto &x : th) x.join();
-        pthread_barrier_destroy(&cta_bar);
-        for (int w = 0; w < threads / 32; ++w) pthread_barrier_destroy(&warp_bar[w]);
+        for (Cta *b : ctas) {
+            pthread_barrier_destroy(&b->bar);
+            for (int w = 0; w < threads / 32; ++w) pthread_barrier_destroy(&b->warp_bar[w]);
+            delete b;
+        }
+        pthread_barrier_destroy(&cl.bar);
+        pthread_mutex_destroy(&cl.mu);
     }
 }
 }
 
 // One frame pair through a tracking kernel.  variant: 0 = k_track<128,4> (library), 1 = k_track_lean<128,4,0,false>,
 // 2 = k_track_lean<128,4,0,true> (packed accumulation); the lean variants exist only when the experiment source was given.
-extern "C" int emu_track_pairs(int variant, int n_pairs, int n_ctas, int n_levels, const float *const *pts, const int *n_pts,
+extern "C" int emu_track_pairs(int variant, int n_pairs, int n_clusters, int ctas_per_pair, int n_levels, const float *const *pts, const int *n_pts,
                                const float *const *dt, const int *w, const int *h, const float *cam4, const float *R9s, const float *t3s,
                                const revo_tracker_config *cfg, int mode, int level, int pcap, revo_track_result *results, double *records)
 {
@@ -183,13 +265,13 @@ extern "C" int emu_track_pairs(int variant, int n_pairs, int n_ctas, int n_level
     const PairDesc *d_pairs = pairs.data();
     int *wc = work_counter;
     if (variant == 0) {
-        emu::run_grid(n_ctas, T, dyn, [=]() { k_track<T, 4>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
+        emu::run_grid(n_clusters, ctas_per_pair, T, dyn, [=]() { k_track<T, 4>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
     }
 #ifdef EMU_WITH_LEAN
     else if (variant == 1) {
-        emu::run_grid(n_ctas, T, dyn, [=]() { k_track_lean<T, 4, 0, false>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
+        emu::run_grid(n_clusters, ctas_per_pair, T, dyn, [=]() { k_track_lean<T, 4, 0, false>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
     } else if (variant == 2) {
-        emu::run_grid(n_ctas, T, dyn, [=]() { k_track_lean<T, 4, 0, true>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
+        emu::run_grid(n_clusters, ctas_per_pair, T, dyn, [=]() { k_track_lean<T, 4, 0, true>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
     }
 #endif
     else return 1;
@@ -224,9 +306,22 @@ def _kernel(text, name):
     assert m, name
     j = text.index("\n}\n", m.start())
     k = text[m.start():j + 3]
-    k = k.replace("extern __shared__ float s_pts[];", "float *s_pts = emu::dyn_smem;")
+    k = k.replace("extern __shared__ float s_pts[];", "float *s_pts = emu::cta->dyn.data();")
     k = re.sub(r'\n[^\n]*asm volatile\("fence\.mbarrier_init[^\n]*\n', "\n", k)
     assert "asm" not in k, "unexpected inline PTX left in " + name
+    # `__shared__ [__align__(n)] T name[dims];`  ->  a reference into the CTA's arena (same offset in every CTA of the cluster)
+    slot = [0]
+
+    def repl(mm):
+        align, typ, var, dims = mm.group(2) or "8", mm.group(3), mm.group(4), mm.group(5) or ""
+        i = slot[0]
+        slot[0] += 1
+        if dims:
+            return (f"{mm.group(1)}{typ} (&{var}){dims} = *reinterpret_cast<{typ} (*){dims}>(emu::smem_slot({i}, sizeof({typ}{dims}), {align}));")
+        return f"{mm.group(1)}{typ} &{var} = *reinterpret_cast<{typ} *>(emu::smem_slot({i}, sizeof({typ}), {align}));"
+
+    k = re.sub(r"^(\s*)__shared__ (?:__align__\((\d+)\) )?([A-Za-z_][A-Za-z0-9_]*) ([A-Za-z_][A-Za-z0-9_]*)((?:\[[^\]]+\])*);", repl, k, flags=re.M)
+    assert "__shared__" not in k, "unhandled __shared__ declaration in " + name
     return k
 
 

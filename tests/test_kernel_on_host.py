@@ -18,7 +18,7 @@ def emu(tmp_path_factory):
     return _cuda_emu.build(str(tmp_path_factory.mktemp("cuda_emu")))
 
 
-def run_kernel(lib, variant, pairs, cfg, mode=0, level=0, n_ctas=1, pcap=18):
+def run_kernel(lib, variant, pairs, cfg, mode=0, level=0, n_ctas=1, pcap=18, ctas_per_pair=1):
     """pairs: list of (kf oracle pyramid, cur oracle pyramid, R (3,3), T (3,)).  Returns the revo_track_result records."""
     from revo_b200 import api
 
@@ -40,7 +40,7 @@ def run_kernel(lib, variant, pairs, cfg, mode=0, level=0, n_ctas=1, pcap=18):
     out = np.zeros(n, api.TRACK_RESULT_DTYPE)
     rec = np.zeros((n, 32), np.float64)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
-    rc = lib.emu_track_pairs(C.c_int(variant), C.c_int(n), C.c_int(n_ctas), C.c_int(NL), pts_a, vp(npts_a), dts_a, vp(ws_a), vp(hs_a),
+    rc = lib.emu_track_pairs(C.c_int(variant), C.c_int(n), C.c_int(n_ctas), C.c_int(ctas_per_pair), C.c_int(NL), pts_a, vp(npts_a), dts_a, vp(ws_a), vp(hs_a),
                              vp(cams_a), vp(R9), vp(t3), C.byref(cfg), C.c_int(mode), C.c_int(level), C.c_int(pcap), vp(out), vp(rec))
     assert rc == 0
     return out, rec
@@ -137,3 +137,23 @@ def test_k_track_on_host_single_evaluation_and_init_check(emu, orc64):
     # not a rotation: the pair is refused with the error code that replaces Sophus' abort()
     out, _ = run_kernel(emu, 0, [(kf, cur, 1.01 * np.eye(3, dtype=np.float32), T)], tracker_cfg(3))
     assert out["rc"][0] == 5
+
+
+@pytest.mark.parametrize("ctas_per_pair", [2, 4])
+def test_k_track_on_host_multi_cta_cluster_exchange(emu, orc64, ctas_per_pair):
+    """Clusters of several CTAs: the block-cyclic split of the point list over the CTAs and the one-sided exchange of the
+    per-CTA partials (st.async into every peer's shared memory + transaction barrier, emulated) must give the oracle's result;
+    two pairs on one cluster exercise the hand-over of the next pair through distributed shared memory."""
+    from revo_b200 import synth
+
+    T0 = synth.se3_exp([0.002, -0.001, 0.0015, 0.001, -0.0005, 0.0007])
+    R0, t0 = np.asarray(T0[:3, :3], np.float32), np.asarray(T0[:3, 3], np.float32)
+    pairs = [build_pair(orc64, seed) + (R0, t0) for seed in (1, 22)]
+    n_tries = 4
+    out, _ = run_kernel(emu, 0, pairs, tracker_cfg(n_tries), n_ctas=1, pcap=4, ctas_per_pair=ctas_per_pair)
+    for i, (kf, cur, _, _) in enumerate(pairs):
+        Ro, To, evals, last = oracle_chain(orc64, kf, cur, R0, t0, n_tries)
+        R = out["R"][i].reshape(3, 3).T
+        assert out["rc"][i] == 0 and list(out["n_evals"][i][:3]) == evals
+        assert rot_angle(R, Ro) <= 1e-4 and np.linalg.norm(out["t"][i] - To) <= 1e-4
+        assert out["good"][i] == last["good"] and out["bad"][i] == last["bad"]
