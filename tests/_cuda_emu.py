@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PRELUDE = r'''
 #include <pthread.h>
 #include <sched.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -46,6 +47,8 @@ struct Cta {                        // one thread block: its barriers, shuffle s
     D3 bidx;
     pthread_barrier_t bar, warp_bar[kMaxWarps];
     float shfl_slot[kMaxWarps][32];
+    alignas(8) unsigned long long coll_slot[kMaxWarps][32];
+    int or_flag;
     alignas(64) char arena[kArenaBytes];      // the __shared__ variables of the kernel, same offsets in every CTA
     std::vector<float> dyn;                   // dynamic shared memory
 };
@@ -107,6 +110,75 @@ static inline float __shfl_xor_sync(unsigned, float v, int m)
     pthread_barrier_wait(&emu::cta->warp_bar[w]);
     return r;
 }
+namespace emu {
+static inline int lin_tid() { return (int)(tidx.x + bdim.x * (tidx.y + bdim.y * tidx.z)); }
+// all lanes of the warp publish a value, then read what they need: the building block of every warp collective
+template <class T, class F> static inline auto warp_collective(T v, F pick) -> decltype(pick((const T *)nullptr))
+{
+    static_assert(sizeof(T) <= 8, "slot size");
+    const int w = lin_tid() >> 5, lane = lin_tid() & 31;
+    T *slots = (T *)cta->coll_slot[w];
+    slots[lane] = v;
+    pthread_barrier_wait(&cta->warp_bar[w]);
+    T copy[32];
+    for (int i = 0; i < 32; ++i) copy[i] = slots[i];
+    auto r = pick((const T *)copy);
+    pthread_barrier_wait(&cta->warp_bar[w]);
+    return r;
+}
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu::warp_collective(v, [=](const T *s) { return s[src & 31]; }); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d)
+{
+    const int lane = emu::lin_tid() & 31;
+    return emu::warp_collective(v, [=](const T *s) { return lane >= (int)d ? s[lane - d] : s[lane]; });
+}
+template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d)
+{
+    const int lane = emu::lin_tid() & 31;
+    return emu::warp_collective(v, [=](const T *s) { return lane + (int)d < 32 ? s[lane + d] : s[lane]; });
+}
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int m)
+{
+    const int lane = emu::lin_tid() & 31;
+    return emu::warp_collective(v, [=](const unsigned *s) { return s[lane ^ m]; });
+}
+static inline unsigned __ballot_sync(unsigned, bool p)
+{
+    return emu::warp_collective((unsigned)p, [](const unsigned *s) { unsigned b = 0; for (int i = 0; i < 32; ++i) b |= (s[i] ? 1u : 0u) << i; return b; });
+}
+static inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
+static inline int __reduce_add_sync(unsigned, int v)
+{
+    return emu::warp_collective(v, [](const int *s) { int t = 0; for (int i = 0; i < 32; ++i) t += s[i]; return t; });
+}
+static inline int __syncthreads_or(int p)
+{
+    if (p) __atomic_store_n(&emu::cta->or_flag, 1, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&emu::cta->bar);
+    const int r = __atomic_load_n(&emu::cta->or_flag, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&emu::cta->bar);
+    if (emu::lin_tid() == 0) __atomic_store_n(&emu::cta->or_flag, 0, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&emu::cta->bar);
+    return r;
+}
+static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
+static inline unsigned long long __brevll(unsigned long long v) { unsigned long long r = 0; for (int i = 0; i < 64; ++i) r |= ((v >> i) & 1ull) << (63 - i); return r; }
+static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
+{
+    const unsigned long long ab = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((ab >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T __ldcg(const T *p) { return *p; }
+using std::max;
+using std::min;
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __sync_fetch_and_add(p, v); }
@@ -186,6 +258,7 @@ static inline float pin(float x) { return x; }
 '''
 
 RUNNER = r'''
+// @GENERIC_BEGIN
 namespace emu {
 // Clusters run one after the other; the CTAs of a cluster run concurrently (one OS thread per CUDA thread).
 template <class F> static void run_grid(int n_clusters, int ctas_per_cluster, int threads, size_t dyn_bytes, F kernel)
@@ -225,6 +298,48 @@ template <class F> static void run_grid(int n_clusters, int ctas_per_cluster, in
 }
 }
 
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+namespace emu {
+// kernel<<<grid, block, smem>>>: thread blocks one after the other, one OS thread per CUDA thread (no clusters)
+template <class F> static void launch(dim3 grid, dim3 block, size_t dyn_bytes, F kernel)
+{
+    const int threads = (int)(block.x * block.y * block.z), n_warps = (threads + 31) / 32;
+    bdim = D3{block.x, block.y, block.z};
+    gdim = D3{grid.x, grid.y, grid.z};
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                Cluster cl;
+                cl.n_ctas = 1; cl.used = 0;
+                std::memset(cl.slot_set, 0, sizeof(cl.slot_set));
+                pthread_mutex_init(&cl.mu, nullptr);
+                pthread_barrier_init(&cl.bar, nullptr, threads);
+                Cta *b = new Cta();
+                b->rank = 0; b->cluster = &cl; b->bidx = D3{bx, by, bz};
+                std::memset(b->arena, 0, sizeof(b->arena));
+                b->dyn.assign(dyn_bytes / 4 + 64, 0.f);
+                pthread_barrier_init(&b->bar, nullptr, threads);
+                for (int w = 0; w < n_warps; ++w) pthread_barrier_init(&b->warp_bar[w], nullptr, std::min(32, threads - 32 * w));
+                cl.cta.assign(1, b);
+                std::vector<std::thread> th;
+                for (unsigned tz = 0; tz < block.z; ++tz)
+                    for (unsigned ty = 0; ty < block.y; ++ty)
+                        for (unsigned tx = 0; tx < block.x; ++tx)
+                            th.emplace_back([=]() { cta = b; tidx = D3{tx, ty, tz}; kernel(); });
+                for (auto &x : th) x.join();
+                pthread_barrier_destroy(&b->bar);
+                for (int w = 0; w < n_warps; ++w) pthread_barrier_destroy(&b->warp_bar[w]);
+                delete b;
+                pthread_barrier_destroy(&cl.bar);
+                pthread_mutex_destroy(&cl.mu);
+            }
+}
+}
+
+// @GENERIC_END
 // One frame pair through a tracking kernel.  variant: 0 = k_track<128,4> (library), 1 = k_track_lean<128,4,0,false>,
 // 2 = k_track_lean<128,4,0,true> (packed accumulation); the lean variants exist only when the experiment source was given.
 extern "C" int emu_track_pairs(int variant, int n_pairs, int n_clusters, int ctas_per_pair, int n_levels, const float *const *pts, const int *n_pts,
@@ -348,4 +463,109 @@ def build(out_dir, with_lean=False):
     open(src, "w").write(PRELUDE + "\n".join(parts) + RUNNER)
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-pthread", *flags,
                     "-I", os.path.join(ROOT, "include"), src, "-o", lib], check=True)
+    return C.CDLL(lib)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Canny (bit-mask pipeline of canny.cu: NMS -> hysteresis -> expand -> histogram) on the same layer
+# ---------------------------------------------------------------------------------------------------------------------
+CANNY_SHIMS = r'''
+namespace revo {
+static inline int dp4a_us(unsigned a, int b, int c)      // dp4a.u32.s32: unsigned bytes of a x signed bytes of b
+{
+    for (int i = 0; i < 4; ++i) c += (int)((a >> (8 * i)) & 0xffu) * (int)(int8_t)((b >> (8 * i)) & 0xff);
+    return c;
+}
+}
+struct revo_ctx { int stream; uint64_t launches; };
+#define REVO_CUDA(ctx, expr) do { (void)(expr); } while (0)
+#define LAUNCH_CHECK(ctx) do { (ctx)->launches++; } while (0)
+#define REVO_OK 0
+static inline int cudaMemset2DAsync(void *p, size_t pitch, int v, size_t width, size_t height, int)
+{
+    for (size_t r = 0; r < height; ++r) std::memset((char *)p + r * pitch, v, width);
+    return 0;
+}
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class K> static inline int cudaFuncSetAttribute(K, int, int) { return 0; }
+'''
+
+CANNY_DRIVER = r'''
+// cv::Canny(gray, edges, t1, t2, 3, true) + the patch histogram of generateDistHistogram through the bit-mask kernels
+extern "C" int emu_canny_bits(const uint8_t *gray, int w, int h, int low_sq, int high_sq, int patch, uint8_t *edges, uint8_t *edges_orig,
+                              uint8_t *hist, int *nz_patches)
+{
+    using namespace revo;
+    std::vector<int> labels((size_t)w * h + 64, 0);
+    std::vector<uint8_t> flags((size_t)w * h + 256, 0);
+    ImgLevel L;
+    std::memset(&L, 0, sizeof(L));
+    L.gray = (uint8_t *)gray; L.edges = edges; L.edges_orig = edges_orig; L.hist = hist; L.nz_patches = nz_patches;
+    L.labels = labels.data(); L.flags = flags.data(); L.w = w; L.h = h; L.patch = patch; L.hist_w = w / patch; L.hist_h = h / patch;
+    revo_ctx ctx{0, 0};
+    return launch_canny_bits(&ctx, &L, 1, w, h, low_sq, high_sq, patch, flags.data(), flags.size());
+}
+'''
+
+
+def _split_top(text):
+    out, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    out.append(cur.strip())
+    return out
+
+
+def _launches(text):
+    """kernel<<<grid, block[, smem[, stream]]>>>(args);  ->  emu::launch(grid, block, smem, [=]() { kernel(args); });"""
+    def repl(m):
+        cfg = _split_top(m.group(2))
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        return f"emu::launch({cfg[0]}, {cfg[1]}, {smem}, [=]() {{ {m.group(1)}({m.group(3)}); }});"
+    return re.sub(r"([A-Za-z_][A-Za-z0-9_]*(?:<[^<>;]*>)?)<<<(.*?)>>>\((.*?)\);", repl, text, flags=re.S)
+
+
+def _device_text(text):
+    """__shared__ declarations -> arena slots, dynamic shared memory -> the CTA's dynamic buffer."""
+    text = re.sub(r"extern __shared__ ([A-Za-z_ ]+?) ([A-Za-z_][A-Za-z0-9_]*)\[\];", r"\1 *\2 = (\1 *)emu::cta->dyn.data();", text)
+    slot = [16]                                    # the tracking kernels use the first slots
+
+    def repl(mm):
+        align, typ, var, dims = mm.group(2) or "8", mm.group(3), mm.group(4), mm.group(5) or ""
+        i = slot[0]
+        slot[0] += 1
+        if dims:
+            return f"{mm.group(1)}{typ} (&{var}){dims} = *reinterpret_cast<{typ} (*){dims}>(emu::smem_slot({i}, sizeof({typ}{dims}), {align}));"
+        return f"{mm.group(1)}{typ} &{var} = *reinterpret_cast<{typ} *>(emu::smem_slot({i}, sizeof({typ}), {align}));"
+
+    text = re.sub(r"^(\s*)__shared__ (?:__align__\((\d+)\) )?([A-Za-z_][A-Za-z0-9_]*) ([A-Za-z_][A-Za-z0-9_]*)((?:\[[^\]]+\])*);", repl, text, flags=re.M)
+    assert "__shared__" not in text
+    return text
+
+
+def build_canny(out_dir):
+    rd = lambda *p: open(os.path.join(ROOT, *p)).read()      # noqa: E731
+    canny, internal = rd("revo_b200", "csrc", "canny.cu"), rd("revo_b200", "csrc", "internal.h")
+    a = canny.index("// counts -> wrapping u8 histogram")
+    b = canny.index("\n}\n", canny.index("static int launch_canny_bits")) + 3
+    body = canny[a:b]
+    body = _strip_functions(body, ["dp4a_us"])
+    body = body.replace("#pragma unroll", "")
+    body = _launches(_device_text(body))
+    assert "asm" not in body and "<<<" not in body
+    generic = RUNNER[RUNNER.index("// @GENERIC_BEGIN"):RUNNER.index("// @GENERIC_END")]
+    src_text = (PRELUDE + CANNY_SHIMS + generic + "namespace revo {\nstatic inline int cdiv(int a, int b) { return (a + b - 1) / b; }\n"
+                + _struct(internal, "ImgLevel") + "\n" + body + "}  // namespace revo\n" + CANNY_DRIVER)
+    src, lib = os.path.join(out_dir, "canny_emu.cpp"), os.path.join(out_dir, "libcanny_emu.so")
+    open(src, "w").write(src_text)
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", lib],
+                   check=True)
     return C.CDLL(lib)
