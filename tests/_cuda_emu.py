@@ -167,6 +167,12 @@ static inline unsigned long long __brevll(unsigned long long v) { unsigned long 
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c)
+{
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+    return c;
+}
+using std::isfinite;
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
 {
     const unsigned long long ab = ((unsigned long long)b << 32) | a;
@@ -188,6 +194,8 @@ static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f
 static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __float2int_rn(float a) { return (int)lrintf(a); }
 static inline double __drcp_rn(double x) { return 1.0 / x; }
 static inline float __fdividef(float a, float b) { return a / b; }
@@ -339,6 +347,35 @@ template <class F> static void launch(dim3 grid, dim3 block, size_t dyn_bytes, F
 }
 }
 
+namespace emu {
+// kernels without barriers or warp collectives: the threads of a block simply run one after the other
+template <class F> static void launch_seq(dim3 grid, dim3 block, size_t dyn_bytes, F kernel)
+{
+    bdim = D3{block.x, block.y, block.z};
+    gdim = D3{grid.x, grid.y, grid.z};
+    Cluster cl;
+    cl.n_ctas = 1;
+    pthread_mutex_init(&cl.mu, nullptr);
+    Cta *b = new Cta();
+    b->rank = 0; b->cluster = &cl;
+    cl.cta.assign(1, b);
+    cta = b;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                cl.used = 0;
+                std::memset(cl.slot_set, 0, sizeof(cl.slot_set));
+                b->bidx = D3{bx, by, bz};
+                b->dyn.assign(dyn_bytes / 4 + 64, 0.f);
+                for (unsigned tz = 0; tz < block.z; ++tz)
+                    for (unsigned ty = 0; ty < block.y; ++ty)
+                        for (unsigned tx = 0; tx < block.x; ++tx) { tidx = D3{tx, ty, tz}; kernel(); }
+            }
+    cta = nullptr;
+    delete b;
+    pthread_mutex_destroy(&cl.mu);
+}
+}
 // @GENERIC_END
 // One frame pair through a tracking kernel.  variant: 0 = k_track<128,4> (library), 1 = k_track_lean<128,4,0,false>,
 // 2 = k_track_lean<128,4,0,true> (packed accumulation); the lean variants exist only when the experiment source was given.
@@ -486,6 +523,7 @@ static inline int cudaMemset2DAsync(void *p, size_t pitch, int v, size_t width, 
     for (size_t r = 0; r < height; ++r) std::memset((char *)p + r * pitch, v, width);
     return 0;
 }
+static inline int cudaMemsetAsync(void *p, int v, size_t bytes, int) { std::memset(p, v, bytes); return 0; }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class K> static inline int cudaFuncSetAttribute(K, int, int) { return 0; }
 '''
@@ -524,12 +562,28 @@ def _split_top(text):
     return out
 
 
+_COLLECTIVES = ("__syncthreads", "__shfl", "__ballot", "__any_sync", "__reduce", "__syncwarp", "flood_row", "spread_row", "flood_up_row")
+
+
+def _kernel_bodies(text):
+    """name -> body text of every __global__ function of `text`."""
+    out = {}
+    for m in re.finditer(r"^__global__ void (?:__launch_bounds__\([^)]*\)\s*)?([A-Za-z_][A-Za-z0-9_]*)\(", text, re.M):
+        out[m.group(1)] = text[m.start():text.index("\n}\n", m.start()) + 3]
+    return out
+
+
 def _launches(text):
-    """kernel<<<grid, block[, smem[, stream]]>>>(args);  ->  emu::launch(grid, block, smem, [=]() { kernel(args); });"""
+    """kernel<<<grid, block[, smem[, stream]]>>>(args);  ->  emu::launch(grid, block, smem, [=]() { kernel(args); });
+    kernels whose body has no barrier / warp collective run their threads sequentially (emu::launch_seq)."""
+    bodies = _kernel_bodies(text)
+
     def repl(m):
         cfg = _split_top(m.group(2))
         smem = cfg[2] if len(cfg) > 2 else "0"
-        return f"emu::launch({cfg[0]}, {cfg[1]}, {smem}, [=]() {{ {m.group(1)}({m.group(3)}); }});"
+        base = re.sub(r"<.*", "", m.group(1))
+        seq = base in bodies and not any(c in bodies[base] for c in _COLLECTIVES)
+        return f"emu::{'launch_seq' if seq else 'launch'}({cfg[0]}, {cfg[1]}, {smem}, [=]() {{ {m.group(1)}({m.group(3)}); }});"
     return re.sub(r"([A-Za-z_][A-Za-z0-9_]*(?:<[^<>;]*>)?)<<<(.*?)>>>\((.*?)\);", repl, text, flags=re.S)
 
 
@@ -565,6 +619,104 @@ def build_canny(out_dir):
     src_text = (PRELUDE + CANNY_SHIMS + generic + "namespace revo {\nstatic inline int cdiv(int a, int b) { return (a + b - 1) / b; }\n"
                 + _struct(internal, "ImgLevel") + "\n" + body + "}  // namespace revo\n" + CANNY_DRIVER)
     src, lib = os.path.join(out_dir, "canny_emu.cpp"), os.path.join(out_dir, "libcanny_emu.so")
+    open(src, "w").write(src_text)
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", lib],
+                   check=True)
+    return C.CDLL(lib)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The whole pyramid construction (pyramid.cu + the bit-mask Canny) with the launch sequence of capi.cu:create_batch_impl
+# ---------------------------------------------------------------------------------------------------------------------
+PYRAMID_DRIVER = r'''
+struct EmuLevelOut {          // caller-provided host buffers of one level
+    uint8_t *gray; float *depth; uint8_t *edges, *edges_orig, *hist; float *pts; int *n_pts, *nz_patches;
+    float *dt; uint32_t *opt; float *pts_ref; int *n_ref; float *opt_f4;
+    int w, h, patch, cap, n_tiles;
+    float fx, fy, cx, cy;
+};
+
+// n identical frames (n >= 8 takes the group compaction of launch_compact, n < 8 the tile one); outputs of frame 0
+extern "C" int emu_pyramid(const uint8_t *bgr, int channels, const float *depth, int n_frames, int n_levels, EmuLevelOut *out, int low_sq,
+                           int high_sq, float dmin, float dmax, int use_edge_hist, float n_percentage, int keyframe)
+{
+    using namespace revo;
+    revo_ctx ctx{0, 0};
+    const int w0 = out[0].w, h0 = out[0].h, n = n_frames;
+    std::vector<std::vector<ImgLevel>> desc(n_levels, std::vector<ImgLevel>(n));
+    std::vector<std::vector<uint8_t>> store;
+    auto alloc = [&](size_t bytes) { store.emplace_back(bytes + 256, 0); return store.back().data(); };
+    std::vector<uint8_t *> labels(n), flags(n);
+    for (int f = 0; f < n; ++f) { labels[f] = alloc((size_t)w0 * h0 * 4); flags[f] = alloc((size_t)w0 * h0); }
+    for (int l = 0; l < n_levels; ++l)
+        for (int f = 0; f < n; ++f) {
+            const EmuLevelOut &o = out[l];
+            ImgLevel &L = desc[l][f];
+            std::memset(&L, 0, sizeof(L));
+            const size_t px = (size_t)o.w * o.h;
+            const bool first = f == 0;
+            L.gray = first ? o.gray : alloc(px); L.depth = first ? o.depth : (float *)alloc(px * 4);
+            L.edges = first ? o.edges : alloc(px); L.edges_orig = first ? o.edges_orig : alloc(px);
+            L.hist = first ? o.hist : alloc(px); L.pts = (float4 *)(first ? (uint8_t *)o.pts : alloc((size_t)o.cap * 16));
+            L.n_pts = first ? o.n_pts : (int *)alloc(8); L.nz_patches = first ? o.nz_patches : (int *)alloc(8);
+            L.tile_off = (int *)alloc(((size_t)o.n_tiles + 1) * 4);
+            L.labels = (int *)labels[f]; L.flags = flags[f];
+            L.dt = first ? o.dt : (float *)alloc(px * 4); L.opt = (uint4 *)(first ? (uint8_t *)o.opt : alloc(px * 32));
+            L.w = o.w; L.h = o.h; L.pts_cap = o.cap; L.patch = o.patch; L.hist_w = o.w / o.patch; L.hist_h = o.h / o.patch;
+            L.fx = o.fx; L.fy = o.fy; L.cx = o.cx; L.cy = o.cy;
+        }
+    // n copies of the input frame, tightly packed (what revo_pyr_create_batch takes)
+    const size_t bgr_frame = (size_t)w0 * h0 * channels;
+    std::vector<uint8_t> bgr_n(bgr_frame * n);
+    for (int f = 0; f < n; ++f) {
+        std::memcpy(bgr_n.data() + bgr_frame * f, bgr, bgr_frame);
+        std::memcpy(desc[0][f].depth, depth, (size_t)w0 * h0 * 4);
+    }
+    // the launch sequence of create_batch_impl (capi.cu)
+    int rc = launch_gray(&ctx, bgr_n.data(), (size_t)w0 * channels, channels, bgr_frame, desc[0].data(), n, w0, h0);
+    for (int l = 0; l < n_levels && !rc; ++l) {
+        const EmuLevelOut &o = out[l];
+        if (l > 0) rc = launch_pyrdown_depth(&ctx, desc[l - 1].data(), desc[l].data(), n, o.w, o.h, out[l - 1].w, out[l - 1].h);
+        if (!rc) rc = launch_canny_bits(&ctx, desc[l].data(), n, o.w, o.h, low_sq, high_sq, o.patch, flags[0], 0);
+        const bool fill = use_edge_hist && l >= 1 && l <= 2;
+        if (!rc) rc = launch_hist_fill(&ctx, desc[l].data(), l > 0 ? desc[l - 1].data() : nullptr, n, o.w, o.h, o.patch,
+                                      l > 0 ? out[l - 1].patch : o.patch, fill, n_percentage);
+        if (!rc) rc = launch_compact(&ctx, desc[l].data(), n, o.w, o.h, dmin, dmax);
+    }
+    for (int l = 0; l < n_levels && !rc; ++l) {
+        const EmuLevelOut &o = out[l];
+        std::vector<int> col_off(o.w + 2);
+        rc = launch_edges3d_reference_order(&ctx, desc[l].data(), o.w, o.h, dmin, dmax, (float4 *)o.pts_ref, o.n_ref, col_off.data());
+        if (!rc && keyframe) rc = launch_keyframe(&ctx, desc[l].data(), n, o.w, o.h);
+        if (!rc && keyframe) rc = launch_opt_struct_f4(&ctx, o.dt, o.w, o.h, (float4 *)o.opt_f4);
+    }
+    return rc;
+}
+'''
+
+
+def build_pyramid(out_dir):
+    rd = lambda *p: open(os.path.join(ROOT, *p)).read()      # noqa: E731
+    canny, pyr, internal = rd("revo_b200", "csrc", "canny.cu"), rd("revo_b200", "csrc", "pyramid.cu"), rd("revo_b200", "csrc", "internal.h")
+    a = canny.index("// counts -> wrapping u8 histogram")
+    b = canny.index("\n}\n", canny.index("static int launch_canny_bits")) + 3
+    cbody = _strip_functions(canny[a:b], ["dp4a_us"])
+    pa = pyr.index("// ---------------------------------------------------------------------------\n// K1: BGR(A) -> gray")
+    pb = pyr.index("}  // namespace revo")
+    pbody = pyr[pa:pb]
+    # the memset of the histogram counters in launch_canny_bits takes the per-frame pitch of the slab: here every frame has its
+    # own counter buffer, so clear them through the descriptors instead
+    cbody = cbody.replace("REVO_CUDA(ctx, cudaMemset2DAsync(d_counts0, counts_stride, 0, (size_t)hist_w * hist_h * sizeof(int), (size_t)n, ctx->stream));",
+                          "for (int f_ = 0; f_ < n; ++f_) std::memset(d_desc[f_].flags, 0, (size_t)hist_w * hist_h * sizeof(int));")
+    body = (cbody + pbody).replace("#pragma unroll", "")
+    body = _launches(_device_text(body))
+    assert "asm" not in body and "<<<" not in body
+    generic = RUNNER[RUNNER.index("// @GENERIC_BEGIN"):RUNNER.index("// @GENERIC_END")]
+    src_text = (PRELUDE + CANNY_SHIMS + generic + "namespace revo {\nstatic inline int cdiv(int a, int b) { return (a + b - 1) / b; }\n"
+                + "constexpr int kTileW = 8;\nconstexpr int kTileH = 4;\n"
+                + _struct(internal, "ImgLevel") + "\n" + _struct(internal, "QualityFrame") + "\n" + _struct(internal, "QualityArgs") + "\n"
+                + body + "}  // namespace revo\n" + PYRAMID_DRIVER)
+    src, lib = os.path.join(out_dir, "pyramid_emu.cpp"), os.path.join(out_dir, "libpyramid_emu.so")
     open(src, "w").write(src_text)
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", lib],
                    check=True)

@@ -1,0 +1,116 @@
+"""The whole pyramid construction on the CPU: every kernel of pyramid.cu and of the bit-mask Canny, with their launch code and
+the launch sequence of ``capi.cu:create_batch_impl`` / ``launch_keyframe``, compiled from the CUDA source text against the
+emulation layer of ``tests/_cuda_emu.py``, against the oracle pyramid (cv2 + the C restatement): gray, depth pyramid, Canny,
+patch histogram, edge fill-in, 3-D edge list (tile-major list as a set, reference-order list exactly), exact EDT and the
+lookup structure -- ``test_pyramid_bit_exact`` of the `-m gpu` suite without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import synth_pair
+
+
+class EmuLevelOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("gray", "depth", "edges", "edges_orig", "hist", "pts", "n_pts", "nz_patches", "dt", "opt",
+                                          "pts_ref", "n_ref", "opt_f4")] + \
+               [(n, C.c_int) for n in ("w", "h", "patch", "cap", "n_tiles")] + [(n, C.c_float) for n in ("fx", "fy", "cx", "cy")]
+
+
+@pytest.fixture(scope="module")
+def pyr_emu(tmp_path_factory):
+    import _cuda_emu
+
+    return _cuda_emu.build_pyramid(str(tmp_path_factory.mktemp("pyramid_emu")))
+
+
+def run_pyramid(lib, bgr, depth, cam, n_levels, n_frames=1, keyframe=True, n_percentage=0.3):
+    fx, fy, cx, cy, w0, h0 = cam
+    outs = (EmuLevelOut * n_levels)()
+    arrays = []
+    for l in range(n_levels):
+        w, h = w0 >> l, h0 >> l
+        patch = max(1, 20 >> l)
+        cap = w * h // 2 + 1024
+        a = dict(gray=np.zeros((h, w), np.uint8), depth=np.zeros((h, w), np.float32), edges=np.zeros((h, w), np.uint8),
+                 edges_orig=np.zeros((h, w), np.uint8), hist=np.zeros((max(1, h // patch), max(1, w // patch)), np.uint8),
+                 pts=np.zeros((cap, 4), np.float32), n_pts=np.zeros(2, np.int32), nz_patches=np.zeros(2, np.int32),
+                 dt=np.zeros((h, w), np.float32), opt=np.zeros((h, w, 8), np.uint32), pts_ref=np.zeros((w * h, 4), np.float32),
+                 n_ref=np.zeros(2, np.int32), opt_f4=np.zeros((h, w, 4), np.float32))
+        arrays.append(a)
+        o = outs[l]
+        for k, v in a.items():
+            setattr(o, k, v.ctypes.data)
+        o.w, o.h, o.patch, o.cap, o.n_tiles = w, h, patch, cap, ((w + 7) // 8) * ((h + 3) // 4)
+        s = 2.0 ** -l                                    # level_camera: camerapyr.h:98-103
+        o.fx, o.fy, o.cx, o.cy = fx * s, fy * s, cx * s, cy * s
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    depth = np.ascontiguousarray(depth, np.float32)
+    rc = lib.emu_pyramid(bgr.ctypes.data_as(C.c_void_p), C.c_int(bgr.shape[2]), depth.ctypes.data_as(C.c_void_p), C.c_int(n_frames),
+                         C.c_int(n_levels), outs, C.c_int(100 * 100), C.c_int(150 * 150), C.c_float(0.1), C.c_float(5.2), C.c_int(1),
+                         C.c_float(n_percentage), C.c_int(int(keyframe)))
+    assert rc == 0
+    return arrays
+
+
+def compare(arrays, po, n_levels, keyframe=True):
+    for l in range(n_levels):
+        a = arrays[l]
+        assert np.array_equal(a["gray"], po.gray[l]), l
+        assert np.array_equal(a["depth"].view(np.uint32), np.asarray(po.depth[l], np.float32).view(np.uint32)), l
+        assert np.array_equal(a["edges_orig"], po.edges_orig[l]), l
+        assert np.array_equal(a["edges"], po.edges[l]), l
+        if po.hist[l] is not None and l < 3:
+            hh, hw = np.asarray(po.hist[l]).shape
+            assert np.array_equal(a["hist"][:hh, :hw], po.hist[l]), l
+        want = np.asarray(po.edges3d[l], np.float32).reshape(-1, 4)
+        n = int(a["n_ref"][0])
+        assert n == len(want) == int(a["n_pts"][0]), (l, n, len(want), a["n_pts"][0])
+        assert np.array_equal(a["pts_ref"][:n].view(np.uint32), want.view(np.uint32)), l          # reference (column-major) order
+        got_set = {tuple(r) for r in a["pts"][:n].view(np.uint32).tolist()}                       # device (tile-major) order: same set
+        assert got_set == {tuple(r) for r in want.view(np.uint32).tolist()}, l
+        if keyframe:
+            assert np.array_equal(a["dt"].view(np.uint32), np.asarray(po.dt[l], np.float32).view(np.uint32)), l
+            ow = np.asarray(po.opt[l], np.float32)
+            assert np.array_equal(a["opt_f4"][1:-1, :, :3].view(np.uint32), ow[1:-1, :, :3].view(np.uint32)), l
+            # quad records: the structure's dt (0 in rows 0 and h-1, like the gradients) of the four texels as float32,
+            # gradients as snorm16 with step 1/32764
+            q = a["opt"]
+            z = a["opt_f4"][..., 2].view(np.uint32)
+            assert np.array_equal(q[:-1, :-1, 0], z[:-1, :-1]) and np.array_equal(q[:-1, :-1, 1], z[:-1, 1:])
+            assert np.array_equal(q[:-1, :-1, 2], z[1:, :-1]) and np.array_equal(q[:-1, :-1, 3], z[1:, 1:])
+            gx = (q[..., 4] & 0xffff).astype(np.uint16).view(np.int16).astype(np.float32) / 32764.0
+            gy = (q[..., 4] >> 16).astype(np.uint16).view(np.int16).astype(np.float32) / 32764.0
+            assert np.abs(gx[1:-1] - np.clip(ow[1:-1, :, 0], -1, 1)).max() <= 0.5 / 32764 + 1e-7
+            assert np.abs(gy[1:-1] - np.clip(ow[1:-1, :, 1], -1, 1)).max() <= 0.5 / 32764 + 1e-7
+
+
+def oracle_pyramid(orc, cam, n_levels, bgr, depth, n_percentage=0.3):
+    from oracle import oracle as O
+
+    cfg = O.PyrCfg(n_levels=n_levels)
+    cfg.n_percentage = n_percentage
+    p = O.build_pyramid(orc, cfg, cam, bgr, depth)
+    O.make_keyframe(orc, p)
+    return p
+
+
+@pytest.mark.parametrize("seed,w,h,n_levels", [(4, 320, 240, 3), (6, 160, 120, 4)])
+def test_pyramid_kernels_on_host_bit_exact(pyr_emu, orc32, seed, w, h, n_levels):
+    p = synth_pair(seed, w, h)
+    bgr, depth = p["key"]
+    depth = depth.copy()
+    depth[10:20, 30:60] = np.nan                               # holes for the hole-aware depth pyramid
+    depth[h // 2, :] = 0.0
+    po = oracle_pyramid(orc32, p["cam"], n_levels, bgr, depth)
+    compare(run_pyramid(pyr_emu, bgr, depth, p["cam"], n_levels), po, n_levels)
+
+
+def test_pyramid_kernels_on_host_fill_in_and_group_compaction(pyr_emu, orc32):
+    """A high nPercentage forces fillInEdges on levels 1 and 2 (imgpyramidrgbd.cpp:188-196); eight frames per call take the
+    group compaction of launch_compact (k_group_mask / k_group_scatter), the path of every batched build."""
+    p = synth_pair(11, 96, 72)
+    bgr, depth = p["key"]
+    po = oracle_pyramid(orc32, p["cam"], 3, bgr, depth, n_percentage=1.1)
+    assert any(not np.array_equal(po.edges[l], po.edges_orig[l]) for l in (1, 2))          # the fill-in changed something
+    compare(run_pyramid(pyr_emu, bgr, depth, p["cam"], 3, n_frames=8, n_percentage=1.1), po, 3)
