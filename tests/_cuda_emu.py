@@ -1,7 +1,10 @@
-"""Test infrastructure: runs the tracking KERNELS of this repo on the CPU.
+"""Test infrastructure: runs the KERNELS of this repo on the CPU.
 
-The kernel source text (track.cu: k_track; optionally scratch/experiments/track_lean.cu: k_track_lean) and the device helpers
-(track_common.cuh, the quad-record packing of pyramid.cu) are extracted from the CUDA files at test time and compiled with g++
+build(): the tracking kernels (track.cu: k_track; optionally scratch/experiments/track_lean.cu); build_canny(): the bit-mask Canny
+pipeline of canny.cu with its launch code; build_pyramid(): every kernel of pyramid.cu + the Canny pipeline with the launch
+sequence of capi.cu:create_batch_impl / launch_keyframe, and the tracking-quality vote.  The kernel source text and the device
+helpers are extracted from the CUDA files at test time (`kernel<<<grid, block, smem>>>(args)` becomes a call of the emulated
+launcher; kernels without barriers / warp collectives run their threads sequentially) and compiled with g++
 against a small emulation layer: one OS thread per CUDA thread, pthread barriers for __syncthreads / the warp shuffles /
 cluster.sync(), a per-CTA arena for the __shared__ variables (same offsets in every CTA, so that distributed shared memory is
 an offset into the peer's arena), mbarriers with transaction counts as 64-bit atomics, st.async as store + complete_tx, host
@@ -691,6 +694,24 @@ extern "C" int emu_pyramid(const uint8_t *bgr, int channels, const float *depth,
         if (!rc && keyframe) rc = launch_opt_struct_f4(&ctx, o.dt, o.w, o.h, (float4 *)o.opt_f4);
     }
     return rc;
+}
+
+// TrackerNew::assessTrackingQuality on the device (k_quality_scatter + k_quality_hist): the 16 counters of launch_quality
+extern "C" int emu_quality(int n_frames, const float *const *pts, const int *n_pts, const float *R9s, const float *T3s, float fx, float fy,
+                           float cx, float cy, int w, int h, const float *depth, const uint8_t *edges, float dmin, float dmax, int *counters16)
+{
+    using namespace revo;
+    revo_ctx ctx{0, 0};
+    QualityArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n_frames = n_frames; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.w = w; a.h = h;
+    for (int f = 0; f < n_frames; ++f) {
+        a.fr[f].pts = (const float4 *)pts[f]; a.fr[f].n_pts = &n_pts[f];
+        std::memcpy(a.fr[f].R, R9s + 9 * f, sizeof(float) * 9);
+        std::memcpy(a.fr[f].T, T3s + 3 * f, sizeof(float) * 3);
+    }
+    std::vector<unsigned> mbits(((size_t)w * h + 3) / 4 + 16);
+    return launch_quality(&ctx, a, depth, edges, dmin, dmax, mbits.data(), counters16);
 }
 '''
 

@@ -114,3 +114,38 @@ def test_pyramid_kernels_on_host_fill_in_and_group_compaction(pyr_emu, orc32):
     po = oracle_pyramid(orc32, p["cam"], 3, bgr, depth, n_percentage=1.1)
     assert any(not np.array_equal(po.edges[l], po.edges_orig[l]) for l in (1, 2))          # the fill-in changed something
     compare(run_pyramid(pyr_emu, bgr, depth, p["cam"], 3, n_frames=8, n_percentage=1.1), po, 3)
+
+
+def test_quality_vote_kernels_on_host(pyr_emu, orc32):
+    """k_quality_scatter / k_quality_hist (TrackerNew::assessTrackingQuality, tracker.cpp:118-201) on the emulation layer vs the
+    numpy restatement of the vote: exact histogram / overlap counts for three past frames."""
+    from oracle import oracle as O
+    from revo_b200 import synth
+
+    w, h, lvl = 320, 240, 2
+    s = synth.make_stream(31, 4, w, h, max_trans=0.02, max_rot_deg=1.0)
+    cam = synth.intrinsics(w, h)
+    cfg = O.PyrCfg(n_levels=3)
+    pyrs = [O.build_pyramid(orc32, cfg, cam, *s["frames"][i]) for i in range(4)]
+    T_w = [np.linalg.inv(s["T_w_c"][0]) @ s["T_w_c"][i] for i in range(4)]
+    cur, est = pyrs[3], T_w[3].astype(np.float32)
+    past_pts = [np.ascontiguousarray(pyrs[i].edges3d[lvl], np.float32) for i in range(3)]
+    past_poses = [T_w[i].astype(np.float32) for i in range(3)]
+    c = cur.cams[lvl]
+    want = O.assess_tracking_quality(past_pts, past_poses, est, (c.fx, c.fy, c.cx, c.cy, c.w, c.h), cur.depth[lvl], cur.edges_orig[lvl])
+    # inv(estimatedPose) * pastWorldPose in double, then float (revo_track_quality, capi.cu)
+    rel = [np.linalg.inv(est.astype(np.float64)) @ P.astype(np.float64) for P in past_poses]
+    R9 = np.ascontiguousarray(np.stack([r[:3, :3].T.reshape(-1) for r in rel]), np.float32)
+    T3 = np.ascontiguousarray(np.stack([r[:3, 3] for r in rel]), np.float32)
+    n_pts = np.ascontiguousarray([len(p) for p in past_pts], np.int32)
+    ptrs = (C.c_void_p * 3)(*[p.ctypes.data for p in past_pts])
+    depth = np.ascontiguousarray(cur.depth[lvl], np.float32)
+    edges = np.ascontiguousarray(cur.edges_orig[lvl], np.uint8)
+    counters = np.zeros(16, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
+    f = C.c_float
+    rc = pyr_emu.emu_quality(C.c_int(3), ptrs, vp(n_pts), vp(R9), vp(T3), f(c.fx), f(c.fy), f(c.cx), f(c.cy), C.c_int(c.w), C.c_int(c.h),
+                             vp(depth), vp(edges), f(0.1), f(5.2), vp(counters))
+    assert rc == 0
+    assert list(counters[:4]) == list(want["histogram"]) and list(counters[4:8]) == list(want["overlaps"]), (counters[:9], want)
+    assert sum(counters[:4]) > 1000 and counters[5:8].sum() > 0
