@@ -70,3 +70,17 @@ def test_canny_kernels_on_host_edge_cases(canny_emu):
     want = cv2.Canny(img, 150, 100, apertureSize=3, L2gradient=True)
     edges, _, _, _ = run_canny(canny_emu, img)
     assert want.any() and np.array_equal(edges, want)
+
+
+@pytest.mark.parametrize("w,h", [(1088, 48), (64, 1100)])
+def test_canny_kernels_on_host_wide_and_tall_images(canny_emu, w, h):
+    """Rows wider than 1024 pixels take the 64-bit-word instantiation of the hysteresis; images with more than 32 rows per warp
+    take the global-memory fallback ``k_canny_hyst`` (blind band sweeps).  Same result as cv2.Canny either way."""
+    import cv2
+
+    rng = np.random.default_rng(w + h)
+    g = cv2.GaussianBlur((rng.integers(0, 2, (h, w)) * 255).astype(np.uint8), (0, 0), 2.5)
+    gray = cv2.add(g, rng.integers(0, 25, (h, w)).astype(np.uint8))
+    want = cv2.Canny(gray, 150, 100, apertureSize=3, L2gradient=True)
+    edges, orig, _, _ = run_canny(canny_emu, gray)
+    assert want.any() and np.array_equal(edges, want) and np.array_equal(orig, want)
