@@ -15,9 +15,11 @@ schedule).  What this does NOT cover: the multi-GPU mailboxes, and of course tim
 import ctypes as C
 import os
 import re
+import shlex
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXTRA_FLAGS = shlex.split(os.environ.get("REVO_EMU_CXXFLAGS", ""))      # e.g. "-fsanitize=thread -g" (scratch/tools/emu_sanitize.py)
 
 PRELUDE = r'''
 #include <pthread.h>
@@ -501,7 +503,7 @@ def build(out_dir, with_lean=False):
     parts.append("}  // namespace revo")
     src, lib = os.path.join(out_dir, "cuda_emu.cpp"), os.path.join(out_dir, "libcuda_emu.so")
     open(src, "w").write(PRELUDE + "\n".join(parts) + RUNNER)
-    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-pthread", *flags,
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-pthread", *flags, *EXTRA_FLAGS,
                     "-I", os.path.join(ROOT, "include"), src, "-o", lib], check=True)
     return C.CDLL(lib)
 
@@ -623,7 +625,7 @@ def build_canny(out_dir):
                 + _struct(internal, "ImgLevel") + "\n" + body + "}  // namespace revo\n" + CANNY_DRIVER)
     src, lib = os.path.join(out_dir, "canny_emu.cpp"), os.path.join(out_dir, "libcanny_emu.so")
     open(src, "w").write(src_text)
-    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", lib],
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", *EXTRA_FLAGS, "-I", os.path.join(ROOT, "include"), src, "-o", lib],
                    check=True)
     return C.CDLL(lib)
 
@@ -739,6 +741,6 @@ def build_pyramid(out_dir):
                 + body + "}  // namespace revo\n" + PYRAMID_DRIVER)
     src, lib = os.path.join(out_dir, "pyramid_emu.cpp"), os.path.join(out_dir, "libpyramid_emu.so")
     open(src, "w").write(src_text)
-    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", lib],
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", *EXTRA_FLAGS, "-I", os.path.join(ROOT, "include"), src, "-o", lib],
                    check=True)
     return C.CDLL(lib)
