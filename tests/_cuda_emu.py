@@ -44,7 +44,7 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 
 namespace emu {
 struct D3 { unsigned x, y, z; };
-constexpr int kMaxWarps = 32, kArenaBytes = 64 * 1024, kMaxSlots = 32;
+constexpr int kMaxWarps = 32, kArenaBytes = 64 * 1024, kMaxSlots = 128;
 struct Cluster;
 struct Cta {                        // one thread block: its barriers, shuffle slots and "shared memory"
     int rank;
@@ -72,6 +72,7 @@ static D3 bdim, gdim;
 // storage of the k-th __shared__ declaration of the kernel (first caller of the cluster fixes the offset)
 static inline void *smem_slot(int k, size_t bytes, size_t align)
 {
+    if (k < 0 || k >= kMaxSlots) std::abort();
     Cluster *cl = cta->cluster;
     pthread_mutex_lock(&cl->mu);
     if (!cl->slot_set[k]) {

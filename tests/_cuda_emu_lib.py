@@ -116,6 +116,15 @@ int launch_track_queue(revo_ctx *ctx, const PairDesc *, int, const TrackParams &
     return REVO_ERR_UNSUPPORTED;
 }
 size_t track_queue_workspace_bytes(int, int, unsigned *) { return 256; }
+int launch_track_lean(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, revo_track_result *d_results,
+                      double *d_records, revo_trace_entry *d_trace, int *d_trace_counts, int *d_work_counter);   // scratch/experiments/track_lean.cu
+#ifndef EMU_WITH_LEAN
+int launch_track_lean(revo_ctx *ctx, const PairDesc *, int, const TrackParams &, revo_track_result *, double *, revo_trace_entry *, int *, int *)
+{
+    ctx->last_error = "lean engine: not in this build";
+    return REVO_ERR_UNSUPPORTED;
+}
+#endif
 bool make_gray_tensor_map(void *, const uint8_t *, int, int, int, size_t) { return false; }
 }
 '''
@@ -125,7 +134,9 @@ def _strip_includes(text):
     return re.sub(r'^#include [<"][^\n]*\n', "", text, flags=re.M).replace("#pragma once", "").replace("#pragma unroll", "")
 
 
-def build(out_dir):
+def build(out_dir, with_lean=False):
+    """with_lean: also compile scratch/experiments/track_lean.cu and dispatch tracking engine 4 to it (what
+    scratch/experiments/enable_lean_engine.patch does to the library)."""
     rd = lambda *p: open(os.path.join(ROOT, *p)).read()      # noqa: E731
     internal, common = rd("revo_b200", "csrc", "internal.h"), rd("revo_b200", "csrc", "track_common.cuh")
     pyr, canny, track, capi = (rd("revo_b200", "csrc", f) for f in ("pyramid.cu", "canny.cu", "track.cu", "capi.cu"))
@@ -145,7 +156,21 @@ def build(out_dir):
     track = re.sub(r'\n[^\n]*asm volatile\("fence\.mbarrier_init[^\n]*\n', "\n", track)
     track = track.replace("__threadfence_system();", "")
 
-    device = "\n".join(_strip_includes(t) for t in (common, pyr, cbody, track))
+    files = [common, pyr, cbody, track]
+    if with_lean:
+        lean = rd("scratch", "experiments", "track_lean.cu")
+        lean = re.sub(r"#define REVO_LDG_QUAD.*?#undef REVO_LDG_QUAD\n", "", lean, flags=re.S)
+        lean = E._strip_functions(lean, ["lds3", "sts3", "ffma2", "fmul2", "pin"])
+        lean = lean.replace("extern __shared__ float s_pts[];", "float *s_pts = emu::cta->dyn.data();")
+        lean = re.sub(r'\n[^\n]*asm volatile\("fence\.mbarrier_init[^\n]*\n', "\n", lean)
+        files.append(lean)
+        capi = capi.replace("engine < 0 || engine > 3 ||", "engine < 0 || engine > 4 ||")
+        capi = capi.replace("    if (engine != 2 && engine != 3) engine = 1;", "    if (engine != 2 && engine != 3 && engine != 4) engine = 1;")
+        capi = capi.replace("        else if (engine == 3) rc = launch_track_pp(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);\n",
+                            "        else if (engine == 3) rc = launch_track_pp(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);\n"
+                            "        else if (engine == 4) rc = launch_track_lean(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);\n")
+        assert "launch_track_lean" in capi
+    device = "\n".join(_strip_includes(t) for t in files)
     device = E._launches(E._device_text(device))
     assert "asm" not in device and "<<<" not in device, "unexpected PTX / launch syntax left"
     device = re.sub(r"(\.|->)(gridDim|blockDim)\b", r"\1\2_", device)      # members of cudaLaunchConfig_t, not the built-ins
@@ -158,5 +183,5 @@ def build(out_dir):
     src, lib = os.path.join(out_dir, "revo_b200_emu.cpp"), os.path.join(out_dir, "librevo_b200_emu.so")
     open(src, "w").write(src_text)
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-pthread", "-fvisibility=default",
-                    *E.EXTRA_FLAGS, "-I", os.path.join(ROOT, "include"), src, "-o", lib], check=True)
+                    *(["-DEMU_WITH_LEAN"] if with_lean else []), *E.EXTRA_FLAGS, "-I", os.path.join(ROOT, "include"), src, "-o", lib], check=True)
     return lib

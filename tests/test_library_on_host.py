@@ -23,7 +23,7 @@ def emu_ctx(tmp_path_factory):
     import test_gpu_track
     from revo_b200 import api
 
-    lib = _cuda_emu_lib.build(str(tmp_path_factory.mktemp("revo_b200_emu")))
+    lib = _cuda_emu_lib.build(str(tmp_path_factory.mktemp("revo_b200_emu")), with_lean=os.environ.get("REVO_EMU_WITH_LEAN") == "1")
     saved = (api._LIB_PATH, api._lib, test_gpu_pyramid.synth_pair, test_gpu_track.synth_pair)
     api._LIB_PATH, api._lib = lib, None
 
@@ -83,3 +83,22 @@ def test_vote_and_main_loops(emu_ctx, orc32, orc64):
     T.test_tracking_quality_vote(emu_ctx, orc64)
     T.test_revo_main_loop_on_gpu(emu_ctx, orc32, "cluster")
     T.test_multi_stream_main_loop_on_gpu(emu_ctx, "cluster")
+
+
+@pytest.mark.skipif(os.environ.get("REVO_EMU_WITH_LEAN") != "1", reason="the experimental lean engine is only built with REVO_EMU_WITH_LEAN=1")
+@pytest.mark.parametrize("pack", ["0", "1"])
+def test_lean_engine_through_the_c_abi(emu_ctx, orc32, orc64, pack):
+    """scratch/experiments/track_lean.cu wired in as engine 4 (what enable_lean_engine.patch does): the tracking tests through
+    the launcher, the C ABI and the Python API, scalar and packed accumulation."""
+    import test_gpu_track as T
+
+    os.environ["REVO_LEAN_PACK"] = pack
+    emu_ctx.set_track_engine(4, 0)
+    try:
+        T.test_eval_record_matches_oracle(emu_ctx, orc32, orc64, 1)
+        T.test_track_level_fixed_iterations(emu_ctx, orc64, 1, 8)
+        T.test_track_frames_default_rules(emu_ctx, orc32, orc64, 1)
+        T.test_track_batch_matches_single_and_check_init(emu_ctx, orc32)
+    finally:
+        emu_ctx.set_track_engine(1, 0)
+        os.environ.pop("REVO_LEAN_PACK", None)
