@@ -11,6 +11,9 @@ import pytest
 
 from conftest import synth_pair
 
+# an emulation deadlock must not hang the suite (the C call cannot be interrupted by a signal: kill the run instead)
+pytestmark = pytest.mark.timeout(900, method="thread")
+
 
 @pytest.fixture(scope="module")
 def canny_emu(tmp_path_factory):

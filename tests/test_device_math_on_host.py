@@ -17,6 +17,9 @@ import pytest
 
 from conftest import synth_pair
 
+# an emulation deadlock must not hang the suite (the C call cannot be interrupted by a signal: kill the run instead)
+pytestmark = pytest.mark.timeout(600, method="thread")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SHIM = r'''

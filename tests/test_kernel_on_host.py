@@ -10,6 +10,9 @@ import pytest
 
 from conftest import rot_angle, synth_pair
 
+# an emulation deadlock must not hang the suite (the C call cannot be interrupted by a signal: kill the run instead)
+pytestmark = pytest.mark.timeout(900, method="thread")
+
 
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):

@@ -9,8 +9,9 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.skipif(os.environ.get("REVO_RUN_EMULATED_LIBRARY") != "1",
-                                reason="slow emulation run of the GPU tests on the CPU (set REVO_RUN_EMULATED_LIBRARY=1)")
+pytestmark = [pytest.mark.skipif(os.environ.get("REVO_RUN_EMULATED_LIBRARY") != "1",
+                                 reason="slow emulation run of the GPU tests on the CPU (set REVO_RUN_EMULATED_LIBRARY=1)"),
+              pytest.mark.timeout(3600, method="thread")]
 
 SMALL = (160, 120)
 

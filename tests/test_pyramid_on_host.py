@@ -10,6 +10,9 @@ import pytest
 
 from conftest import synth_pair
 
+# an emulation deadlock must not hang the suite (the C call cannot be interrupted by a signal: kill the run instead)
+pytestmark = pytest.mark.timeout(1200, method="thread")
+
 
 class EmuLevelOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("gray", "depth", "edges", "edges_orig", "hist", "pts", "n_pts", "nz_patches", "dt", "opt",
