@@ -98,7 +98,7 @@ def oracle_pyramid(orc, cam, n_levels, bgr, depth, n_percentage=0.3):
     return p
 
 
-@pytest.mark.parametrize("seed,w,h,n_levels", [(4, 320, 240, 3), (6, 160, 120, 4)])
+@pytest.mark.parametrize("seed,w,h,n_levels", [(4, 192, 144, 3), (6, 160, 120, 4)])
 def test_pyramid_kernels_on_host_bit_exact(pyr_emu, orc32, seed, w, h, n_levels):
     p = synth_pair(seed, w, h)
     bgr, depth = p["key"]
@@ -115,8 +115,12 @@ def test_pyramid_kernels_on_host_fill_in_and_group_compaction(pyr_emu, orc32):
     p = synth_pair(11, 96, 72)
     bgr, depth = p["key"]
     po = oracle_pyramid(orc32, p["cam"], 3, bgr, depth, n_percentage=1.1)
-    assert any(not np.array_equal(po.edges[l], po.edges_orig[l]) for l in (1, 2))          # the fill-in changed something
-    compare(run_pyramid(pyr_emu, bgr, depth, p["cam"], 3, n_frames=8, n_percentage=1.1), po, 3)
+    assert all(not np.array_equal(po.edges[l], po.edges_orig[l]) for l in (1, 2))          # the fill-in changed both levels
+    compare(run_pyramid(pyr_emu, bgr, depth, p["cam"], 3, n_percentage=1.1), po, 3)
+    p = synth_pair(5, 64, 48)
+    bgr, depth = p["key"]
+    po = oracle_pyramid(orc32, p["cam"], 2, bgr, depth)
+    compare(run_pyramid(pyr_emu, bgr, depth, p["cam"], 2, n_frames=8), po, 2)
 
 
 def test_quality_vote_kernels_on_host(pyr_emu, orc32):
