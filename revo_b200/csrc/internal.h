@@ -80,7 +80,7 @@ struct revo_ctx {
     int stage_next;
     int track_ctas_per_pair;
     int track_threads;
-    int track_engine;        // 0 = automatic, 1 = one cluster per pair (track.cu), 2 = task queue (track_queue.cu), 3 = ping-pong clusters (track_pp.cu)
+    int track_engine;        // 0 = automatic, 1 = one cluster per pair (track.cu), 2 = task queue (track_queue.cu), 3 = ping-pong clusters (track_pp.cu), 4 = cluster per pair with the lean gather loop (track_lean.cu)
     int track_chunk_points;  // queue engine: minimum points per task (0 = automatic)
     cudaEvent_t ev[8];      // pyramid begin/end, keyframe begin/end, track kernel begin/end, upload begin/end (copy stream)
     bool ev_valid[4];
@@ -188,6 +188,8 @@ int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const Trac
 int launch_stage_in(revo_ctx *ctx, const void *src_mapped_host, void *dst, size_t bytes);
 
 // ---- track_pp.cu: cluster engine with warp-specialised CTAs working on two pairs at once ---------------
+int launch_track_lean(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, revo_track_result *d_results,
+                      double *d_records, revo_trace_entry *d_trace, int *d_trace_counts, int *d_work_counter);
 int launch_track_pp(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, revo_track_result *d_results,
                     double *d_records, revo_trace_entry *d_trace, int *d_trace_counts, int *d_work_counter);
 

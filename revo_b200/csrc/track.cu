@@ -139,17 +139,20 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 __syncwarp();
                 if (tid < world) st_release_sys(&((Mailbox *)prm.split_peers[tid])->flag[par][prm.split_rank], fl);
                 Mailbox *mine_mb = (Mailbox *)prm.split_peers[prm.split_rank];
+                bool timed_out = false;
                 if (tid < world) {
-                    // watchdog (~5 s): a peer that never launches must not hang this GPU; the result is then invalid
-                    // (ranks disagree), which the caller's cross-rank check catches
+                    // watchdog (~5 s): a peer that never launches (or died) must not hang this GPU.  The failure is
+                    // published in slot 31 of the record (otherwise always 0): every CTA of this rank sees it, abandons
+                    // the pair and the result carries REVO_ERR_COMM.
                     const long long t0 = clock64();
                     while (ld_acquire_sys(&mine_mb->flag[par][tid]) < fl) {
-                        if (clock64() - t0 > 10000000000ll) break;
+                        if (clock64() - t0 > 10000000000ll) { timed_out = true; break; }
                     }
                 }
-                __syncwarp();
+                const bool any_timeout = __any_sync(kFull, timed_out);
                 double tot = 0;
                 for (int g = 0; g < world; ++g) tot += ((volatile double *)mine_mb->data[par][g])[tid];
+                if (tid == 31) tot = any_timeout ? 1.0 : 0.0;
                 total[par][tid] = tot;
             }
             cluster.sync();
@@ -168,6 +171,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
         int evals_lvl[REVO_MAX_LEVELS] = {0, 0, 0, 0, 0, 0};
         int used_identity = 0;
         int ntrace = 0;
+        bool comm_failed = false;   // split mode: an exchange timed out (uniform over the CTAs of this rank)
 
         if (tid == 0) {
             for (int i = 0; i < 9; ++i) ctrl.R[i] = P.R[i];
@@ -215,6 +219,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                     acc[1] += cost_point(X, Y, Z, L, P.ref_dt_min, ed, use_filter);
                 }
                 reduce_record(acc);
+                if (world > 1 && rec[31] != 0.0) comm_failed = true;
                 if (tid == 0) {
                     if ((float)rec[0] < (float)rec[1]) {   // tracker.cpp:277
                         for (int i = 0; i < 9; ++i) ctrl.R[i] = (i % 4 == 0) ? 1.f : 0.f;
@@ -234,7 +239,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
             }
             float last_good = 0.f, last_bad = 0.f, last_sw = 0.f, last_su = 0.f;
 
-            for (int lvl = min_lvl; lvl >= max_lvl; --lvl) {
+            for (int lvl = min_lvl; lvl >= max_lvl && !comm_failed; --lvl) {
                 const LevelIn Lin = P.lvl[lvl];
                 const int n = *Lin.n_pts;
                 // block-cyclic split of the list over the CTAs of the cluster (and the ranks of a GPU split): member m takes
@@ -307,6 +312,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                     const long long c_gather = prm.profile ? clock64() : 0;
                     reduce_record(acc);
                     const long long c_reduce = prm.profile ? clock64() : 0;
+                    if (world > 1 && rec[31] != 0.0) { comm_failed = true; break; }
                     evals_lvl[lvl]++;
                     last_good = (float)rec[kRecGood]; last_bad = (float)rec[kRecBad];
                     last_sw = (float)rec[kRecSW]; last_su = (float)rec[kRecSU];
@@ -350,7 +356,8 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 o.res.sum_error_unweighted = last_su;
                 // tracker.cpp:351: good/bad < 4 -> NEW_KF (double division; bad == 0 -> inf -> OK)
                 o.status = ((double)last_good / (double)last_bad < 4.0) ? REVO_TRACKER_STATE_NEW_KF : REVO_TRACKER_STATE_OK;
-                o.rc = REVO_OK;
+                o.rc = comm_failed ? REVO_ERR_COMM : REVO_OK;
+                if (comm_failed) o.status = REVO_TRACKER_STATE_UNKNOWN;
                 for (int l = 0; l < REVO_MAX_LEVELS; ++l) {
                     o.n_evals[l] = evals_lvl[l];
                     o.n_pts[l] = (l >= max_lvl && l <= min_lvl) ? *P.lvl[l].n_pts : 0;
