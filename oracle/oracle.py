@@ -235,6 +235,31 @@ class Oracle:
         return dict(R=Rc.reshape(3, 3).T.copy(), T=Tc.copy(), error=float(err.value), status=status, good=ri.good,
                     bad=ri.bad, evals=list(evals), rc=rc.value)
 
+    def track_frames_traced(self, ref: "Pyramid", cur: "Pyramid", R, T, cfg: OptCfg, min_lvl: int, max_lvl: int = 0,
+                            check_init: bool = True, trace_cap: int = 1024):
+        """``track_frames`` plus the accept / reject sequence of every level: ``accepts[lvl]`` is a string of 'A' / 'r', one
+        character per LM try (coarse-to-fine order of the levels is the caller's to impose)."""
+        keep: list = []
+        arr = self._levels_array(ref, cur, keep)
+        Rc = self._r(np.asarray(R).T.reshape(-1)).copy()
+        Tc = self._r(T).copy()
+        err = self.real(0)
+        ri = self.ResInfo()
+        evals = (C.c_int * 6)()
+        per = (C.c_int * 6)()
+        rc = C.c_int(0)
+        trace = (TraceEntry * trace_cap)()
+        self.lib.orc_track_frames_traced.restype = C.c_int
+        status = self.lib.orc_track_frames_traced(arr, C.c_int(min_lvl), C.c_int(max_lvl), C.c_int(int(check_init)), C.byref(cfg),
+                                                  self._p(Rc), self._p(Tc), C.byref(err), C.byref(ri), evals, C.byref(rc), trace,
+                                                  C.c_int(trace_cap), per)
+        accepts, k = {}, 0
+        for lvl in range(min_lvl, max_lvl - 1, -1):
+            accepts[lvl] = "".join("A" if trace[k + i].accepted else "r" for i in range(per[lvl]))
+            k += per[lvl]
+        return dict(R=Rc.reshape(3, 3).T.copy(), T=Tc.copy(), error=float(err.value), status=status, good=ri.good,
+                    bad=ri.bad, evals=list(evals), rc=rc.value, accepts=accepts)
+
     def track_frames_batch(self, refs, curs, Rs, Ts, cfg: OptCfg, min_lvl: int, max_lvl: int = 0, check_init: bool = True):
         """OpenMP batch over independent pairs (CPU-baseline harness)."""
         n = len(refs)

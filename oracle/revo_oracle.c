@@ -604,6 +604,46 @@ ORC_API int orc_track_frames(const orc_level *levels, int min_lvl, int max_lvl, 
     return 0;
 }
 
+/* orc_track_frames with the LM trace of every level (parity tests: "same trace" = same accept / reject sequence, not only the same
+ * number of evaluations).  trace receives the entries of the levels min_lvl .. max_lvl back to back (capacity trace_cap in
+ * total), trace_per_lvl[lvl] the number of entries of that level. */
+ORC_API int orc_track_frames_traced(const orc_level *levels, int min_lvl, int max_lvl, int check_init,
+                                    const orc_opt_cfg *cfg, real *R, real *T, real *error_out,
+                                    orc_resinfo *ri_out, int *evals_per_lvl, int *rc_out,
+                                    orc_trace_entry *trace, int trace_cap, int *trace_per_lvl)
+{
+    if (check_init) {
+        const orc_level *L = &levels[min_lvl];
+        real I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z[3] = {0, 0, 0};
+        real costEye = orc_eval_cost_function(L->cur_pts4, L->cur_n, L->ref_dt, &L->cam, I, Z, cfg, min_lvl);
+        real costInit = orc_eval_cost_function(L->cur_pts4, L->cur_n, L->ref_dt, &L->cam, R, T, cfg, min_lvl);
+        if (costEye < costInit) {     /* tracker.cpp:277 */
+            memcpy(R, I, sizeof(I)); memcpy(T, Z, sizeof(Z));
+        }
+    }
+    real error = (real)INFINITY;
+    orc_resinfo ri; memset(&ri, 0, sizeof(ri));
+    int rc_all = 0, used = 0;
+    for (int lvl = min_lvl; lvl >= max_lvl; --lvl) {
+        const orc_level *L = &levels[lvl];
+        int ne = 0, rc = 0;
+        error = orc_track_level(L->cur_pts4, L->cur_n, L->ref_opt4, &L->cam, R, T, cfg, lvl, &ri, trace ? trace + used : 0,
+                                trace ? trace_cap - used : 0, &ne, 0, &rc);
+        int nt = ne - 1;
+        if (nt > trace_cap - used) nt = trace_cap - used;
+        if (nt < 0) nt = 0;
+        if (trace_per_lvl) trace_per_lvl[lvl] = nt;
+        used += nt;
+        if (evals_per_lvl) evals_per_lvl[lvl] = ne;
+        if (rc && !rc_all) rc_all = rc;
+    }
+    if (error_out) *error_out = error;
+    if (ri_out) *ri_out = ri;
+    if (rc_out) *rc_out = rc_all;
+    if ((double)ri.good / (double)ri.bad < 4) return 2;   /* tracker.cpp:351 */
+    return 0;
+}
+
 /* Batch of independent frame pairs over OpenMP threads: the CPU-baseline
  * harness ("all host threads the reference path can use": the reference
  * tracker itself is single-threaded per pair). levels is n_pairs*6 entries. */

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librevo_b200.so")
-SOURCES = ["capi.cu", "pyramid.cu", "canny.cu", "track.cu", "track_queue.cu", "track_pp.cu", "track_lean.cu"]
+SOURCES = ["capi.cu", "pyramid.cu", "canny.cu", "track.cu"]
 HEADERS = ["internal.h", "track_common.cuh", os.path.join("..", "..", "include", "revo_b200.h")]
 
 NVCC_FLAGS = [

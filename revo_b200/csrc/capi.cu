@@ -121,7 +121,7 @@ const char *revo_strerror(int code)
         case REVO_ERR_BAD_LEVEL: return "pyramid level out of range";
         case REVO_ERR_BUFFER_TOO_SMALL: return "destination buffer too small";
         case REVO_ERR_UNSUPPORTED: return "unsupported configuration";
-        case REVO_ERR_COMM: return "multi-GPU setup error";
+        case REVO_ERR_COMM: return "multi-GPU exchange failed (setup error, or a peer rank did not answer in time)";
         default: return "unknown error";
     }
 }
@@ -203,7 +203,7 @@ int revo_ctx_create(int device, revo_ctx **out)
     ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0; ctx->pinned_kf = nullptr; ctx->pinned_kf_bytes = 0; ctx->pinned_kf_busy = false;
     for (int i = 0; i < 2; ++i) { ctx->stage[i] = nullptr; ctx->stage_bytes[i] = 0; ctx->stage_used[i] = false; }
     ctx->stage_next = 0;
-    ctx->track_ctas_per_pair = 0; ctx->track_threads = 0; ctx->track_engine = 0; ctx->track_chunk_points = 0;
+    ctx->track_ctas_per_pair = 0; ctx->track_threads = 0;
     for (auto &v : ctx->ev_valid) v = false;
     ctx->split_rank = 0; ctx->split_world = 1; ctx->split_local = nullptr; ctx->split_seq = 0;
     for (auto &p : ctx->split_peers) p = nullptr;
@@ -300,11 +300,12 @@ int revo_ctx_set_track_shape(revo_ctx *ctx, int ctas_per_pair, int threads_per_c
     return REVO_OK;
 }
 
+// Kept for ABI compatibility with round 1: the library has ONE tracking engine (one thread-block cluster per pair, track.cu);
+// the task-queue and ping-pong engines measured slower at every batch size and live in scratch/experiments/ now.
 int revo_ctx_set_track_engine(revo_ctx *ctx, int engine, int chunk_points)
 {
-    if (!ctx || engine < 0 || engine > 4 || chunk_points < 0) return REVO_ERR_INVALID_ARG;
-    ctx->track_engine = engine;
-    ctx->track_chunk_points = chunk_points;
+    if (!ctx || chunk_points < 0) return REVO_ERR_INVALID_ARG;
+    if (engine != 0 && engine != 1) return REVO_ERR_UNSUPPORTED;
     return REVO_OK;
 }
 
@@ -851,6 +852,7 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     if (!trace) trace_cap = 0;
     prm.trace_cap = trace_cap;
     prm.profile = getenv("REVO_TRACK_PROF") != nullptr;
+    prm.speculate = !(getenv("REVO_TRACK_SPEC") && atoi(getenv("REVO_TRACK_SPEC")) == 0);   // A/B switch for profiling
     // device workspace: pairs | results | records | trace | trace counts
     const size_t b_pairs = align_up(sizeof(PairDesc) * (size_t)n, 256);
     const size_t b_res = align_up(sizeof(revo_track_result) * (size_t)n, 256);
@@ -858,34 +860,20 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     const size_t b_tr = align_up(sizeof(revo_trace_entry) * (size_t)trace_cap * n, 256);
     const size_t b_tc = align_up(sizeof(int) * (size_t)n, 256);
     uint8_t *ws = nullptr;
-    // engine: one cluster per pair (track.cu; measured faster at every batch size, scratch/track_bench.py) unless the
-    // caller / REVO_TRACK_ENGINE asks for the task queue (track_queue.cu); a pair split over several GPUs always uses
-    // the cluster engine (the peer mailboxes live there)
-    const int env_engine = getenv("REVO_TRACK_ENGINE") ? atoi(getenv("REVO_TRACK_ENGINE")) : 0;
-    int engine = ctx->track_engine ? ctx->track_engine : env_engine;
-    if (prm.split_world > 1) engine = 1;
-    if (engine != 2 && engine != 3 && engine != 4) engine = 1;
-    const size_t b_q = engine == 2 ? align_up(track_queue_workspace_bytes(n, 8 * ctx->prop.multiProcessorCount, nullptr), 256) : 0;
-    REVO_CUDA(ctx, cudaMallocAsync((void **)&ws, b_pairs + b_res + b_rec + b_tr + b_tc + 256 + b_q, ctx->stream));
+    REVO_CUDA(ctx, cudaMallocAsync((void **)&ws, b_pairs + b_res + b_rec + b_tr + b_tc + 256, ctx->stream));
     PairDesc *d_pairs = (PairDesc *)ws;
     revo_track_result *d_res = (revo_track_result *)(ws + b_pairs);
     double *d_rec = (double *)(ws + b_pairs + b_res);
     revo_trace_entry *d_tr = trace_cap ? (revo_trace_entry *)(ws + b_pairs + b_res + b_rec) : nullptr;
     int *d_tc = (int *)(ws + b_pairs + b_res + b_rec + b_tr);
     int *d_wc = (int *)(ws + b_pairs + b_res + b_rec + b_tr + b_tc);
-    uint8_t *d_q = ws + b_pairs + b_res + b_rec + b_tr + b_tc + 256;
     int rc = REVO_OK;
     rc = launch_stage_in(ctx, host, d_pairs, sizeof(PairDesc) * (size_t)n);
     cudaError_t e = cudaMemsetAsync(d_res, 0, b_res + b_rec, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_wc, 0, 256, ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "track upload");
     cudaEventRecord(ctx->ev[4], ctx->stream);
-    if (!rc) {
-        if (engine == 2) rc = launch_track_queue(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_q, b_q);
-        else if (engine == 3) rc = launch_track_pp(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);
-        else if (engine == 4) rc = launch_track_lean(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);
-        else rc = launch_track(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);
-    }
+    if (!rc) rc = launch_track(ctx, d_pairs, n, prm, d_res, d_rec, d_tr, d_tc, d_wc);
     cudaEventRecord(ctx->ev[5], ctx->stream);
     ctx->ev_valid[2] = true;
     if (!rc && results) {
@@ -904,34 +892,10 @@ static int run_track(revo_ctx *ctx, TrackParams &prm, int n, revo_pyr *const *re
     }
     unsigned long long prof[4] = {0, 0, 0, 0};
     const bool want_prof = getenv("REVO_TRACK_PROF") != nullptr;
-    int q_ctl[4] = {0, 0, 0, 0};   // head, tail, pairs_done, abort of the queue engine
-    if (!rc && engine == 2) cudaMemcpyAsync(q_ctl, d_q, sizeof(q_ctl), cudaMemcpyDeviceToHost, ctx->stream);
-    std::vector<unsigned long long> q_prof;
-    if (!rc && engine == 2 && want_prof) {
-        q_prof.resize(9 + (size_t)n);
-        cudaMemcpyAsync(q_prof.data(), d_q + 16, q_prof.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    }
-    if (!rc && want_prof && (engine == 1 || engine == 4)) cudaMemcpyAsync(prof, d_wc + 2, sizeof(prof), cudaMemcpyDeviceToHost, ctx->stream);
+    if (!rc && want_prof) cudaMemcpyAsync(prof, d_wc + 2, sizeof(prof), cudaMemcpyDeviceToHost, ctx->stream);
     cudaFreeAsync(ws, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess && !rc) rc = cuda_fail(ctx, e, "track kernel");
-    if (!rc && engine == 2 && (q_ctl[3] != 0 || q_ctl[2] != n)) {
-        char buf[160];
-        snprintf(buf, sizeof(buf), "track queue watchdog: abort=%d pairs_done=%d/%d head=%u tail=%u", q_ctl[3], q_ctl[2], n,
-                 (unsigned)q_ctl[0], (unsigned)q_ctl[1]);
-        ctx->last_error = buf;
-        rc = REVO_ERR_CUDA;
-    }
-    if (!rc && want_prof && engine == 2) {
-        const unsigned long long *st = q_prof.data() + 1;
-        std::vector<unsigned long long> fin(q_prof.begin() + 9, q_prof.end());
-        std::sort(fin.begin(), fin.end());
-        const double nt = (double)std::max<unsigned long long>(st[4], 1), nl = (double)std::max<unsigned long long>(st[5], 1);
-        fprintf(stderr, "[k_track_queue prof] pairs %d ctas %llu tasks %llu evals %llu | cycles/task: pop %.0f gather %.0f partial %.0f | "
-                        "cycles/last-arrival %.0f | pair finish us: min %.0f p25 %.0f p50 %.0f p75 %.0f p90 %.0f max %.0f\n",
-                n, st[6], st[4], st[5], st[0] / nt, st[1] / nt, st[2] / nt, st[3] / nl, fin.front() * 1e-3, fin[fin.size() / 4] * 1e-3,
-                fin[fin.size() / 2] * 1e-3, fin[fin.size() * 3 / 4] * 1e-3, fin[fin.size() * 9 / 10] * 1e-3, fin.back() * 1e-3);
-    }
     if (!rc && want_prof && prof[3])
         fprintf(stderr, "[k_track prof] pairs %d evals %llu  cycles/eval: gather %.0f reduce %.0f serial+sync %.0f\n", n, prof[3],
                 (double)prof[0] / prof[3], (double)prof[1] / prof[3], (double)prof[2] / prof[3]);

@@ -80,8 +80,6 @@ struct revo_ctx {
     int stage_next;
     int track_ctas_per_pair;
     int track_threads;
-    int track_engine;        // 0 = automatic, 1 = one cluster per pair (track.cu), 2 = task queue (track_queue.cu), 3 = ping-pong clusters (track_pp.cu), 4 = cluster per pair with the lean gather loop (track_lean.cu)
-    int track_chunk_points;  // queue engine: minimum points per task (0 = automatic)
     cudaEvent_t ev[8];      // pyramid begin/end, keyframe begin/end, track kernel begin/end, upload begin/end (copy stream)
     bool ev_valid[4];
     // split mode (multi-GPU single pair)
@@ -176,6 +174,7 @@ struct TrackParams {
     int level;           // for modes 1,2
     int trace_cap;
     int profile;         // 1: thread 0 accumulates clock64() cycles per phase (REVO_TRACK_PROF)
+    int speculate;       // 1: the reject-successor of every LM try is computed while the record is exchanged (default)
     // split mode
     int split_rank, split_world;
     unsigned long long split_seq0;
@@ -186,17 +185,5 @@ int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const Trac
                  int *d_work_counter);
 
 int launch_stage_in(revo_ctx *ctx, const void *src_mapped_host, void *dst, size_t bytes);
-
-// ---- track_pp.cu: cluster engine with warp-specialised CTAs working on two pairs at once ---------------
-int launch_track_lean(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, revo_track_result *d_results,
-                      double *d_records, revo_trace_entry *d_trace, int *d_trace_counts, int *d_work_counter);
-int launch_track_pp(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, revo_track_result *d_results,
-                    double *d_records, revo_trace_entry *d_trace, int *d_trace_counts, int *d_work_counter);
-
-// ---- track_queue.cu ----------------------------------------------------------
-// Task-queue engine: device workspace size for n_pairs (ring + pair states + partial tables) and the launcher.
-size_t track_queue_workspace_bytes(int n_pairs, int grid_cap, unsigned *cap_out);
-int launch_track_queue(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, revo_track_result *d_results,
-                       double *d_records, revo_trace_entry *d_trace, int *d_trace_counts, void *d_ws, size_t ws_bytes);
 
 }  // namespace revo

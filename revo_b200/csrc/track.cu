@@ -8,20 +8,28 @@
 //   Optimizer::calculateWarpUpdate (PASS B) + LGS6::update/finish             system/optimizer.cpp:192-234, utils/LGSX.h:320-326,392-398
 //   Eigen LDLT 6x6 solve, Sophus::SE3f exp / product                          system/optimizer.cpp:258-266
 //
-// Design (B200): a frame pair is owned by one thread-block CLUSTER (1..16 CTAs); clusters pull pairs from a
-// global work counter (persistent kernel).  PASS A and PASS B are fused: every evaluation at a pose warps each
-// 3-D edge point, fetches the 4 {gx,gy,dt} texels, forms the residual, Huber weight and 1x6 Jacobian and
-// accumulates the 21+6 normal-equation terms + 4 statistics in registers -- the 7 SoA buffers of the reference
-// never exist.  Two points are in flight per thread (their 8 texel gathers are issued back to back) to cover the
-// dependent pts -> texel latency.  The 32-value record is reduced with a transposing warp-shuffle tree, across
-// warps through shared memory, across the CTAs of the cluster through distributed shared memory (one cluster
-// barrier per evaluation), and -- when one pair is split over several GPUs -- across GPUs through peer-mapped
-// mailboxes over NVLink inside the same kernel.  Every CTA then runs the identical 6x6 LDL^T solve, SE3 update
-// and accept/reject test redundantly (bitwise-equal inputs, so no broadcast is needed): all levels and all LM
-// iterations of a pair run without a host round trip.  No tensor cores: there is no dense contraction here.
+// Design (B200): a frame pair is owned by one thread-block CLUSTER (1..16 CTAs); clusters pull pairs from a global work
+// counter (persistent kernel).  PASS A and PASS B are fused: every evaluation at a pose warps each 3-D edge point, fetches
+// the 32-byte quad record of its pixel (one 256-bit gather, L1::no_allocate), forms the residual, Huber weight and 1x6
+// Jacobian and accumulates the 21+6 normal-equation terms + statistics in registers -- the 7 SoA buffers of the reference
+// never exist.  A thread keeps its points of the level in a private column of a shared-memory cache and visits only points
+// that exist; two points are in flight per thread (software pipeline) to cover the point -> record latency.  The 32-value
+// record is reduced with a transposing warp-shuffle tree, across warps through shared memory, across the CTAs of the cluster
+// by a one-sided st.async exchange over distributed shared memory (transaction barrier, no cluster barrier), and -- when
+// one pair is split over several GPUs -- across GPUs through peer-mapped mailboxes over NVLink inside the same kernel.
+// Every CTA then runs the identical LM step (6x6 LDL^T, SE3 exp / product, accept test) redundantly: bitwise-equal inputs,
+// so no broadcast is needed, and all levels and all LM iterations of a pair run without a host round trip.
+// Two thirds of the LM tries of this optimizer are REJECTED (every iteration restarts at lambda = 0), and the pose that
+// follows a rejection depends only on what is known when the try starts (accepted normal equations, next lambda): lane 0
+// of warp 1 computes it while warp 0 waits for the record exchange, so after a rejection the next evaluation starts
+// without the solve on the critical path (lm_step in track_common.cuh picks it up).  The LM step itself runs in float32
+// like the reference's Eigen / Sophus types (a dependent chain: ~0.9 k cycles against ~3.7 k in double).
+// No tensor cores: there is no dense contraction here.
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "internal.h"
 #include "track_common.cuh"
@@ -47,12 +55,33 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// x, y, z of one cached point: three 32-bit shared loads / stores at immediate offsets from one running address
+template <int kThreads>
+__device__ __forceinline__ void lds3(uint32_t addr, float &x, float &y, float &z)
+{
+    asm volatile("ld.shared.f32 %0, [%3];\n\tld.shared.f32 %1, [%3+%4];\n\tld.shared.f32 %2, [%3+%5];"
+                 : "=f"(x), "=f"(y), "=f"(z)
+                 : "r"(addr), "n"(kThreads * 4), "n"(kThreads * 8));
+}
+template <int kThreads>
+__device__ __forceinline__ void sts3(uint32_t addr, float x, float y, float z)
+{
+    asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+%4], %2;\n\tst.shared.f32 [%0+%5], %3;"
+                 :: "r"(addr), "f"(x), "f"(y), "f"(z), "n"(kThreads * 4), "n"(kThreads * 8) : "memory");
+}
+
+// keeps a per-level constant in a register (the compiler otherwise re-derives it from the constant bank for every point)
+__device__ __forceinline__ float pin(float x)
+{
+    asm volatile("" : "+f"(x));
+    return x;
+}
 
 // ---- the kernel ---------------------------------------------------------------
-// Dynamic shared memory: the thread-private cache of the level's 3-D points, float[3][pcap][kThreads] (x, y, z planes):
-// thread t keeps the first `pcap` of ITS points of the current level there for all evaluations of the level, so an
-// evaluation starts with shared-memory reads instead of an L2 round trip and re-reads no list bytes from L2 / HBM.
-template <int kThreads, int kMinBlocks>
+// Dynamic shared memory: the thread-private cache of the level's 3-D points, float[pcap][3][kThreads]: thread t keeps the
+// first `pcap` of ITS points of the current level there for all evaluations of the level, so an evaluation starts with
+// shared-memory reads instead of an L2 round trip and re-reads no list bytes from L2 / HBM.
+template <int kThreads, int kMinBlocks, bool kNoL1>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, revo_track_result *__restrict__ results,
         double *__restrict__ records, revo_trace_entry *__restrict__ trace, int *__restrict__ trace_counts,
@@ -65,22 +94,26 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int kWarps = kThreads / 32;
 
-    extern __shared__ float s_pts[];
-    float *const sx = s_pts + tid, *const sy = sx + (size_t)pcap * kThreads, *const sz = sy + (size_t)pcap * kThreads;
+    extern __shared__ float s_pts[];   // [pcap][3][kThreads]: x, y, z of cached point k of thread t at (k * 3 + c) * kThreads + t
+    const uint32_t s_base = smem_u32(s_pts) + 4u * (uint32_t)tid;
+    constexpr uint32_t kPtStride = 3u * kThreads * 4u;
 
     __shared__ float warp_part[kWarps][32];
     __shared__ __align__(16) double cta_part[2][16][32];   // [parity][source rank]: partials pushed by the CTAs of the cluster
     __shared__ double total[2][32];                        // split mode: CTA 0 publishes the cross-GPU total here
-    __shared__ double rec[32];
+    __shared__ double rec[2][32];                          // [lm.acc]: record of the accepted pose, [lm.acc ^ 1]: the latest one
     __shared__ __align__(8) uint64_t xbar[2];              // transaction barriers of the partial exchange (one per parity)
     __shared__ Ctrl ctrl;
     __shared__ LMState lm;
+    __shared__ Trial trial[3];                             // poses: being evaluated / speculative successor / fresh proposal
+    __shared__ SpecIn specin[2];                           // input of the speculating thread, by evaluation parity
 
     const revo_opt_config &oc = prm.cfg.opt;
     const bool use_filter = oc.use_edge_filter != 0;
     const int world = prm.split_world > 1 ? prm.split_world : 1;
     const int n_members = world * C;
     const int member = (world > 1 ? prm.split_rank : 0) * C + crank;
+    const bool speculate = prm.speculate != 0 && kWarps >= 2;
     unsigned seq = 0;   // evaluation counter of this cluster (drives the double buffers)
 
     if (tid == 0) {
@@ -90,8 +123,16 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
     }
     if (C > 1) cluster.sync(); else __syncthreads();
 
-    // ---- reduction of a per-thread accumulator to `rec` (identical in every CTA of the cluster / every rank)
-    auto reduce_record = [&](float (&acc)[32]) {
+    // The successor of the try being evaluated in case it is rejected (lane 0 of warp 1, while warp 0 exchanges the record).
+    auto speculate_successor = [&](int cur) {
+        const SpecIn s = specin[seq & 1];
+        if (s.active) lm_propose(rec[s.acc], lm.q[s.pacc], lm.t[s.pacc], s.lambda, trial[cur == 2 ? 0 : cur + 1]);
+    };
+
+    // ---- reduction of a per-thread accumulator to rec[wb] (identical in every CTA of the cluster / every rank).  On return
+    // the record is visible to WARP 0 only (it goes straight on to the LM step); the other warps meet it at the block-wide
+    // barrier behind that step.  spec_now: lane 0 of warp 1 computes the reject-successor of trial[cur] meanwhile.
+    auto reduce_record = [&](float (&acc)[32], bool spec_now, int cur, int wb) {
         const float mine = warp_transpose_reduce(acc, lane);
         warp_part[wid][lane] = mine;
         __syncthreads();
@@ -105,8 +146,9 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 double s = 0;
 #pragma unroll
                 for (int w = 0; w < kWarps; ++w) s += (double)warp_part[w][lane];
+                double *dst = rec[wb];
                 if (C == 1) {
-                    rec[lane] = s;
+                    dst[lane] = s;
                 } else {
                     if (lane == 0) mbar_expect_tx(&xbar[par], (uint32_t)C * 256u);
                     const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
@@ -114,8 +156,10 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                     mbar_wait(&xbar[par], (seq >> 1) & 1u);
                     double tot = 0;
                     for (int r = 0; r < C; ++r) tot += cta_part[par][r][lane];   // rank order: deterministic
-                    rec[lane] = tot;
+                    dst[lane] = tot;
                 }
+            } else if (spec_now && tid == 32) {
+                speculate_successor(cur);
             }
         } else {
             if (tid < 32) {
@@ -154,12 +198,14 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 for (int g = 0; g < world; ++g) tot += ((volatile double *)mine_mb->data[par][g])[tid];
                 if (tid == 31) tot = any_timeout ? 1.0 : 0.0;
                 total[par][tid] = tot;
+            } else if (spec_now && tid == 32) {
+                speculate_successor(cur);      // overlaps the NVLink round trip
             }
             cluster.sync();
-            if (tid < 32) rec[tid] = *cluster.map_shared_rank(&total[par][tid], 0);
+            if (tid < 32) rec[wb][tid] = *cluster.map_shared_rank(&total[par][tid], 0);
         }
         seq++;
-        __syncthreads();
+        if (wid == 0) __syncwarp();
     };
 
     long long prof_gather = 0, prof_reduce = 0, prof_serial = 0, prof_evals = 0;   // thread 0: cycles per phase
@@ -174,10 +220,13 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
         bool comm_failed = false;   // split mode: an exchange timed out (uniform over the CTAs of this rank)
 
         if (tid == 0) {
-            for (int i = 0; i < 9; ++i) ctrl.R[i] = P.R[i];
-            for (int i = 0; i < 3; ++i) ctrl.t[i] = P.t[i];
+            for (int i = 0; i < 9; ++i) trial[0].R[i] = P.R[i];
+            for (int i = 0; i < 3; ++i) trial[0].t[i] = P.t[i];
+            ctrl.cur = 0;
             ctrl.pair_skip = rotation_ok(P.R) ? 0 : 1;
             ctrl.level_done = 0;
+            lm.acc = 0; lm.pacc = 0;
+            specin[0].active = 0; specin[1].active = 0;
         }
         __syncthreads();
         const bool skip = ctrl.pair_skip != 0;
@@ -207,9 +256,9 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 const float ed = oc.edge_distance_lvl[min_lvl];
                 float R[9], t[3];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) R[i] = ctrl.R[i];
+                for (int i = 0; i < 9; ++i) R[i] = trial[0].R[i];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) t[i] = ctrl.t[i];
+                for (int i = 0; i < 3; ++i) t[i] = trial[0].t[i];
                 for (int i = lo + tid; i < hi; i += kThreads) {
                     const float4 p = __ldg(L.pts + i);
                     acc[0] += cost_point(p.x, p.y, p.z, L, P.ref_dt_min, ed, use_filter);
@@ -218,26 +267,26 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                     const float Z = R[2] * p.x + R[5] * p.y + R[8] * p.z + t[2];
                     acc[1] += cost_point(X, Y, Z, L, P.ref_dt_min, ed, use_filter);
                 }
-                reduce_record(acc);
-                if (world > 1 && rec[31] != 0.0) comm_failed = true;
-                if (tid == 0) {
-                    if ((float)rec[0] < (float)rec[1]) {   // tracker.cpp:277
-                        for (int i = 0; i < 9; ++i) ctrl.R[i] = (i % 4 == 0) ? 1.f : 0.f;
-                        for (int i = 0; i < 3; ++i) ctrl.t[i] = 0.f;
-                        ctrl.pair_skip = 2;   // marker: identity init used
-                    }
-                }
+                reduce_record(acc, false, 0, 1);
                 __syncthreads();
-                used_identity = ctrl.pair_skip == 2;
+                const double *r = rec[1];
+                if (world > 1 && r[31] != 0.0) comm_failed = true;
+                const bool take_identity = (float)r[0] < (float)r[1];   // tracker.cpp:277 (uniform: every thread reads the same record)
+                __syncthreads();
+                if (tid == 0 && take_identity) {
+                    for (int i = 0; i < 9; ++i) trial[0].R[i] = (i % 4 == 0) ? 1.f : 0.f;
+                    for (int i = 0; i < 3; ++i) trial[0].t[i] = 0.f;
+                }
+                used_identity = take_identity ? 1 : 0;
                 __syncthreads();
             }
 
             if (tid == 0) {
-                quat_from_R(ctrl.R, lm.q);
-                for (int i = 0; i < 3; ++i) lm.t[i] = ctrl.t[i];
+                quat_from_R<lmreal>(trial[0].R, lm.q[0]);
+                for (int i = 0; i < 3; ++i) lm.t[0][i] = (lmreal)trial[0].t[i];
                 lm.last_residual = INFINITY;
             }
-            float last_good = 0.f, last_bad = 0.f, last_sw = 0.f, last_su = 0.f;
+            float last_good = 0.f, last_bad = 0.f, last_sw = 0.f, last_su = 0.f;   // of the last evaluation (thread 0 only)
 
             for (int lvl = min_lvl; lvl >= max_lvl && !comm_failed; --lvl) {
                 const LevelIn Lin = P.lvl[lvl];
@@ -247,94 +296,105 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 // and the cluster as a whole still sweeps the tile-major list front to back
                 const int stride = n_members * kThreads;
                 const int first_idx = member * kThreads + tid;
-                const int n_iter = (n + stride - 1) / stride;          // uniform over the cluster
-                const int n_cached = n_iter < pcap ? n_iter : pcap;
+                // this thread's points: first_idx, first_idx + stride, ... (the count differs by at most one over the cluster)
+                const int my_iter = first_idx < n ? (n - first_idx + stride - 1) / stride : 0;
+                const int my_cached = my_iter < pcap ? my_iter : pcap;
                 const float4 *__restrict__ pts = Lin.pts;
                 LevelConst L;
                 L.fx = Lin.fx; L.fy = Lin.fy; L.cx = Lin.cx; L.cy = Lin.cy;
-                L.umax = (float)(Lin.w - 2); L.vmax = (float)(Lin.h - 2); L.w = Lin.w; L.opt = Lin.opt;
-                const float ed = oc.edge_distance_lvl[lvl];
-                const float huber = oc.huber_edge;
-                // this thread's points of the level -> its private columns of the shared-memory cache
-                for (int k = 0; k < n_cached; ++k) {
-                    const int i = first_idx + k * stride;
-                    const float4 p = i < n ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    sx[k * kThreads] = p.x; sy[k * kThreads] = p.y; sz[k * kThreads] = p.z;
+                L.umax = pin((float)(Lin.w - 2)); L.vmax = pin((float)(Lin.h - 2)); L.w = Lin.w; L.opt = Lin.opt;
+                const float ed_eff = pin(use_filter ? oc.edge_distance_lvl[lvl] : INFINITY);
+                const float huber = pin(oc.huber_edge);
+                const float kqfx = pin(Lin.fx * (1.0f / 32764.0f)), kqfy = pin(Lin.fy * (1.0f / 32764.0f));
+                // this thread's points of the level -> its private slots of the shared-memory cache
+                for (int k = 0; k < my_cached; ++k) {
+                    const float4 p = __ldg(pts + first_idx + (size_t)k * stride);
+                    sts3<kThreads>(s_base + (uint32_t)k * kPtStride, p.x, p.y, p.z);
                 }
-                auto fetch = [&](int k, bool &exists) -> float4 {
-                    const int i = first_idx + k * stride;
-                    exists = i < n;
-                    if (k < n_cached) return make_float4(sx[k * kThreads], sy[k * kThreads], sz[k * kThreads], 1.f);
-                    return __ldg(pts + (exists ? i : 0));
-                };
                 bool first = true;
                 __syncthreads();
                 while (true) {
+                    const int cur = ctrl.cur;
+                    const int wb = lm.acc ^ 1;     // record buffer this evaluation writes (lm.acc: the accepted pose's record)
                     float R[9], t[3];
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) R[i] = ctrl.R[i];
+                    for (int i = 0; i < 9; ++i) R[i] = trial[cur].R[i];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) t[i] = ctrl.t[i];
+                    for (int i = 0; i < 3; ++i) t[i] = trial[cur].t[i];
                     float acc[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
                     const long long c_begin = prm.profile ? clock64() : 0;
-                    // Software pipeline, two register sets (A/B): while point k is being finished the 256-bit gather of
-                    // point k+1 is in flight.  All loop conditions are uniform over the CTA; points that do not exist,
-                    // project out of bounds or fail the edge filter run the same straight-line code with weight 0.
-                    if (n_iter > 0) {
-                        bool eA, eB;
-                        float4 p = fetch(0, eA);
-                        ProjB A = project_b(eA, p, L, R, t), B;
+                    // Two pipelined segments (cached points, then the uncached tail of a long level), each with two
+                    // register sets (A/B): while point k is being finished the 256-bit gather of point k+1 is in flight.
+                    auto segment = [&](auto from_smem, int k0, int k1) {
+                        constexpr bool kS = decltype(from_smem)::value;
+                        if (k0 >= k1) return;
+                        uint32_t sp = s_base + (uint32_t)k0 * kPtStride;
+                        const float4 *gp = pts + first_idx + (size_t)k0 * stride;
+                        auto arm = [&](ProjB &Q, uint4 &q0, uint4 &q1) {
+                            float x, y, z;
+                            if constexpr (kS) {
+                                lds3<kThreads>(sp, x, y, z);
+                                sp += kPtStride;
+                            } else {
+                                const float4 p = __ldg(gp);
+                                gp += stride;
+                                x = p.x; y = p.y; z = p.z;
+                            }
+                            Q = project_b(x, y, z, L, R, t);
+                            ldg_quad<kNoL1>(Q.bp, q0, q1);
+                        };
+                        ProjB A, B;
                         uint4 a0, a1, b0, b1;
-                        ldg_quad(A.bp, a0, a1);
-                        int k = 0;
+                        arm(A, a0, a1);
+                        int left = k1 - k0 - 1;   // points of the segment not yet armed
                         while (true) {
-                            const bool hasB = k + 1 < n_iter;
-                            if (hasB) {
-                                p = fetch(k + 1, eB);
-                                B = project_b(eB, p, L, R, t);
-                                ldg_quad(B.bp, b0, b1);
-                            }
-                            finish_point_b(A, a0, a1, L, ed, use_filter, huber, acc);
-                            if (!hasB) break;
-                            const bool hasA = k + 2 < n_iter;
-                            if (hasA) {
-                                p = fetch(k + 2, eA);
-                                A = project_b(eA, p, L, R, t);
-                                ldg_quad(A.bp, a0, a1);
-                            }
-                            finish_point_b(B, b0, b1, L, ed, use_filter, huber, acc);
-                            if (!hasA) break;
-                            k += 2;
+                            if (left > 0) arm(B, b0, b1);
+                            finish_point_b(A, a0, a1, kqfx, kqfy, ed_eff, huber, acc);
+                            if (left <= 0) break;
+                            if (left > 1) arm(A, a0, a1);
+                            finish_point_b(B, b0, b1, kqfx, kqfy, ed_eff, huber, acc);
+                            if (left <= 1) break;
+                            left -= 2;
                         }
-                    }
+                    };
+                    segment(std::true_type{}, 0, my_cached);
+                    segment(std::false_type{}, my_cached, my_iter);
+                    acc[kRecBad] = (float)my_iter - acc[kRecGood];   // every visited point exists
                     const long long c_gather = prm.profile ? clock64() : 0;
-                    reduce_record(acc);
+                    const bool spec_now = speculate && !first && prm.mode != 2;
+                    reduce_record(acc, spec_now, cur, wb);
                     const long long c_reduce = prm.profile ? clock64() : 0;
-                    if (world > 1 && rec[31] != 0.0) { comm_failed = true; break; }
                     evals_lvl[lvl]++;
-                    last_good = (float)rec[kRecGood]; last_bad = (float)rec[kRecBad];
-                    last_sw = (float)rec[kRecSW]; last_su = (float)rec[kRecSU];
-
-                    if (prm.mode == 2) {   // single evaluation: export the record
-                        if (crank == 0 && tid < 32 && records) records[(size_t)pair * 32 + tid] = rec[tid];
+                    if (prm.mode == 2) {   // single evaluation: export the record (warp 0 wrote it)
+                        if (crank == 0 && tid < 32 && records) records[(size_t)pair * 32 + tid] = rec[wb][tid];
                         break;
                     }
-
                     if (tid == 0) {
-                        // Optimizer::trackFrames LM logic, optimizer.cpp:243-306 (track_common.cuh: lm_step)
+                        const double *r = rec[wb];
+                        last_good = (float)r[kRecGood]; last_bad = (float)r[kRecBad];
+                        last_sw = (float)r[kRecSW]; last_su = (float)r[kRecSU];
+                        // Optimizer::trackFrames LM logic, optimizer.cpp:243-306 (track_common.cuh: lm_step).  reduce_record
+                        // advanced seq: the evaluation just finished used specin[(seq - 1) & 1], the next reads specin[seq & 1]
                         revo_trace_entry te;
                         bool traced;
-                        const bool done = lm_step(lm, rec, oc, lvl, first, ctrl.R, ctrl.t, &te, &traced);
+                        int next = cur;
+                        LMOrder order;
+                        const bool done = lm_step(lm, trial, next, rec, spec_now, specin[(seq - 1) & 1], specin[seq & 1], order, oc, lvl,
+                                                  first, &te, &traced);
+                        // a fresh proposal is needed (first evaluation, accepted try, or no speculation)
+                        if (order.propose) lm_propose(rec[order.acc], lm.q[order.pacc], lm.t[order.pacc], order.lambda, trial[order.slot]);
                         if (traced) {
                             if (trace && crank == 0 && ntrace < prm.trace_cap) trace[(size_t)pair * prm.trace_cap + ntrace] = te;
                             ntrace++;
                         }
+                        ctrl.cur = next;
                         ctrl.level_done = done ? 1 : 0;
                     }
                     first = false;
                     __syncthreads();
+                    if (world > 1 && rec[wb][31] != 0.0) { comm_failed = true; break; }   // an exchange timed out (uniform)
                     if (prm.profile && tid == 0) {
                         const long long c_end = clock64();
                         prof_gather += c_gather - c_begin; prof_reduce += c_reduce - c_gather; prof_serial += c_end - c_reduce;
@@ -347,8 +407,9 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
 
             if (crank == 0 && tid == 0 && prm.mode != 2) {
                 revo_track_result &o = results[pair];
-                for (int i = 0; i < 9; ++i) o.R[i] = ctrl.R[i];
-                for (int i = 0; i < 3; ++i) o.t[i] = ctrl.t[i];
+                const Trial &fin = trial[ctrl.cur];
+                for (int i = 0; i < 9; ++i) o.R[i] = fin.R[i];
+                for (int i = 0; i < 3; ++i) o.t[i] = fin.t[i];
                 o.error = lm.last_residual;
                 o.res.good_pts_edges = (int)last_good;
                 o.res.bad_pts_edges = (int)last_bad;
@@ -403,12 +464,12 @@ int launch_stage_in(revo_ctx *ctx, const void *src_mapped_host, void *dst, size_
 }
 
 // ---- launcher -------------------------------------------------------------------
-template <int kThreads, int kMinBlocks>
+template <int kThreads, int kMinBlocks, bool kNoL1>
 static int launch_track_t(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, int ctas_per_pair,
                           revo_track_result *d_results, double *d_records, revo_trace_entry *d_trace, int *d_trace_counts,
                           int *d_work_counter)
 {
-    auto kern = k_track<kThreads, kMinBlocks>;
+    auto kern = k_track<kThreads, kMinBlocks, kNoL1>;
     if (ctas_per_pair > 8) REVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     // points per thread cached in shared memory: ~half of the SM's shared memory over the resident CTAs (the rest stays L1)
     const int env_pcap = getenv("REVO_TRACK_PCAP") ? atoi(getenv("REVO_TRACK_PCAP")) : -1;
@@ -456,12 +517,14 @@ int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const Trac
     const int slots256 = 2 * ctx->prop.multiProcessorCount;
     int C = ctx->track_ctas_per_pair > 0 ? ctx->track_ctas_per_pair : 8;
     const int T = ctx->track_threads > 0 ? ctx->track_threads : ((long long)n_pairs * C > slots256 ? 128 : 256);
+    // A/B switch for profiling only (REVO_TRACK_HINT=0: plain gather; default: L1::no_allocate)
+    const bool plain = getenv("REVO_TRACK_HINT") && atoi(getenv("REVO_TRACK_HINT")) == 0;
 #define REVO_TRACK_ARGS ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter
     switch (T) {
-        case 128: return launch_track_t<128, 4>(REVO_TRACK_ARGS);
-        case 512: return launch_track_t<512, 1>(REVO_TRACK_ARGS);
-        case 1024: return launch_track_t<1024, 1>(REVO_TRACK_ARGS);
-        default: return launch_track_t<256, 2>(REVO_TRACK_ARGS);
+        case 128: return plain ? launch_track_t<128, 4, false>(REVO_TRACK_ARGS) : launch_track_t<128, 4, true>(REVO_TRACK_ARGS);
+        case 512: return launch_track_t<512, 1, true>(REVO_TRACK_ARGS);
+        case 1024: return launch_track_t<1024, 1, true>(REVO_TRACK_ARGS);
+        default: return plain ? launch_track_t<256, 2, false>(REVO_TRACK_ARGS) : launch_track_t<256, 2, true>(REVO_TRACK_ARGS);
     }
 #undef REVO_TRACK_ARGS
 }

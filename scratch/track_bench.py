@@ -51,27 +51,24 @@ def main():
 
     # (name, engine, ctas_per_pair, threads, chunk_points, env)
     configs = [
-        ("cluster C8 T128 (default for > 37 pairs)", 1, 8, 128, 0, {}),
-        ("cluster C4 T256", 1, 4, 256, 0, {}),
-        ("cluster C8 T256", 1, 8, 256, 0, {}),
-        ("cluster C8 T128 pcap8", 1, 8, 128, 0, {"REVO_TRACK_PCAP": "8"}),
-        ("pingpong C8", 3, 8, 0, 0, {}),
-        ("queue T128 s512 o2", 2, 0, 128, 0, {}),
-        # engine 4 exists only after scratch/experiments/enable_lean_engine.patch (otherwise these lines print FAILED)
-        ("lean C8 T128", 4, 8, 128, 0, {}),
-        ("lean C8 T128 packed", 4, 8, 128, 0, {"REVO_LEAN_PACK": "1"}),
-        ("lean C8 T128 packed no-L1", 4, 8, 128, 0, {"REVO_LEAN_PACK": "1", "REVO_LEAN_HINT": "3"}),
+        ("C8 T128 (default)", 1, 8, 128, 0, {}),
+        ("C8 T128 no speculation", 1, 8, 128, 0, {"REVO_TRACK_SPEC": "0"}),
+        ("C8 T128 plain gather", 1, 8, 128, 0, {"REVO_TRACK_HINT": "0"}),
+        ("C8 T128 plain, no spec", 1, 8, 128, 0, {"REVO_TRACK_HINT": "0", "REVO_TRACK_SPEC": "0"}),
+        ("C4 T256", 1, 4, 256, 0, {}),
+        ("C8 T256", 1, 8, 256, 0, {}),
+        ("C8 T128 pcap8", 1, 8, 128, 0, {"REVO_TRACK_PCAP": "8"}),
+        ("C8 T128 maxc64", 1, 8, 128, 0, {"REVO_TRACK_MAX_CLUSTERS": "64"}),
     ]
     if args.configs:
         keep = set(int(x) for x in args.configs.split(","))
         configs = [c for i, c in enumerate(configs) if i in keep]
     base = None
     for name, eng, C, T, chunk, env in configs:
-        for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS", "REVO_LEAN_PACK", "REVO_LEAN_HINT"):
+        for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS", "REVO_TRACK_SPEC", "REVO_TRACK_HINT"):
             os.environ.pop(k, None)
         os.environ.update(env)
         try:
-            ctx.set_track_engine(eng, chunk)
             ctx.set_track_shape(C, T)
             ms = []
             for r in range(args.reps + 2):
@@ -103,17 +100,14 @@ def main():
     print("evals per pair: min %d p50 %d p90 %d max %d" % (tot.min(), np.median(tot), np.percentile(tot, 90), tot.max()))
     # profile pass (phase cycle counters; slows the kernel slightly) + sub-batches (critical path vs throughput)
     os.environ["REVO_TRACK_PROF"] = "1"
-    for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS", "REVO_LEAN_PACK", "REVO_LEAN_HINT"):
+    for k in ("REVO_Q_OVERSUB_X4", "REVO_Q_SMIN", "REVO_Q_THREADS", "REVO_TRACK_PCAP", "REVO_TRACK_MAX_CLUSTERS", "REVO_TRACK_SPEC", "REVO_TRACK_HINT"):
         os.environ.pop(k, None)
-    for eng in (1,):
-        ctx.set_track_engine(eng, 0)
-        ctx.set_track_shape(0, 0)
-        trk.trackFramesBatch(Rs, Ts, kf, cur)
+    ctx.set_track_shape(0, 0)
+    trk.trackFramesBatch(Rs, Ts, kf, cur)
     os.environ.pop("REVO_TRACK_PROF")
     for nb in (1, 8, 32, 64, B):
         sub_k = api.PyramidBatch.__new__(api.PyramidBatch)
-        for eng in (3, 1):
-            ctx.set_track_engine(eng, 0)
+        for eng in (1,):
             refs = [kf[i] for i in range(nb)]
             curs = [cur[i] for i in range(nb)]
             ms = []

@@ -204,6 +204,10 @@ static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __float2int_rn(float a) { return (int)lrintf(a); }
 static inline double __drcp_rn(double x) { return 1.0 / x; }
+static inline float __frcp_rn(float x) { return 1.0f / x; }
+static inline int __double2loint(double v) { uint64_t u; std::memcpy(&u, &v, 8); return (int)(uint32_t)u; }
+static inline int __double2hiint(double v) { uint64_t u; std::memcpy(&u, &v, 8); return (int)(uint32_t)(u >> 32); }
+static inline double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double v; std::memcpy(&v, &u, 8); return v; }
 static inline float __fdividef(float a, float b) { return a / b; }
 namespace cooperative_groups {
 struct cluster_group {
@@ -218,13 +222,12 @@ namespace cg = cooperative_groups;
 
 namespace revo {
 // host versions of the PTX helpers of track_common.cuh / track.cu
-static inline void ldg_quad(const uint4 *p, uint4 &r0, uint4 &r1)
+template <bool kNoL1> static inline void ldg_quad(const uint4 *p, uint4 &r0, uint4 &r1)
 {
     const uint32_t *q = (const uint32_t *)p;
     r0 = make_uint4(q[0], q[1], q[4], q[5]);
     r1 = make_uint4(q[2], q[3], q[6], q[7]);
 }
-template <int kHint> static inline void ldg_quad_h(const uint4 *p, uint4 &r0, uint4 &r1) { ldg_quad(p, r0, r1); }
 static inline float rcp_approx(float x) { return 1.0f / x; }
 static inline uint32_t smem_u32(const void *p) { return (uint32_t)((const char *)p - (const char *)emu::cta->dyn.data()); }   // only meaningful for the dynamic buffer
 // mbarrier with transaction count in one 64-bit word: [31:0] pending transaction bytes (signed: completions may come before the
@@ -383,8 +386,8 @@ template <class F> static void launch_seq(dim3 grid, dim3 block, size_t dyn_byte
 }
 }
 // @GENERIC_END
-// One frame pair through a tracking kernel.  variant: 0 = k_track<128,4> (library), 1 = k_track_lean<128,4,0,false>,
-// 2 = k_track_lean<128,4,0,true> (packed accumulation); the lean variants exist only when the experiment source was given.
+// Frame pairs through the tracking kernel k_track<128, 4, true>.  variant: 0 = with the speculative reject-successor (lane 0 of
+// warp 1, the default of the library), 1 = without it.
 extern "C" int emu_track_pairs(int variant, int n_pairs, int n_clusters, int ctas_per_pair, int n_levels, const float *const *pts, const int *n_pts,
                                const float *const *dt, const int *w, const int *h, const float *cam4, const float *R9s, const float *t3s,
                                const revo_tracker_config *cfg, int mode, int level, int pcap, revo_track_result *results, double *records)
@@ -422,20 +425,13 @@ extern "C" int emu_track_pairs(int variant, int n_pairs, int n_clusters, int cta
     const size_t dyn = (size_t)pcap * T * 12;
     const PairDesc *d_pairs = pairs.data();
     int *wc = work_counter;
-    if (variant == 0) {
-        emu::run_grid(n_clusters, ctas_per_pair, T, dyn, [=]() { k_track<T, 4>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
-    }
-#ifdef EMU_WITH_LEAN
-    else if (variant == 1) {
-        emu::run_grid(n_clusters, ctas_per_pair, T, dyn, [=]() { k_track_lean<T, 4, 0, false>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
-    } else if (variant == 2) {
-        emu::run_grid(n_clusters, ctas_per_pair, T, dyn, [=]() { k_track_lean<T, 4, 0, true>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
-    }
-#endif
-    else return 1;
+    if (variant != 0 && variant != 1) return 1;
+    prm.speculate = variant == 0 ? 1 : 0;
+    emu::run_grid(n_clusters, ctas_per_pair, T, dyn, [=]() { k_track<T, 4, true>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
     return 0;
 }
 '''
+
 
 
 def _strip_functions(text, names):
@@ -496,11 +492,6 @@ def build(out_dir, with_lean=False):
              grab(pyr, r"^__device__ __forceinline__ float4 opt_texel"), grab(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
              grab(pyr, r"^__device__ __forceinline__ void store_quad"), _struct(track, "Mailbox"), _kernel(track, "k_track")]
     flags = []
-    if with_lean:
-        lean = rd("scratch", "experiments", "track_lean.cu")
-        parts += [grab(lean, r"^__device__ __forceinline__ ProjB project_l"), grab(lean, r"^__device__ __forceinline__ void finish_point_l"),
-                  _struct(lean, "PackedAcc"), grab(lean, r"^__device__ __forceinline__ void finish_point_p"), _kernel(lean, "k_track_lean")]
-        flags = ["-DEMU_WITH_LEAN"]
     parts.append("}  // namespace revo")
     src, lib = os.path.join(out_dir, "cuda_emu.cpp"), os.path.join(out_dir, "libcuda_emu.so")
     open(src, "w").write(PRELUDE + "\n".join(parts) + RUNNER)

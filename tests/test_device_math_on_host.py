@@ -41,10 +41,13 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline int __float2int_rn(float a) { return (int)lrintf(a); }
 static inline float rcp_approx(float x) { return 1.0f / x; }
 static inline double __drcp_rn(double x) { return 1.0 / x; }
+static inline float __frcp_rn(float x) { return 1.0f / x; }
 #include "revo_b200.h"
 constexpr int kRecA = 0, kRecB = 21, kRecSW = 27, kRecSU = 28, kRecGood = 29, kRecBad = 30;
 struct LevelIn { float fx, fy, cx, cy; int w, h; };   // the fields of internal.h's LevelIn that cost_point reads
 static inline float __ldg(const float *p) { return *p; }
+using std::fmaf;
+using std::fma;
 '''
 
 DRIVER = r'''
@@ -66,11 +69,13 @@ extern "C" int host_eval_record(const float *pts4, int n, const float *dt, int w
     for (int i = 0; i < 32; ++i) rec32[i] = 0.0;
     for (int i = 0; i < n; ++i) {
         const float4 p = make_float4(pts4[4 * i], pts4[4 * i + 1], pts4[4 * i + 2], 1.f);
-        const ProjB P = project_b(true, p, L, R9, t3);
+        const ProjB P = project_b(p.x, p.y, p.z, L, R9, t3);
         const uint32_t *q = (const uint32_t *)P.bp;        // ldg_quad: one 32-byte record -> the two row records
         const uint4 r0 = make_uint4(q[0], q[1], q[4], q[5]), r1 = make_uint4(q[2], q[3], q[6], q[7]);
         float acc[32] = {0};
-        finish_point_b(P, r0, r1, L, ed, use_filter != 0, huber, acc);
+        // the kernel's per-level constants (k_track): gradient scale folded with the focal length, +inf = filter off
+        finish_point_b(P, r0, r1, fx * (1.0f / 32764.0f), fy * (1.0f / 32764.0f), use_filter ? ed : INFINITY, huber, acc);
+        acc[kRecBad] = 1.f - acc[kRecGood];                 // every visited point exists: bad = visited - good
         for (int k = 0; k < 32; ++k) rec32[k] += acc[k];
     }
     return 0;
@@ -93,36 +98,74 @@ extern "C" double host_cost(const float *pts4, int n, const float *dt, int w, in
 }
 
 // thin exports of the double-precision SE3 / solver helpers of the serial LM step
-extern "C" void host_se3_exp(const double *xi, double *q, double *t) { se3_exp(xi, q, t); }
-extern "C" void host_se3_mul(const double *qa, const double *ta, const double *qb, const double *tb, double *q, double *t) { se3_mul(qa, ta, qb, tb, q, t); }
-extern "C" void host_quat_from_R(const float *R9, double *q) { quat_from_R(R9, q); }
-extern "C" void host_quat_to_R(const double *q, double *R9) { quat_to_R(q, R9); }
-extern "C" void host_solve6(const double *Au21, const double *b, double inv_n, double lam1, double *x) { solve6(Au21, b, inv_n, lam1, x); }
+extern "C" void host_se3_exp(const double *xi, double *q, double *t) { se3_exp<double>(xi, q, t); }
+extern "C" void host_se3_mul(const double *qa, const double *ta, const double *qb, const double *tb, double *q, double *t) { se3_mul<double>(qa, ta, qb, tb, q, t); }
+extern "C" void host_quat_from_R(const float *R9, double *q) { quat_from_R<double>(R9, q); }
+extern "C" void host_quat_to_R(const double *q, double *R9) { quat_to_R<double>(q, R9); }
+extern "C" void host_solve6(const double *Au21, const double *b, double inv_n, double lam1, double *x) { solve6<double>(Au21, b, inv_n, lam1, x); }
+// the float instantiations (what the library runs): float in / out through double arrays
+extern "C" void host_se3_exp_f(const double *xi, double *q, double *t)
+{
+    float xf[6], qf[4], tf[3];
+    for (int i = 0; i < 6; ++i) xf[i] = (float)xi[i];
+    se3_exp<float>(xf, qf, tf);
+    for (int i = 0; i < 4; ++i) q[i] = qf[i];
+    for (int i = 0; i < 3; ++i) t[i] = tf[i];
+}
+extern "C" void host_solve6_f(const double *Au21, const double *b, double inv_n, double lam1, double *x)
+{
+    float xf[6];
+    solve6<float>(Au21, b, inv_n, (float)lam1, xf);
+    for (int i = 0; i < 6; ++i) x[i] = xf[i];
+}
+extern "C" int host_lm_real_bytes() { return (int)sizeof(lmreal); }
 
 // The level loop of k_track (track.cu) on one host thread: evaluate, lm_step, repeat until the level is done.
 extern "C" int host_track_level(const float *pts4, int n, const float *dt, int w, int h, float fx, float fy, float cx, float cy,
                                 float *R9_inout, float *t3_inout, const revo_opt_config *oc, int lvl, float *err_out, int *n_evals_out,
-                                double *last_rec32)
+                                double *last_rec32, int speculate)
 {
+    // the shared-memory state of k_track: LM state, the three pose slots, two record buffers, the speculation inputs
+    // (speculate != 0: the reject-successor of every try is computed ahead like lane 0 of warp 1 does on the device, so the
+    // pick-up path of lm_step runs; the result must not depend on it)
     LMState lm;
     std::memset(&lm, 0, sizeof(lm));
-    float R[9], t[3];
-    std::memcpy(R, R9_inout, sizeof(R));
-    std::memcpy(t, t3_inout, sizeof(t));
-    quat_from_R(R, lm.q);
-    for (int i = 0; i < 3; ++i) lm.t[i] = t[i];
+    static Trial trial[3];
+    static double rec[2][32];
+    SpecIn specin[2];
+    std::memset(trial, 0, sizeof(trial));
+    std::memset(specin, 0, sizeof(specin));
+    std::memcpy(trial[0].R, R9_inout, sizeof(float) * 9);
+    std::memcpy(trial[0].t, t3_inout, sizeof(float) * 3);
+    quat_from_R<lmreal>(trial[0].R, lm.q[0]);
+    for (int i = 0; i < 3; ++i) lm.t[0][i] = (lmreal)trial[0].t[i];
     lm.last_residual = INFINITY;
     bool first = true;
-    int evals = 0;
+    int evals = 0, cur = 0;
+    unsigned seq = 0;
     while (true) {
-        host_eval_record(pts4, n, dt, w, h, fx, fy, cx, cy, R, t, oc->edge_distance_lvl[lvl], oc->use_edge_filter, oc->huber_edge, last_rec32);
+        const int wb = lm.acc ^ 1;
+        host_eval_record(pts4, n, dt, w, h, fx, fy, cx, cy, trial[cur].R, trial[cur].t, oc->edge_distance_lvl[lvl], oc->use_edge_filter,
+                         oc->huber_edge, rec[wb]);
+        std::memcpy(last_rec32, rec[wb], sizeof(double) * 32);
+        if (speculate && !first) {
+            const SpecIn s = specin[seq & 1];
+            if (s.active) lm_propose(rec[s.acc], lm.q[s.pacc], lm.t[s.pacc], s.lambda, trial[cur == 2 ? 0 : cur + 1]);
+        }
+        ++seq;
         ++evals;
         revo_trace_entry te;
         bool traced;
-        const bool done = lm_step(lm, last_rec32, *oc, lvl, first, R, t, &te, &traced);
+        LMOrder order;
+        const bool done = lm_step(lm, trial, cur, rec, speculate && !first, specin[(seq - 1) & 1], specin[seq & 1], order, *oc, lvl, first,
+                                  &te, &traced);
+        if (order.propose) lm_propose(rec[order.acc], lm.q[order.pacc], lm.t[order.pacc], order.lambda, trial[order.slot]);
         first = false;
         if (done || evals > 10000) break;
     }
+    float R[9], t[3];
+    std::memcpy(R, trial[cur].R, sizeof(R));
+    std::memcpy(t, trial[cur].t, sizeof(t));
     std::memcpy(R9_inout, R, sizeof(R));
     std::memcpy(t3_inout, t, sizeof(t));
     *err_out = lm.last_residual;
@@ -135,22 +178,41 @@ extern "C" int host_track_level(const float *pts4, int n, const float *dt, int w
 def _grab(text, start_pat):
     m = re.search(start_pat, text, re.M)
     assert m, start_pat
+    start = m.start()
+    prev = text.rfind("\n", 0, start - 1) + 1          # a `template <...>` line directly above belongs to the function
+    if text[prev:start].startswith("template <"):
+        start = prev
     j = text.index("\n}", m.start())
-    return text[m.start():text.index("\n", j + 1) + 1]
+    return text[start:text.index("\n", j + 1) + 1]
 
 
 def device_parts():
     """The function / struct texts taken from the CUDA sources, in dependency order."""
     common = open(os.path.join(ROOT, "revo_b200", "csrc", "track_common.cuh")).read()
     pyr = open(os.path.join(ROOT, "revo_b200", "csrc", "pyramid.cu")).read()
+    LM_SPECIALISATIONS = _lm_spec(common)
+    i = common.index("#ifdef REVO_LM_DOUBLE")
+    LM_TYPEDEF = common[i:common.index("#endif", i) + len("#endif")] + "\n"
     return [_grab(pyr, r"^__device__ __forceinline__ float4 opt_texel"), _grab(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
             _grab(pyr, r"^__device__ __forceinline__ void store_quad"), _grab(common, r"^__device__ __forceinline__ void unpack_grad"),
             _grab(common, r"^struct ProjB \{"), _grab(common, r"^struct LevelConst \{"),
             _grab(common, r"^__device__ __forceinline__ ProjB project_b"), _grab(common, r"^__device__ __forceinline__ void finish_point_b"),
-            _grab(common, r"^struct LMState \{"), _grab(common, r"^__device__ __forceinline__ void quat_to_R"),
+            LM_TYPEDEF,
+            _grab(common, r"^struct Trial \{"), _grab(common, r"^struct LMState \{"), _grab(common, r"^struct SpecIn \{"), _grab(common, r"^struct LMOrder \{"),
+            LM_SPECIALISATIONS,
+            _grab(common, r"^__device__ __forceinline__ void quat_to_R"),
             _grab(common, r"^__device__ inline void quat_from_R"), _grab(common, r"^__device__ __forceinline__ void se3_exp"),
-            _grab(common, r"^__device__ __forceinline__ void se3_mul"), _grab(common, r"^__device__ __forceinline__ void solve6"),
+            _grab(common, r"^__device__ __forceinline__ void se3_mul"), _grab(common, r"^__device__ __forceinline__ void solve6\("),
+            _grab(common, r"^__device__ __forceinline__ void lm_pose_from_inc"), _grab(common, r"^__device__ __forceinline__ void lm_propose\("),
+            _grab(common, r"^__device__ __forceinline__ float lm_reject_lambda"),
             _grab(common, r"^__device__ __forceinline__ bool lm_step"), _grab(common, r"^__device__ __forceinline__ float cost_point")]
+
+
+# lm_rcp / lm_fma: one-line template specialisations in the device source (taken as a block)
+def _lm_spec(common):
+    i = common.index("template <typename T> __device__ __forceinline__ T lm_rcp(T x);")
+    j = common.index("\n\n", i)
+    return common[i:j] + "\n"
 
 
 @pytest.fixture(scope="module")
@@ -215,8 +277,8 @@ def test_device_point_math_matches_oracle_record(host_lib, orc64, seed):
                 _rec_close(g, o)
 
 
-@pytest.mark.parametrize("seed,n_tries", [(1, 8), (22, 5)])
-def test_device_lm_loop_matches_oracle_after_same_iterations(host_lib, orc64, seed, n_tries):
+@pytest.mark.parametrize("seed,n_tries,speculate", [(1, 8, 0), (1, 8, 1), (22, 5, 1)])
+def test_device_lm_loop_matches_oracle_after_same_iterations(host_lib, orc64, seed, n_tries, speculate):
     """The level loop of k_track on one host thread -- per-point arithmetic + ``lm_step`` (6x6 LDL^T, SE3 exp / product,
     accept / reject, lambda schedule) from the device source text -- against the oracle's ``Optimizer::trackFrames`` after
     the SAME number of LM tries: <= 1e-4 rad / 1e-4 m (the tolerance of the path), same evaluation count."""
@@ -250,7 +312,7 @@ def test_device_lm_loop_matches_oracle_after_same_iterations(host_lib, orc64, se
         host_lib.host_track_level(pts4.ctypes.data_as(C.c_void_p), C.c_int(len(pts4)), dt.ctypes.data_as(C.c_void_p), C.c_int(cam.w),
                                   C.c_int(cam.h), f(cam.fx), f(cam.fy), f(cam.cx), f(cam.cy), R9.ctypes.data_as(C.c_void_p),
                                   t3.ctypes.data_as(C.c_void_p), C.byref(oc), C.c_int(lvl), C.byref(err), C.byref(n_evals),
-                                  rec.ctypes.data_as(C.c_void_p))
+                                  rec.ctypes.data_as(C.c_void_p), C.c_int(speculate))
         R, T = R9.reshape(3, 3).T.copy(), t3.copy()
         assert n_evals.value == r["n_evals"], (lvl, n_evals.value, r["n_evals"])
         assert rot_angle(R, Ro) <= 1e-4 and np.linalg.norm(T - To) <= 1e-4, (lvl, rot_angle(R, Ro), np.linalg.norm(T - To))
@@ -323,6 +385,7 @@ def test_device_se3_and_solver_helpers_match_oracle(host_lib, orc64):
             assert np.allclose(qb, tum_io.quaternion_from_R(Ro.astype(np.float32)), atol=1e-12)      # Eigen's Shepperd branches
     # normal equations: a damped sum of outer products, like the tracker's
     host_lib.host_solve6.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    host_lib.host_solve6_f.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
     for lam in (0.0, 0.2, 6.4):
         J = rng.normal(0, 1, (500, 6)) * np.array([1, 1, 1, 3, 3, 3])
         w = rng.uniform(0.1, 1, 500)
@@ -335,3 +398,16 @@ def test_device_se3_and_solver_helpers_match_oracle(host_lib, orc64):
         Ad[np.diag_indices(6)] *= 1.0 + lam
         assert np.allclose(x, np.linalg.solve(Ad, b / 500), rtol=1e-10, atol=1e-12)
         assert np.allclose(x, orc64.ldlt_solve6(Ad, b / 500), rtol=1e-9, atol=1e-12)
+        # the float instantiation (what the library runs; the reference solves in float as well): float accuracy x conditioning
+        xf = np.zeros(6)
+        host_lib.host_solve6_f(dp(Au), dp(np.ascontiguousarray(b)), 1.0 / 500, 1.0 + lam, dp(xf))
+        assert np.abs(xf - x).max() <= 2e-5 * np.abs(x).max(), (lam, xf, x)
+    # se3_exp in float: power series in theta^2, no cancellation -> float accuracy at every angle
+    for scale in (1e-7, 1e-4, 1e-3, 0.05, 0.4, 1.5):
+        xi = np.ascontiguousarray(np.r_[rng.normal(0, 0.3, 3), rng.normal(0, 1, 3) * scale]).astype(np.float32).astype(np.float64)
+        qf, tf = np.zeros(4), np.zeros(3)
+        host_lib.host_se3_exp_f(dp(xi), dp(qf), dp(tf))
+        qo, to = orc64.se3_exp(xi)
+        if scale < 1e-5:
+            to = orc64.quat_to_R(qo) @ xi[:3]
+        assert np.abs(qf - qo).max() <= 2e-7 and np.abs(tf - to).max() <= 2e-7 * max(1.0, np.abs(to).max()), (scale, qf - qo, tf - to)

@@ -18,17 +18,10 @@ from conftest import rot_angle, synth_pair
 pytestmark = pytest.mark.gpu
 
 
-_ENGINES = ["cluster", "lean"] + (["pingpong", "queue"] if os.environ.get("REVO_TEST_ALL_ENGINES") == "1" else [])
-
-
-@pytest.fixture(params=_ENGINES, autouse=True)
-def engine(request, ctx):
-    """Every test of this file runs on the tracking engines of the library (cluster per pair: track.cu, its lean-loop
-    variant: track_lean.cu; REVO_TEST_ALL_ENGINES=1 adds the two engines that are slower at every measured batch size:
-    warp-specialised clusters working on two pairs, track_pp.cu, and the task queue, track_queue.cu)."""
-    ctx.set_track_engine({"cluster": 1, "queue": 2, "pingpong": 3, "lean": 4}[request.param], 0)
-    yield request.param
-    ctx.set_track_engine(0, 0)
+@pytest.fixture(autouse=True)
+def engine(ctx):
+    """The library has one tracking engine (one thread-block cluster per pair, track.cu)."""
+    return "cluster"
 
 
 def _settings(cam, n_levels):
@@ -289,8 +282,6 @@ def test_config3_1280x960_five_levels(ctx, orc32, orc64, engine):
     from oracle import oracle as O
     from revo_b200 import api
 
-    if engine == "queue":
-        pytest.skip("same arithmetic as the other engines; keeps the suite short")
     p = synth_pair(3, 1280, 960)
     st = _settings(p["cam"], 5)
     gk = api.ImgPyramidRGBD(ctx, st, None, *p["key"])
@@ -330,8 +321,6 @@ def test_revo_main_loop_on_gpu(ctx, orc32, engine):
     from revo_b200 import api, synth
     from revo_b200.system import REVO
 
-    if engine != "cluster":
-        pytest.skip("host logic: one engine is enough")
     w, h, n = 320, 240, 7
     s = synth.make_stream(77, n, w, h, max_trans=0.03, max_rot_deg=1.5)
     cam = synth.intrinsics(w, h)
@@ -364,8 +353,6 @@ def test_multi_stream_main_loop_on_gpu(ctx, engine):
     from revo_b200 import api, synth
     from revo_b200.system import REVO, MultiStreamREVO, cuda_track_batch
 
-    if engine != "cluster":
-        pytest.skip("host logic: one engine is enough")
     w, h, n, B = 320, 240, 7, 3
     cam = synth.intrinsics(w, h)
     st = _settings(cam, 3)
