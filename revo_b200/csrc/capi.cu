@@ -568,13 +568,13 @@ static void wait_for_build(revo_ctx *ctx, const revo_pyr *p)
     if (p && p->slab && p->slab->ready && p->slab->stream != ctx->stream) cudaStreamWaitEvent(ctx->stream, p->slab->ready, 0);
 }
 
-// One stream-ordered allocation for the keyframe structures (dt 4 B/px + quad structure 32 B/px, all levels) of
+// One stream-ordered allocation for the keyframe structures (dt 4 B/px + tiled lookup texels 8 B/px, all levels) of
 // every pyramid in `ps` that does not have them yet.
 static int alloc_keyframe_mem(revo_ctx *ctx, revo_pyr *const *ps, int n)
 {
     auto bytes_of = [](const revo_pyr *p) {
         size_t b = 0;
-        for (int l = 0; l < p->n_levels; ++l) b += align_up((size_t)p->lv[l].w * p->lv[l].h * 36, 256);
+        for (int l = 0; l < p->n_levels; ++l) b += align_up(opt_bytes(p->lv[l].w, p->lv[l].h) + (size_t)p->lv[l].w * p->lv[l].h * 4, 256);
         return b;
     };
     size_t total = 0;
@@ -593,10 +593,10 @@ static int alloc_keyframe_mem(revo_ctx *ctx, revo_pyr *const *ps, int n)
         if (p->kf_slab) continue;
         p->kf_slab = ks;
         for (int l = 0; l < p->n_levels; ++l) {
-            const size_t px = (size_t)p->lv[l].w * p->lv[l].h;
-            p->lv[l].opt = (uint4 *)mem;
-            p->lv[l].dt = (float *)(mem + px * 32);
-            mem += align_up(px * 36, 256);
+            const size_t px = (size_t)p->lv[l].w * p->lv[l].h, ob = opt_bytes(p->lv[l].w, p->lv[l].h);
+            p->lv[l].opt = (uint2 *)mem;
+            p->lv[l].dt = (float *)(mem + ob);
+            mem += align_up(ob + px * 4, 256);
         }
     }
     return REVO_OK;

@@ -26,13 +26,26 @@ struct ImgLevel {
     int *labels;          // scratch h*w int32: union-find labels (Canny) / column distances (EDT)
     uint8_t *flags;       // scratch w0*h0 bytes per frame: integer patch counters of the histogram (K5)
     float *dt;            // dtPyr[l]         h*w   (keyframes, else nullptr)
-    uint4 *opt;           // optimizationStructure[l] in the device QUAD layout (see k_opt_struct), 2 x uint4 per pixel (keyframes)
+    uint2 *opt;           // optimizationStructure[l] in the device layout: 8-byte texels in 4x4 tiles (see opt_texel_index; keyframes)
     int w, h;
     int pts_cap;
     int patch;            // distPatchSizes[l]
     int hist_w, hist_h;
     float fx, fy, cx, cy; // Camera at this level (camerapyr.h:98-103)
 };
+
+// Device layout of the lookup structure (optimizationStructure of the reference: one float4 {gx, gy, dt, .} per pixel,
+// imgpyramidrgbd.cpp:255-276): one 8-byte TEXEL per pixel -- dt as float32 (the residual is exact) and the gradient as two
+// snorm16 (step 1/32764) -- stored in 4x4-pixel TILES of 128 bytes = one L2 line, tiles row-major.  The tracker reads the
+// 2x2 texels around a projected point; with tiles a line serves a 4x4 neighbourhood in every direction, which halves the
+// number of L2 lines a frame pair keeps busy against a row-major 32-byte record per pixel (profiles/r1_lookup_layout_study.txt)
+// and is what lets twice as many pairs be in flight.  Index of texel (x, y) in uint2 units; tw = tiles per row.
+__host__ __device__ inline unsigned opt_texel_index(int x, int y, int tw)
+{
+    return (((unsigned)(y >> 2) * (unsigned)tw + (unsigned)(x >> 2)) << 4) + ((unsigned)(y & 3) << 2) + (unsigned)(x & 3);
+}
+inline int opt_tiles_per_row(int w) { return (w + 3) >> 2; }
+inline size_t opt_bytes(int w, int h) { return (size_t)opt_tiles_per_row(w) * (size_t)((h + 3) >> 2) * 128; }
 
 // Point-list tile: one warp <-> one 8x4 pixel tile (row-major inside, tiles row-major).
 constexpr int kTileW = 8;
@@ -149,7 +162,7 @@ struct QualityArgs {
 int launch_quality(revo_ctx *ctx, const QualityArgs &args, const float *d_depth, const uint8_t *d_edges, float dmin, float dmax,
                    unsigned *d_mbits, int *d_counters);
 int launch_opt_struct_f4(revo_ctx *ctx, const float *d_dt, int w, int h, float4 *d_out);
-int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uint4 *d_out);
+int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uint2 *d_out);
 // reference-order (column-major scan) 3-D edge list into d_out (capacity w*h float4); *d_n receives the count
 int launch_edges3d_reference_order(revo_ctx *ctx, const ImgLevel *d_desc_one, int w, int h, float dmin, float dmax,
                                    float4 *d_out, int *d_n, int *d_col_off);
@@ -158,7 +171,7 @@ int launch_edges3d_reference_order(revo_ctx *ctx, const ImgLevel *d_desc_one, in
 struct LevelIn {
     const float4 *pts;
     const int *n_pts;
-    const uint4 *opt;    // quad layout, 32 B per pixel: dt of (x,y),(x+1,y),(x,y+1),(x+1,y+1) | snorm16 gx|gy of the same four
+    const uint2 *opt;    // tiled texel layout (opt_texel_index): {dt f32 | snorm16 gx, gy} per pixel
     float fx, fy, cx, cy;
     int w, h;
 };

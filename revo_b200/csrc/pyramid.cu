@@ -615,30 +615,22 @@ __device__ __forceinline__ uint32_t pack_grad(float gx, float gy)
     return ((uint32_t)qx & 0xffffu) | ((uint32_t)qy << 16);
 }
 
-// K8 (device layout): one 32-byte QUAD record per pixel (x,y) holding everything the bilinear fetch of the tracker
-// needs for a point that projects into [x,x+1) x [y,y+1): {dt(x,y), dt(x+1,y), dt(x,y+1), dt(x+1,y+1)} as float32 and
-// the snorm16 (gx,gy) of the same four texels.  A residual evaluation then costs ONE 256-bit gather per edge point
-// instead of four 16-byte texel fetches; dt stays float32, only the Jacobian direction is quantised (1.5e-5 absolute).
-// The reference's float4 array is produced on demand for the accessor (k_opt_struct_f4).
-__device__ __forceinline__ void store_quad(uint4 *__restrict__ out, size_t i, const float4 a, const float4 b, const float4 c, const float4 d)
+// K8 (device layout, internal.h: opt_texel_index): one 8-byte texel {dt float32 | snorm16 gx, gy} per pixel in 4x4 tiles.
+// dt stays float32, only the Jacobian direction is quantised (1.5e-5 absolute).  The reference's float4 array is produced on
+// demand for the accessor (k_opt_struct_f4).
+__device__ __forceinline__ uint2 pack_texel(const float4 t)
 {
-    out[2 * i] = make_uint4(__float_as_uint(a.z), __float_as_uint(b.z), __float_as_uint(c.z), __float_as_uint(d.z));
-    out[2 * i + 1] = make_uint4(pack_grad(a.x, a.y), pack_grad(b.x, b.y), pack_grad(c.x, c.y), pack_grad(d.x, d.y));
+    return make_uint2(__float_as_uint(t.z), pack_grad(t.x, t.y));
 }
 
 __global__ void __launch_bounds__(256) k_opt_struct(const ImgLevel *__restrict__ desc, int w, int h)
 {
+    // one thread per pixel; a warp covers 32 consecutive pixels of a row = 8 tiles x one 32-byte tile row: full sectors
     const int f = blockIdx.z;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t n = (size_t)w * h;
-    if (i >= n) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
     const float *__restrict__ dt = desc[f].dt;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 a = opt_texel(dt, i, w, h);
-    const float4 b = (i + 1 < n) ? opt_texel(dt, i + 1, w, h) : z;
-    const float4 c = (i + w < n) ? opt_texel(dt, i + w, w, h) : z;
-    const float4 d = (i + w + 1 < n) ? opt_texel(dt, i + w + 1, w, h) : z;
-    store_quad(desc[f].opt, i, a, b, c, d);
+    desc[f].opt[opt_texel_index(x, y, (w + 3) >> 2)] = pack_texel(opt_texel(dt, (size_t)y * w + x, w, h));
 }
 
 // the reference layout, for returnOptimizationStructure(): out[i] = {gx, gy, dt, 0}
@@ -649,18 +641,12 @@ __global__ void __launch_bounds__(256) k_opt_struct_f4(const float *__restrict__
     out[i] = opt_texel(dt, i, w, h);
 }
 
-// test hook: caller-provided float4 structure -> device quad layout
-__global__ void __launch_bounds__(256) k_opt_pack_from_f4(const float4 *__restrict__ in, int w, int h, uint4 *__restrict__ out)
+// test hook: caller-provided float4 structure -> device layout
+__global__ void __launch_bounds__(256) k_opt_pack_from_f4(const float4 *__restrict__ in, int w, int h, uint2 *__restrict__ out)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t n = (size_t)w * h;
-    if (i >= n) return;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 a = in[i];
-    const float4 b = (i + 1 < n) ? in[i + 1] : z;
-    const float4 c = (i + w < n) ? in[i + w] : z;
-    const float4 d = (i + w + 1 < n) ? in[i + w + 1] : z;
-    store_quad(out, i, a, b, c, d);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    out[opt_texel_index(x, y, (w + 3) >> 2)] = pack_texel(in[(size_t)y * w + x]);
 }
 
 int launch_opt_struct_f4(revo_ctx *ctx, const float *d_dt, int w, int h, float4 *d_out)
@@ -670,9 +656,9 @@ int launch_opt_struct_f4(revo_ctx *ctx, const float *d_dt, int w, int h, float4 
     return REVO_OK;
 }
 
-int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uint4 *d_out)
+int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uint2 *d_out)
 {
-    k_opt_pack_from_f4<<<cdiv(w * h, 256), 256, 0, ctx->stream>>>(d_in, w, h, d_out);
+    k_opt_pack_from_f4<<<dim3(cdiv(w, 256), h), 256, 0, ctx->stream>>>(d_in, w, h, d_out);
     LAUNCH_CHECK(ctx);
     return REVO_OK;
 }
@@ -756,7 +742,7 @@ int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h)
         LAUNCH_CHECK(ctx);
     }
     {
-        dim3 grid(cdiv(w * h, 256), 1, n);
+        dim3 grid(cdiv(w, 256), h, n);
         k_opt_struct<<<grid, 256, 0, ctx->stream>>>(d_desc, w, h);
         LAUNCH_CHECK(ctx);
     }

@@ -10,7 +10,7 @@
 //
 // Design (B200): a frame pair is owned by one thread-block CLUSTER (1..16 CTAs); clusters pull pairs from a global work
 // counter (persistent kernel).  PASS A and PASS B are fused: every evaluation at a pose warps each 3-D edge point, fetches
-// the 32-byte quad record of its pixel (one 256-bit gather, L1::no_allocate), forms the residual, Huber weight and 1x6
+// the 2x2 texels around its projection from the tiled lookup structure (four 64-bit gathers), forms the residual, Huber weight and 1x6
 // Jacobian and accumulates the 21+6 normal-equation terms + statistics in registers -- the 7 SoA buffers of the reference
 // never exist.  A thread keeps its points of the level in a private column of a shared-memory cache and visits only points
 // that exist; two points are in flight per thread (software pipeline) to cover the point -> record latency.  The 32-value
@@ -70,6 +70,8 @@ __device__ __forceinline__ void sts3(uint32_t addr, float x, float y, float z)
                  :: "r"(addr), "f"(x), "f"(y), "f"(z), "n"(kThreads * 4), "n"(kThreads * 8) : "memory");
 }
 
+__device__ __forceinline__ int opt_tiles_per_row_dev(int w) { return (w + 3) >> 2; }
+
 // keeps a per-level constant in a register (the compiler otherwise re-derives it from the constant bank for every point)
 __device__ __forceinline__ float pin(float x)
 {
@@ -81,7 +83,7 @@ __device__ __forceinline__ float pin(float x)
 // Dynamic shared memory: the thread-private cache of the level's 3-D points, float[pcap][3][kThreads]: thread t keeps the
 // first `pcap` of ITS points of the current level there for all evaluations of the level, so an evaluation starts with
 // shared-memory reads instead of an L2 round trip and re-reads no list bytes from L2 / HBM.
-template <int kThreads, int kMinBlocks, bool kNoL1>
+template <int kThreads, int kMinBlocks, int kHint>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, revo_track_result *__restrict__ results,
         double *__restrict__ records, revo_trace_entry *__restrict__ trace, int *__restrict__ trace_counts,
@@ -102,6 +104,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
     __shared__ __align__(16) double cta_part[2][16][32];   // [parity][source rank]: partials pushed by the CTAs of the cluster
     __shared__ double total[2][32];                        // split mode: CTA 0 publishes the cross-GPU total here
     __shared__ double rec[2][32];                          // [lm.acc]: record of the accepted pose, [lm.acc ^ 1]: the latest one
+    __shared__ lmreal recs[2][32];                         // the same records divided by their good count, as the LM step reads them
     __shared__ __align__(8) uint64_t xbar[2];              // transaction barriers of the partial exchange (one per parity)
     __shared__ Ctrl ctrl;
     __shared__ LMState lm;
@@ -114,6 +117,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
     const int n_members = world * C;
     const int member = (world > 1 ? prm.split_rank : 0) * C + crank;
     const bool speculate = prm.speculate != 0 && kWarps >= 2;
+    const unsigned long long policy = kHint == 2 ? l2_policy_evict_last() : 0ull;
     unsigned seq = 0;   // evaluation counter of this cluster (drives the double buffers)
 
     if (tid == 0) {
@@ -126,7 +130,14 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
     // The successor of the try being evaluated in case it is rejected (lane 0 of warp 1, while warp 0 exchanges the record).
     auto speculate_successor = [&](int cur) {
         const SpecIn s = specin[seq & 1];
-        if (s.active) lm_propose(rec[s.acc], lm.q[s.pacc], lm.t[s.pacc], s.lambda, trial[cur == 2 ? 0 : cur + 1]);
+        if (s.active) lm_propose(recs[s.acc], lm.q[s.pacc], lm.t[s.pacc], s.lambda, trial[cur == 2 ? 0 : cur + 1]);
+    };
+
+    // warp 0: lane l publishes value l of the record, in double and scaled for the LM step (n = value kRecGood)
+    auto publish = [&](double tot, int wb) {
+        rec[wb][lane] = tot;
+        const int nlo = __shfl_sync(kFull, __double2loint(tot), kRecGood), nhi = __shfl_sync(kFull, __double2hiint(tot), kRecGood);
+        recs[wb][lane] = lm_scaled(tot, __hiloint2double(nhi, nlo));
     };
 
     // ---- reduction of a per-thread accumulator to rec[wb] (identical in every CTA of the cluster / every rank).  On return
@@ -146,18 +157,16 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 double s = 0;
 #pragma unroll
                 for (int w = 0; w < kWarps; ++w) s += (double)warp_part[w][lane];
-                double *dst = rec[wb];
-                if (C == 1) {
-                    dst[lane] = s;
-                } else {
+                double tot = s;
+                if (C > 1) {
                     if (lane == 0) mbar_expect_tx(&xbar[par], (uint32_t)C * 256u);
                     const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
                     for (int r = 0; r < C; ++r) st_async_b64(&cta_part[par][crank][lane], (unsigned)r, bits, &xbar[par]);
                     mbar_wait(&xbar[par], (seq >> 1) & 1u);
-                    double tot = 0;
+                    tot = 0;
                     for (int r = 0; r < C; ++r) tot += cta_part[par][r][lane];   // rank order: deterministic
-                    dst[lane] = tot;
                 }
+                publish(tot, wb);
             } else if (spec_now && tid == 32) {
                 speculate_successor(cur);
             }
@@ -202,7 +211,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 speculate_successor(cur);      // overlaps the NVLink round trip
             }
             cluster.sync();
-            if (tid < 32) rec[wb][tid] = *cluster.map_shared_rank(&total[par][tid], 0);
+            if (tid < 32) publish(*cluster.map_shared_rank(&total[par][tid], 0), wb);
         }
         seq++;
         if (wid == 0) __syncwarp();
@@ -302,13 +311,13 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                 const float4 *__restrict__ pts = Lin.pts;
                 LevelConst L;
                 L.fx = Lin.fx; L.fy = Lin.fy; L.cx = Lin.cx; L.cy = Lin.cy;
-                L.umax = pin((float)(Lin.w - 2)); L.vmax = pin((float)(Lin.h - 2)); L.w = Lin.w; L.opt = Lin.opt;
+                L.umax = pin((float)(Lin.w - 2)); L.vmax = pin((float)(Lin.h - 2)); L.tw16 = (unsigned)opt_tiles_per_row_dev(Lin.w) << 4; L.opt = Lin.opt;
                 const float ed_eff = pin(use_filter ? oc.edge_distance_lvl[lvl] : INFINITY);
                 const float huber = pin(oc.huber_edge);
                 const float kqfx = pin(Lin.fx * (1.0f / 32764.0f)), kqfy = pin(Lin.fy * (1.0f / 32764.0f));
                 // this thread's points of the level -> its private slots of the shared-memory cache
                 for (int k = 0; k < my_cached; ++k) {
-                    const float4 p = __ldg(pts + first_idx + (size_t)k * stride);
+                    const float4 p = ldg_point<kHint>(pts + first_idx + (size_t)k * stride);
                     sts3<kThreads>(s_base + (uint32_t)k * kPtStride, p.x, p.y, p.z);
                 }
                 bool first = true;
@@ -332,29 +341,30 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                         if (k0 >= k1) return;
                         uint32_t sp = s_base + (uint32_t)k0 * kPtStride;
                         const float4 *gp = pts + first_idx + (size_t)k0 * stride;
-                        auto arm = [&](ProjB &Q, uint4 &q0, uint4 &q1) {
+                        auto arm = [&](ProjB &Q, uint2 (&q)[4]) {
                             float x, y, z;
                             if constexpr (kS) {
                                 lds3<kThreads>(sp, x, y, z);
                                 sp += kPtStride;
                             } else {
-                                const float4 p = __ldg(gp);
+                                const float4 p = ldg_point<kHint>(gp);
                                 gp += stride;
                                 x = p.x; y = p.y; z = p.z;
                             }
                             Q = project_b(x, y, z, L, R, t);
-                            ldg_quad<kNoL1>(Q.bp, q0, q1);
+                            q[0] = ldg_texel<kHint>(L.opt + Q.i00, policy); q[1] = ldg_texel<kHint>(L.opt + Q.i10, policy);
+                            q[2] = ldg_texel<kHint>(L.opt + Q.i01, policy); q[3] = ldg_texel<kHint>(L.opt + Q.i11, policy);
                         };
                         ProjB A, B;
-                        uint4 a0, a1, b0, b1;
-                        arm(A, a0, a1);
+                        uint2 qa[4], qb[4];
+                        arm(A, qa);
                         int left = k1 - k0 - 1;   // points of the segment not yet armed
                         while (true) {
-                            if (left > 0) arm(B, b0, b1);
-                            finish_point_b(A, a0, a1, kqfx, kqfy, ed_eff, huber, acc);
+                            if (left > 0) arm(B, qb);
+                            finish_point_b(A, qa[0], qa[1], qa[2], qa[3], kqfx, kqfy, ed_eff, huber, acc);
                             if (left <= 0) break;
-                            if (left > 1) arm(A, a0, a1);
-                            finish_point_b(B, b0, b1, kqfx, kqfy, ed_eff, huber, acc);
+                            if (left > 1) arm(A, qa);
+                            finish_point_b(B, qb[0], qb[1], qb[2], qb[3], kqfx, kqfy, ed_eff, huber, acc);
                             if (left <= 1) break;
                             left -= 2;
                         }
@@ -384,7 +394,7 @@ k_track(const PairDesc *__restrict__ pairs, int n_pairs, const TrackParams prm, 
                         const bool done = lm_step(lm, trial, next, rec, spec_now, specin[(seq - 1) & 1], specin[seq & 1], order, oc, lvl,
                                                   first, &te, &traced);
                         // a fresh proposal is needed (first evaluation, accepted try, or no speculation)
-                        if (order.propose) lm_propose(rec[order.acc], lm.q[order.pacc], lm.t[order.pacc], order.lambda, trial[order.slot]);
+                        if (order.propose) lm_propose(recs[order.acc], lm.q[order.pacc], lm.t[order.pacc], order.lambda, trial[order.slot]);
                         if (traced) {
                             if (trace && crank == 0 && ntrace < prm.trace_cap) trace[(size_t)pair * prm.trace_cap + ntrace] = te;
                             ntrace++;
@@ -464,16 +474,17 @@ int launch_stage_in(revo_ctx *ctx, const void *src_mapped_host, void *dst, size_
 }
 
 // ---- launcher -------------------------------------------------------------------
-template <int kThreads, int kMinBlocks, bool kNoL1>
+template <int kThreads, int kMinBlocks, int kHint>
 static int launch_track_t(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const TrackParams &prm, int ctas_per_pair,
                           revo_track_result *d_results, double *d_records, revo_trace_entry *d_trace, int *d_trace_counts,
                           int *d_work_counter)
 {
-    auto kern = k_track<kThreads, kMinBlocks, kNoL1>;
+    auto kern = k_track<kThreads, kMinBlocks, kHint>;
     if (ctas_per_pair > 8) REVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    // points per thread cached in shared memory: ~half of the SM's shared memory over the resident CTAs (the rest stays L1)
+    // points per thread cached in shared memory: 144 KB of the SM's 228 KB over the resident CTAs (24 points per thread at
+    // 4 x 128 threads: a VGA level 0 has ~20-25; the gathers bypass L1, so little L1 is needed)
     const int env_pcap = getenv("REVO_TRACK_PCAP") ? atoi(getenv("REVO_TRACK_PCAP")) : -1;
-    int pcap = env_pcap >= 0 ? env_pcap : (int)((112 * 1024 / kMinBlocks) / (12 * kThreads));
+    int pcap = env_pcap >= 0 ? env_pcap : (int)((144 * 1024 / kMinBlocks) / (12 * kThreads));
     if (pcap > 64) pcap = 64;
     const size_t dyn = (size_t)pcap * kThreads * 12;
     REVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -517,14 +528,18 @@ int launch_track(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, const Trac
     const int slots256 = 2 * ctx->prop.multiProcessorCount;
     int C = ctx->track_ctas_per_pair > 0 ? ctx->track_ctas_per_pair : 8;
     const int T = ctx->track_threads > 0 ? ctx->track_threads : ((long long)n_pairs * C > slots256 ? 128 : 256);
-    // A/B switch for profiling only (REVO_TRACK_HINT=0: plain gather; default: L1::no_allocate)
-    const bool plain = getenv("REVO_TRACK_HINT") && atoi(getenv("REVO_TRACK_HINT")) == 0;
+    // A/B switch for profiling only: REVO_TRACK_HINT = 0 plain gathers, 1 L1::no_allocate, 2 (default) L2 eviction priorities
+    const int hint = getenv("REVO_TRACK_HINT") ? atoi(getenv("REVO_TRACK_HINT")) : 2;
 #define REVO_TRACK_ARGS ctx, d_pairs, n_pairs, prm, C, d_results, d_records, d_trace, d_trace_counts, d_work_counter
     switch (T) {
-        case 128: return plain ? launch_track_t<128, 4, false>(REVO_TRACK_ARGS) : launch_track_t<128, 4, true>(REVO_TRACK_ARGS);
-        case 512: return launch_track_t<512, 1, true>(REVO_TRACK_ARGS);
-        case 1024: return launch_track_t<1024, 1, true>(REVO_TRACK_ARGS);
-        default: return plain ? launch_track_t<256, 2, false>(REVO_TRACK_ARGS) : launch_track_t<256, 2, true>(REVO_TRACK_ARGS);
+        case 128:
+            return hint == 0 ? launch_track_t<128, 4, 0>(REVO_TRACK_ARGS)
+                 : hint == 2 ? launch_track_t<128, 4, 2>(REVO_TRACK_ARGS) : launch_track_t<128, 4, 1>(REVO_TRACK_ARGS);
+        case 512: return launch_track_t<512, 1, 2>(REVO_TRACK_ARGS);
+        case 1024: return launch_track_t<1024, 1, 2>(REVO_TRACK_ARGS);
+        default:
+            return hint == 0 ? launch_track_t<256, 2, 0>(REVO_TRACK_ARGS)
+                 : hint == 2 ? launch_track_t<256, 2, 2>(REVO_TRACK_ARGS) : launch_track_t<256, 2, 1>(REVO_TRACK_ARGS);
     }
 #undef REVO_TRACK_ARGS
 }

@@ -150,7 +150,7 @@ __device__ inline bool rotation_ok(const float *Rf)
 
 // Sophus::SE3::exp (se3.hpp:723-748, so3.hpp:531-564).  The four coefficients sin(t/2)/t, cos(t/2), (1 - cos t)/t^2 and
 // (t - sin t)/t^3 are even functions of t; for the increments of a tracker (t < 0.5 rad, in practice < 0.05) they are
-// evaluated as power series in t^2 (8 terms: truncation < 1e-17 relative) as four independent Horner chains: no sqrt,
+// evaluated as power series in t^2 as four independent Horner chains: no sqrt,
 // sincos or division on the serial critical path of an evaluation, and -- unlike the closed forms evaluated in float, as
 // the reference does -- no cancellation in (1 - cos t) and (t - sin t).  Larger angles take the closed form.
 template <typename T>
@@ -167,25 +167,25 @@ __device__ __forceinline__ void se3_exp(const T *xi, T *q, T *t)
         c1 = (T)2.0 * re * imag;
         c2 = (T)2.0 * imag * imag;
     } else if (s < (T)0.25) {
-        // coefficients: 1/(2^(2k+1) (2k+1)!), 1/(4^k (2k)!), 1/(2k+2)!, 1/(2k+3)!  with alternating sign
-        imag = (T)(1.0 / 42849873690624000.0);
-        re = (T)(1.0 / 1428329123020800.0);
-        c1 = (T)(1.0 / 20922789888000.0);
-        c2 = (T)(1.0 / 355687428096000.0);
-        imag = imag * -s + (T)(1.0 / 51011754393600.0);     re = re * -s + (T)(1.0 / 1961990553600.0);
-        c1 = c1 * -s + (T)(1.0 / 87178291200.0);             c2 = c2 * -s + (T)(1.0 / 1307674368000.0);
-        imag = imag * -s + (T)(1.0 / 81749606400.0);         re = re * -s + (T)(1.0 / 3715891200.0);
-        c1 = c1 * -s + (T)(1.0 / 479001600.0);               c2 = c2 * -s + (T)(1.0 / 6227020800.0);
-        imag = imag * -s + (T)(1.0 / 185794560.0);           re = re * -s + (T)(1.0 / 10321920.0);
-        c1 = c1 * -s + (T)(1.0 / 3628800.0);                 c2 = c2 * -s + (T)(1.0 / 39916800.0);
-        imag = imag * -s + (T)(1.0 / 645120.0);              re = re * -s + (T)(1.0 / 46080.0);
-        c1 = c1 * -s + (T)(1.0 / 40320.0);                   c2 = c2 * -s + (T)(1.0 / 362880.0);
-        imag = imag * -s + (T)(1.0 / 3840.0);                re = re * -s + (T)(1.0 / 384.0);
-        c1 = c1 * -s + (T)(1.0 / 720.0);                     c2 = c2 * -s + (T)(1.0 / 5040.0);
-        imag = imag * -s + (T)(1.0 / 48.0);                  re = re * -s + (T)(1.0 / 8.0);
-        c1 = c1 * -s + (T)(1.0 / 24.0);                      c2 = c2 * -s + (T)(1.0 / 120.0);
-        imag = imag * -s + (T)0.5;                           re = re * -s + (T)1.0;
-        c1 = c1 * -s + (T)0.5;                               c2 = c2 * -s + (T)(1.0 / 6.0);
+        // coefficient k of (-s)^k: 1/(2^(2k+1) (2k+1)!), 1/(4^k (2k)!), 1/(2k+2)!, 1/(2k+3)!.  8 terms leave < 1e-17 (double),
+        // 5 terms < 4e-10 (float: below half an ulp of every coefficient function on this range)
+        constexpr int N = sizeof(T) == 4 ? 5 : 8;
+        constexpr double ci[8] = {0.5, 1.0 / 48.0, 1.0 / 3840.0, 1.0 / 645120.0, 1.0 / 185794560.0, 1.0 / 81749606400.0,
+                                  1.0 / 51011754393600.0, 1.0 / 42849873690624000.0};
+        constexpr double cr[8] = {1.0, 1.0 / 8.0, 1.0 / 384.0, 1.0 / 46080.0, 1.0 / 10321920.0, 1.0 / 3715891200.0,
+                                  1.0 / 1961990553600.0, 1.0 / 1428329123020800.0};
+        constexpr double c1c[8] = {0.5, 1.0 / 24.0, 1.0 / 720.0, 1.0 / 40320.0, 1.0 / 3628800.0, 1.0 / 479001600.0,
+                                   1.0 / 87178291200.0, 1.0 / 20922789888000.0};
+        constexpr double c2c[8] = {1.0 / 6.0, 1.0 / 120.0, 1.0 / 5040.0, 1.0 / 362880.0, 1.0 / 39916800.0, 1.0 / 6227020800.0,
+                                   1.0 / 1307674368000.0, 1.0 / 355687428096000.0};
+        imag = (T)ci[N - 1]; re = (T)cr[N - 1]; c1 = (T)c1c[N - 1]; c2 = (T)c2c[N - 1];
+#pragma unroll
+        for (int k = N - 2; k >= 0; --k) {      // four independent Horner chains
+            imag = imag * -s + (T)ci[k];
+            re = re * -s + (T)cr[k];
+            c1 = c1 * -s + (T)c1c[k];
+            c2 = c2 * -s + (T)c2c[k];
+        }
     } else {
         const double sd = (double)s, theta = sqrt(sd);      // rare (a step of more than 0.5 rad): closed form in double
         double sn, cs;
@@ -231,12 +231,13 @@ __device__ __forceinline__ void se3_mul(const T *qa, const T *ta, const T *qb, c
 
 // Solve (A with diag * lam1) x = b for the symmetric positive (semi-)definite 6x6 normal equations
 // (system/optimizer.cpp:258-262, "A.ldlt().solve(b)"; the reference divides A and b by the number of constraints first,
-// LGSX.h:320-326, which leaves x unchanged -- here they are divided by n as well so that the float range is never an issue).
+// LGSX.h:320-326; lm_scaled below does the same when the record leaves double precision, one value per lane of the warp that
+// reduced it, so that the float range is never an issue and the serial step starts from ready-made floats).
 // LDL^T without pivoting, fully unrolled so that everything stays in registers (the matrix is a damped sum of outer
 // products; Eigen's diagonal pivoting only changes rounding).  Non-positive / non-finite pivots are treated like Eigen's
 // pseudo-inverse of D: that component becomes 0.
 template <typename T>
-__device__ __forceinline__ void solve6(const double *Au /* 21 upper slots */, const double *b, T inv_n, T lam1, T *x)
+__device__ __forceinline__ void solve6(const T *Au /* 21 upper slots of A / n */, const T *b /* (sum w r v) / n */, T lam1, T *x)
 {
     T a[6][6];     // lower triangle: a[i][j], i >= j; after step k column k holds L(:,k) below the diagonal
     {
@@ -244,11 +245,11 @@ __device__ __forceinline__ void solve6(const double *Au /* 21 upper slots */, co
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-            for (int j = i; j < 6; ++j) a[j][i] = (T)Au[s++] * inv_n;
+            for (int j = i; j < 6; ++j) a[j][i] = Au[s++];
     }
     T y[6], invd[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { a[i][i] *= lam1; y[i] = (T)b[i] * inv_n; }
+    for (int i = 0; i < 6; ++i) { a[i][i] *= lam1; y[i] = b[i]; }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         const T dk = a[k][k];
@@ -278,7 +279,7 @@ __device__ __forceinline__ void solve6(const double *Au /* 21 upper slots */, co
 // finished, decide, and name the next pose to evaluate".
 
 // The proposal for one lambda: solve (A with diag * (1 + lambda)) inc = sum w r v, pose = exp(inc) * accepted pose
-// (optimizer.cpp:258-266).  rec: the record of the accepted pose; (q, t): the accepted pose.
+// (optimizer.cpp:258-266).  (q, t): the accepted pose.
 __device__ __forceinline__ void lm_pose_from_inc(const lmreal *inc, const lmreal *q, const lmreal *t, lmreal *qn, lmreal *tn, float *R,
                                                  float *tf)
 {
@@ -292,9 +293,17 @@ __device__ __forceinline__ void lm_pose_from_inc(const lmreal *inc, const lmreal
 #pragma unroll
     for (int i = 0; i < 3; ++i) tf[i] = (float)tn[i];
 }
-__device__ __forceinline__ void lm_propose(const double *rec, const lmreal *q, const lmreal *t, float lambda, Trial &o)
+// One value of the record as the LM step uses it: A / n and (sum w r v) / n in lmreal (LGS6::finish, LGSX.h:320-326); n: the
+// number of good points (slot kRecGood of the same record).
+__device__ __forceinline__ lmreal lm_scaled(double v, double n)
 {
-    solve6<lmreal>(rec + kRecA, rec + kRecB, lm_rcp<lmreal>((lmreal)rec[kRecGood]), (lmreal)(1.f + lambda), o.inc);
+    return (lmreal)v * lm_rcp<lmreal>((lmreal)n);
+}
+
+// recs: the scaled record (lm_scaled) of the accepted pose
+__device__ __forceinline__ void lm_propose(const lmreal *recs, const lmreal *q, const lmreal *t, float lambda, Trial &o)
+{
+    solve6<lmreal>(recs + kRecA, recs + kRecB, (lmreal)(1.f + lambda), o.inc);
     lm_pose_from_inc(o.inc, q, t, o.qn, o.tn, o.R, o.t);
     o.lambda = lambda;
 }
@@ -394,24 +403,43 @@ __device__ __forceinline__ bool lm_step(LMState &lm, Trial *trial, int &cur, con
 }
 
 // ---- per-point work: PASS A + PASS B fused ---------------------------------------
-// One 256-bit load (LDG.E.ENL2.256 on sm_100a) of the 32-byte QUAD record of pixel (ix,iy): the four distance-transform
-// values and the four packed gradients the bilinear fetch of optimizer.h:173-185 needs.  Returned as the two row
-// records r0 = {dt(x,y), dt(x+1,y), g(x,y), g(x+1,y)}, r1 = the same for row y+1.  One gather and one address per point
-// instead of two (or four texel fetches); on its own this measured neutral -- the gather phase is bound neither by L1
-// wavefronts nor by per-thread memory parallelism (profiles/r1_k_track_v6_hotspots.txt) -- but it is the cheapest fetch.
-// kNoL1: ld.global.nc.L1::no_allocate -- a record is used once per evaluation, caching it in L1 only evicts the shared-memory
-// neighbours' lines (measured: -9 % kernel time, profiles/r2_k_track_ab.txt).
-template <bool kNoL1>
-__device__ __forceinline__ void ldg_quad(const uint4 *p, uint4 &r0, uint4 &r1)
+// The four texels around a projected point (optimizer.h:173-185), each one 64-bit load from the tiled lookup structure
+// (internal.h: opt_texel_index): .x = dt (float32 bits), .y = snorm16 gx | gy.
+// kHint 0: plain; 1: ld.global.nc.L1::no_allocate; 2: additionally L2::evict_last through a cache policy, i.e. the keyframe
+// texels of the pairs in flight outlive the streamed data (point lists, other kernels' traffic) in L2.
+template <int kHint>
+__device__ __forceinline__ uint2 ldg_texel(const uint2 *p, unsigned long long policy)
 {
-    if (kNoL1)
-        asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-            : "=r"(r0.x), "=r"(r0.y), "=r"(r1.x), "=r"(r1.y), "=r"(r0.z), "=r"(r0.w), "=r"(r1.z), "=r"(r1.w)
-            : "l"(p));
+    uint2 v;
+    if (kHint == 2)
+        asm("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(policy));
+    else if (kHint == 1)
+        asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     else
-        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-            : "=r"(r0.x), "=r"(r0.y), "=r"(r1.x), "=r"(r1.y), "=r"(r0.z), "=r"(r0.w), "=r"(r1.z), "=r"(r1.w)
-            : "l"(p));
+        asm("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// A 3-D edge point of the current frame: read once per level (then cached in shared memory), so it should neither stay in
+// L1 nor displace the texels in L2 (kHint 2: L2 evict_first through a cache policy).
+template <int kHint>
+__device__ __forceinline__ float4 ldg_point(const float4 *p)
+{
+    if (kHint == 2) {
+        float4 v;
+        unsigned long long pol;
+        asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+            : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+        return v;
+    }
+    return __ldg(p);
 }
 
 // snorm16 pair -> floats (scale folded in by the caller)
@@ -430,17 +458,17 @@ __device__ __forceinline__ void unpack_grad(uint32_t g, float &gx, float &gy)
 
 struct ProjB {
     float a, b, iz, dx, dy;   // a = Wx/Wz, b = Wy/Wz (0 when the point projects out of bounds)
-    const uint4 *bp;
+    unsigned i00, i10, i01, i11;   // texel indices (opt_texel_index) of (ix,iy), (ix+1,iy), (ix,iy+1), (ix+1,iy+1)
     bool valid;
 };
 
 struct LevelConst {           // per-level constants of an evaluation, kept in registers
     float fx, fy, cx, cy, umax, vmax;
-    int w;
-    const uint4 *opt;
+    unsigned tw16;            // tiles per row x 16 texels
+    const uint2 *opt;
 };
 
-// optimizer.cpp:93-100: rigid transform (three FMA chains), projection, NaN-safe bounds test
+// optimizer.cpp:93-100: rigid transform (three FMA chains), projection, NaN-safe bounds test, texel addresses
 __device__ __forceinline__ ProjB project_b(float x, float y, float z, const LevelConst &L, const float *__restrict__ R,
                                            const float *__restrict__ t)
 {
@@ -460,25 +488,30 @@ __device__ __forceinline__ ProjB project_b(float x, float y, float z, const Leve
     o.a = inb ? a : 0.f;
     o.b = inb ? b : 0.f;
     o.iz = inb ? iz : 0.f;
-    o.bp = L.opt + 2u * (unsigned)(iy * L.w + ix);
+    // x part: (tile column) * 16 + (x & 3); y part: (tile row) * tw16 + (y & 3) * 4
+    const unsigned ux = (unsigned)ix, uy = (unsigned)iy;
+    const unsigned cx0 = ((ux & ~3u) << 2) | (ux & 3u), cx1 = (((ux + 1u) & ~3u) << 2) | ((ux + 1u) & 3u);
+    const unsigned cy0 = (uy >> 2) * L.tw16 + ((uy & 3u) << 2), cy1 = ((uy + 1u) >> 2) * L.tw16 + (((uy + 1u) & 3u) << 2);
+    o.i00 = cy0 + cx0; o.i10 = cy0 + cx1; o.i01 = cy1 + cx0; o.i11 = cy1 + cx1;
     return o;
 }
 
 // optimizer.cpp:101-131 + calculateWarpUpdate (:204-228) + LGS6::update (LGSX.h:392-398) for a point that exists.
-// kqfx = fx / 32764, kqfy = fy / 32764 (gradient scale), ed_eff = edge filter distance or +inf when the filter is off.
-// The "bad" counter is not kept here: every visited point exists, so bad = visited - good (set by the caller).
-__device__ __forceinline__ void finish_point_b(const ProjB &P, const uint4 r0, const uint4 r1, float kqfx, float kqfy, float ed_eff,
-                                               float huber, float (&acc)[32])
+// t00 .. t11: the texels of (ix,iy), (ix+1,iy), (ix,iy+1), (ix+1,iy+1).  kqfx = fx / 32764, kqfy = fy / 32764 (gradient
+// scale), ed_eff = edge filter distance or +inf when the filter is off.  The "bad" counter is not kept here: every visited
+// point exists, so bad = visited - good (set by the caller).
+__device__ __forceinline__ void finish_point_b(const ProjB &P, const uint2 t00, const uint2 t10, const uint2 t01, const uint2 t11, float kqfx,
+                                               float kqfy, float ed_eff, float huber, float (&acc)[32])
 {
     // getInterpolatedElement43, optimizer.h:173-185
     const float dxdy = P.dx * P.dy;
     const float w11 = dxdy, w01 = P.dy - dxdy, w10 = P.dx - dxdy, w00 = 1.f - P.dx - P.dy + dxdy;
     float gx00, gy00, gx10, gy10, gx01, gy01, gx11, gy11;
-    unpack_grad(r0.z, gx00, gy00); unpack_grad(r0.w, gx10, gy10);
-    unpack_grad(r1.z, gx01, gy01); unpack_grad(r1.w, gx11, gy11);
+    unpack_grad(t00.y, gx00, gy00); unpack_grad(t10.y, gx10, gy10);
+    unpack_grad(t01.y, gx01, gy01); unpack_grad(t11.y, gx11, gy11);
     const float gx = (w11 * gx11 + w01 * gx01 + w10 * gx10 + w00 * gx00) * kqfx;   // optimizer.cpp:119
     const float gy = (w11 * gy11 + w01 * gy01 + w10 * gy10 + w00 * gy00) * kqfy;   // optimizer.cpp:120
-    const float r = w11 * __uint_as_float(r1.y) + w01 * __uint_as_float(r1.x) + w10 * __uint_as_float(r0.y) + w00 * __uint_as_float(r0.x);
+    const float r = w11 * __uint_as_float(t11.x) + w01 * __uint_as_float(t01.x) + w10 * __uint_as_float(t10.x) + w00 * __uint_as_float(t00.x);
     const bool pass = P.valid && !(r > ed_eff);                                     // optimizer.cpp:100,112
     const float hub = huber * rcp_approx(fmaxf(r, huber));                          // optimizer.h:159: r <= huber ? 1 : huber / r
     const float wr = pass ? ((r <= huber) ? 1.f : hub) : 0.f;

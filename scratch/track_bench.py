@@ -53,12 +53,19 @@ def main():
     configs = [
         ("C8 T128 (default)", 1, 8, 128, 0, {}),
         ("C8 T128 no speculation", 1, 8, 128, 0, {"REVO_TRACK_SPEC": "0"}),
-        ("C8 T128 plain gather", 1, 8, 128, 0, {"REVO_TRACK_HINT": "0"}),
-        ("C8 T128 plain, no spec", 1, 8, 128, 0, {"REVO_TRACK_HINT": "0", "REVO_TRACK_SPEC": "0"}),
+        ("C8 T128 plain gathers", 1, 8, 128, 0, {"REVO_TRACK_HINT": "0"}),
+        ("C8 T128 L1::no_allocate", 1, 8, 128, 0, {"REVO_TRACK_HINT": "1"}),
         ("C4 T256", 1, 4, 256, 0, {}),
         ("C8 T256", 1, 8, 256, 0, {}),
         ("C8 T128 pcap8", 1, 8, 128, 0, {"REVO_TRACK_PCAP": "8"}),
+        ("C8 T128 pcap18", 1, 8, 128, 0, {"REVO_TRACK_PCAP": "18"}),
         ("C8 T128 maxc64", 1, 8, 128, 0, {"REVO_TRACK_MAX_CLUSTERS": "64"}),
+        ("C4 T128", 1, 4, 128, 0, {}),
+        ("C4 T128 plain", 1, 4, 128, 0, {"REVO_TRACK_HINT": "0"}),
+        ("C4 T128 maxc100", 1, 4, 128, 0, {"REVO_TRACK_MAX_CLUSTERS": "100"}),
+        ("C4 T128 maxc120", 1, 4, 128, 0, {"REVO_TRACK_MAX_CLUSTERS": "120"}),
+        ("C2 T256", 1, 2, 256, 0, {}),
+        ("C4 T128 pcap40", 1, 4, 128, 0, {"REVO_TRACK_PCAP": "40"}),
     ]
     if args.configs:
         keep = set(int(x) for x in args.configs.split(","))

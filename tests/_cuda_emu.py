@@ -36,11 +36,13 @@ PRELUDE = r'''
 #include "revo_b200.h"
 
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
 struct float4 { float x, y, z, w; };
 struct float2 { float x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 
 namespace emu {
 struct D3 { unsigned x, y, z; };
@@ -101,6 +103,7 @@ template <class T> static inline T *map_rank(T *p, unsigned rank)
 #define gridDim emu::gdim
 #define __global__
 #define __device__
+#define __host__
 #define __forceinline__ inline
 #define __restrict__
 #define __align__(n) __attribute__((aligned(n)))
@@ -222,12 +225,10 @@ namespace cg = cooperative_groups;
 
 namespace revo {
 // host versions of the PTX helpers of track_common.cuh / track.cu
-template <bool kNoL1> static inline void ldg_quad(const uint4 *p, uint4 &r0, uint4 &r1)
-{
-    const uint32_t *q = (const uint32_t *)p;
-    r0 = make_uint4(q[0], q[1], q[4], q[5]);
-    r1 = make_uint4(q[2], q[3], q[6], q[7]);
-}
+template <int kHint> static inline float4 ldg_point(const float4 *p) { return *p; }
+template <int kHint> static inline uint2 ldg_texel(const uint2 *p, unsigned long long) { return *p; }
+static inline unsigned long long l2_policy_evict_last() { return 0; }
+static inline int opt_tiles_per_row_dev(int w) { return (w + 3) >> 2; }
 static inline float rcp_approx(float x) { return 1.0f / x; }
 static inline uint32_t smem_u32(const void *p) { return (uint32_t)((const char *)p - (const char *)emu::cta->dyn.data()); }   // only meaningful for the dynamic buffer
 // mbarrier with transaction count in one 64-bit word: [31:0] pending transaction bytes (signed: completions may come before the
@@ -393,22 +394,17 @@ extern "C" int emu_track_pairs(int variant, int n_pairs, int n_clusters, int cta
                                const revo_tracker_config *cfg, int mode, int level, int pcap, revo_track_result *results, double *records)
 {
     using namespace revo;
-    std::vector<std::vector<uint4>> opt((size_t)n_pairs * n_levels);
+    std::vector<std::vector<uint2>> opt((size_t)n_pairs * n_levels);
     std::vector<PairDesc> pairs(n_pairs);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int p = 0; p < n_pairs; ++p) {
         std::memset(&pairs[p], 0, sizeof(PairDesc));
         for (int l = 0; l < n_levels; ++l) {
             const int k = p * n_levels + l;
-            const size_t npx = (size_t)w[k] * h[k];
-            opt[k].resize(2 * npx);
-            for (size_t i = 0; i < npx; ++i) {              // k_opt_struct, pyramid.cu
-                const float4 a = opt_texel(dt[k], i, w[k], h[k]);
-                const float4 b = (i + 1 < npx) ? opt_texel(dt[k], i + 1, w[k], h[k]) : z;
-                const float4 c = (i + w[k] < npx) ? opt_texel(dt[k], i + w[k], w[k], h[k]) : z;
-                const float4 d = (i + w[k] + 1 < npx) ? opt_texel(dt[k], i + w[k] + 1, w[k], h[k]) : z;
-                store_quad(opt[k].data(), i, a, b, c, d);
-            }
+            const int tw = (w[k] + 3) >> 2, th = (h[k] + 3) >> 2;
+            opt[k].resize((size_t)tw * th * 16);
+            for (int y = 0; y < h[k]; ++y)                  // k_opt_struct, pyramid.cu
+                for (int x = 0; x < w[k]; ++x)
+                    opt[k][opt_texel_index(x, y, tw)] = pack_texel(opt_texel(dt[k], (size_t)y * w[k] + x, w[k], h[k]));
             LevelIn &L = pairs[p].lvl[l];
             L.pts = (const float4 *)pts[k]; L.n_pts = &n_pts[k]; L.opt = opt[k].data();
             L.fx = cam4[4 * k]; L.fy = cam4[4 * k + 1]; L.cx = cam4[4 * k + 2]; L.cy = cam4[4 * k + 3]; L.w = w[k]; L.h = h[k];
@@ -427,7 +423,7 @@ extern "C" int emu_track_pairs(int variant, int n_pairs, int n_clusters, int cta
     int *wc = work_counter;
     if (variant != 0 && variant != 1) return 1;
     prm.speculate = variant == 0 ? 1 : 0;
-    emu::run_grid(n_clusters, ctas_per_pair, T, dyn, [=]() { k_track<T, 4, true>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
+    emu::run_grid(n_clusters, ctas_per_pair, T, dyn, [=]() { k_track<T, 4, 1>(d_pairs, n_pairs, prm, results, records, nullptr, nullptr, wc, pcap); });
     return 0;
 }
 '''
@@ -485,12 +481,13 @@ def build(out_dir, with_lean=False):
     common, pyr, internal, track = rd("revo_b200", "csrc", "track_common.cuh"), rd("revo_b200", "csrc", "pyramid.cu"), \
         rd("revo_b200", "csrc", "internal.h"), rd("revo_b200", "csrc", "track.cu")
     body = common[common.index("namespace revo {") + len("namespace revo {"):common.index("}  // namespace revo")]
-    body = _strip_functions(body, ["ldg_quad", "rcp_approx", "smem_u32", "mbar_init", "mbar_expect_tx", "mbar_wait", "st_async_b64"])
+    body = _strip_functions(body, ["ldg_texel", "l2_policy_evict_last", "ldg_point", "rcp_approx", "smem_u32", "mbar_init", "mbar_expect_tx", "mbar_wait", "st_async_b64"])
     assert "asm" not in body
     grab = lambda t, pat: t[re.search(pat, t, re.M).start():t.index("\n}\n", re.search(pat, t, re.M).start()) + 3]      # noqa: E731
     parts = ["namespace revo {", _struct(internal, "LevelIn"), _struct(internal, "PairDesc"), _struct(internal, "TrackParams"), body,
+             grab(internal, r"^__host__ __device__ inline unsigned opt_texel_index"),
              grab(pyr, r"^__device__ __forceinline__ float4 opt_texel"), grab(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
-             grab(pyr, r"^__device__ __forceinline__ void store_quad"), _struct(track, "Mailbox"), _kernel(track, "k_track")]
+             grab(pyr, r"^__device__ __forceinline__ uint2 pack_texel"), _struct(track, "Mailbox"), _kernel(track, "k_track")]
     flags = []
     parts.append("}  // namespace revo")
     src, lib = os.path.join(out_dir, "cuda_emu.cpp"), os.path.join(out_dir, "libcuda_emu.so")
@@ -658,7 +655,7 @@ extern "C" int emu_pyramid(const uint8_t *bgr, int channels, const float *depth,
             L.n_pts = first ? o.n_pts : (int *)alloc(8); L.nz_patches = first ? o.nz_patches : (int *)alloc(8);
             L.tile_off = (int *)alloc(((size_t)o.n_tiles + 1) * 4);
             L.labels = (int *)labels[f]; L.flags = flags[f];
-            L.dt = first ? o.dt : (float *)alloc(px * 4); L.opt = (uint4 *)(first ? (uint8_t *)o.opt : alloc(px * 32));
+            L.dt = first ? o.dt : (float *)alloc(px * 4); L.opt = (uint2 *)(first ? (uint8_t *)o.opt : alloc(px * 8 + 4096));
             L.w = o.w; L.h = o.h; L.pts_cap = o.cap; L.patch = o.patch; L.hist_w = o.w / o.patch; L.hist_h = o.h / o.patch;
             L.fx = o.fx; L.fy = o.fy; L.cx = o.cx; L.cy = o.cy;
         }
@@ -729,7 +726,8 @@ def build_pyramid(out_dir):
     generic = RUNNER[RUNNER.index("// @GENERIC_BEGIN"):RUNNER.index("// @GENERIC_END")]
     src_text = (PRELUDE + CANNY_SHIMS + generic + "namespace revo {\nstatic inline int cdiv(int a, int b) { return (a + b - 1) / b; }\n"
                 + "constexpr int kTileW = 8;\nconstexpr int kTileH = 4;\n"
-                + _struct(internal, "ImgLevel") + "\n" + _struct(internal, "QualityFrame") + "\n" + _struct(internal, "QualityArgs") + "\n"
+                + _struct(internal, "ImgLevel") + "\n" + internal[internal.index("__host__ __device__ inline unsigned opt_texel_index"):internal.index("inline int opt_tiles_per_row")]
+                + _struct(internal, "QualityFrame") + "\n" + _struct(internal, "QualityArgs") + "\n"
                 + body + "}  // namespace revo\n" + PYRAMID_DRIVER)
     src, lib = os.path.join(out_dir, "pyramid_emu.cpp"), os.path.join(out_dir, "libpyramid_emu.so")
     open(src, "w").write(src_text)

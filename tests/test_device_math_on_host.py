@@ -1,8 +1,8 @@
 """The device source text of the per-point tracking arithmetic, compiled for the HOST and checked against the oracle -- a CPU
 test of what the GPU executes per edge point (the `-m gpu` tests check the same through the kernels).
 
-Taken verbatim from the CUDA sources (function text, extracted at test time): ``opt_texel`` / ``pack_grad`` / ``store_quad``
-(pyramid.cu: the 32-byte quad record with snorm16 gradients) and ``project_b`` / ``unpack_grad`` / ``finish_point_b``
+Taken verbatim from the CUDA sources (function text, extracted at test time): ``opt_texel`` / ``pack_grad`` / ``pack_texel`` /
+``opt_texel_index`` (pyramid.cu, internal.h: the tiled 8-byte texels with snorm16 gradients) and ``project_b`` / ``unpack_grad`` / ``finish_point_b``
 (track_common.cuh: warp, project, bounds, bilinear fetch, edge filter, Huber weight, Jacobian, normal-equation terms;
 optimizer.cpp:93-131, 204-228, LGSX.h:392-398).  Host shims replace the intrinsics (``rcp.approx`` -> 1/x, ``__float2int_rn``
 -> lrintf, ...); g++ fuses ``a * b + c`` like nvcc does (-mfma -ffp-contract=fast).  The summed record must agree with the
@@ -31,6 +31,9 @@ SHIM = r'''
 #define __forceinline__ inline
 #define __restrict__
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+#define __host__
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
@@ -54,27 +57,20 @@ DRIVER = r'''
 extern "C" int host_eval_record(const float *pts4, int n, const float *dt, int w, int h, float fx, float fy, float cx, float cy,
                                 const float *R9, const float *t3, float ed, int use_filter, float huber, double *rec32)
 {
-    const size_t npx = (size_t)w * h;
-    std::vector<uint4> opt(2 * npx);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (size_t i = 0; i < npx; ++i) {                      // k_opt_struct, pyramid.cu
-        const float4 a = opt_texel(dt, i, w, h);
-        const float4 b = (i + 1 < npx) ? opt_texel(dt, i + 1, w, h) : z;
-        const float4 c = (i + w < npx) ? opt_texel(dt, i + w, w, h) : z;
-        const float4 d = (i + w + 1 < npx) ? opt_texel(dt, i + w + 1, w, h) : z;
-        store_quad(opt.data(), i, a, b, c, d);
-    }
+    const int tw = (w + 3) >> 2, th = (h + 3) >> 2;
+    std::vector<uint2> opt((size_t)tw * th * 16);
+    for (int y = 0; y < h; ++y)                              // k_opt_struct, pyramid.cu
+        for (int x = 0; x < w; ++x) opt[opt_texel_index(x, y, tw)] = pack_texel(opt_texel(dt, (size_t)y * w + x, w, h));
     LevelConst L;
-    L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.umax = (float)(w - 2); L.vmax = (float)(h - 2); L.w = w; L.opt = opt.data();
+    L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.umax = (float)(w - 2); L.vmax = (float)(h - 2); L.tw16 = (unsigned)tw << 4; L.opt = opt.data();
     for (int i = 0; i < 32; ++i) rec32[i] = 0.0;
     for (int i = 0; i < n; ++i) {
         const float4 p = make_float4(pts4[4 * i], pts4[4 * i + 1], pts4[4 * i + 2], 1.f);
         const ProjB P = project_b(p.x, p.y, p.z, L, R9, t3);
-        const uint32_t *q = (const uint32_t *)P.bp;        // ldg_quad: one 32-byte record -> the two row records
-        const uint4 r0 = make_uint4(q[0], q[1], q[4], q[5]), r1 = make_uint4(q[2], q[3], q[6], q[7]);
         float acc[32] = {0};
         // the kernel's per-level constants (k_track): gradient scale folded with the focal length, +inf = filter off
-        finish_point_b(P, r0, r1, fx * (1.0f / 32764.0f), fy * (1.0f / 32764.0f), use_filter ? ed : INFINITY, huber, acc);
+        finish_point_b(P, L.opt[P.i00], L.opt[P.i10], L.opt[P.i01], L.opt[P.i11], fx * (1.0f / 32764.0f), fy * (1.0f / 32764.0f),
+                       use_filter ? ed : INFINITY, huber, acc);
         acc[kRecBad] = 1.f - acc[kRecGood];                 // every visited point exists: bad = visited - good
         for (int k = 0; k < 32; ++k) rec32[k] += acc[k];
     }
@@ -102,7 +98,13 @@ extern "C" void host_se3_exp(const double *xi, double *q, double *t) { se3_exp<d
 extern "C" void host_se3_mul(const double *qa, const double *ta, const double *qb, const double *tb, double *q, double *t) { se3_mul<double>(qa, ta, qb, tb, q, t); }
 extern "C" void host_quat_from_R(const float *R9, double *q) { quat_from_R<double>(R9, q); }
 extern "C" void host_quat_to_R(const double *q, double *R9) { quat_to_R<double>(q, R9); }
-extern "C" void host_solve6(const double *Au21, const double *b, double inv_n, double lam1, double *x) { solve6<double>(Au21, b, inv_n, lam1, x); }
+extern "C" void host_solve6(const double *Au21, const double *b, double inv_n, double lam1, double *x)
+{
+    double A[21], y[6];
+    for (int i = 0; i < 21; ++i) A[i] = Au21[i] * inv_n;
+    for (int i = 0; i < 6; ++i) y[i] = b[i] * inv_n;
+    solve6<double>(A, y, lam1, x);
+}
 // the float instantiations (what the library runs): float in / out through double arrays
 extern "C" void host_se3_exp_f(const double *xi, double *q, double *t)
 {
@@ -114,8 +116,10 @@ extern "C" void host_se3_exp_f(const double *xi, double *q, double *t)
 }
 extern "C" void host_solve6_f(const double *Au21, const double *b, double inv_n, double lam1, double *x)
 {
-    float xf[6];
-    solve6<float>(Au21, b, inv_n, (float)lam1, xf);
+    float xf[6], A[21], y[6];
+    for (int i = 0; i < 21; ++i) A[i] = (float)Au21[i] * (float)inv_n;
+    for (int i = 0; i < 6; ++i) y[i] = (float)b[i] * (float)inv_n;
+    solve6<float>(A, y, (float)lam1, xf);
     for (int i = 0; i < 6; ++i) x[i] = xf[i];
 }
 extern "C" int host_lm_real_bytes() { return (int)sizeof(lmreal); }
@@ -132,6 +136,7 @@ extern "C" int host_track_level(const float *pts4, int n, const float *dt, int w
     std::memset(&lm, 0, sizeof(lm));
     static Trial trial[3];
     static double rec[2][32];
+    static lmreal recs[2][32];
     SpecIn specin[2];
     std::memset(trial, 0, sizeof(trial));
     std::memset(specin, 0, sizeof(specin));
@@ -148,9 +153,10 @@ extern "C" int host_track_level(const float *pts4, int n, const float *dt, int w
         host_eval_record(pts4, n, dt, w, h, fx, fy, cx, cy, trial[cur].R, trial[cur].t, oc->edge_distance_lvl[lvl], oc->use_edge_filter,
                          oc->huber_edge, rec[wb]);
         std::memcpy(last_rec32, rec[wb], sizeof(double) * 32);
+        for (int i = 0; i < 32; ++i) recs[wb][i] = lm_scaled(rec[wb][i], rec[wb][kRecGood]);      // k_track: publish()
         if (speculate && !first) {
             const SpecIn s = specin[seq & 1];
-            if (s.active) lm_propose(rec[s.acc], lm.q[s.pacc], lm.t[s.pacc], s.lambda, trial[cur == 2 ? 0 : cur + 1]);
+            if (s.active) lm_propose(recs[s.acc], lm.q[s.pacc], lm.t[s.pacc], s.lambda, trial[cur == 2 ? 0 : cur + 1]);
         }
         ++seq;
         ++evals;
@@ -159,7 +165,7 @@ extern "C" int host_track_level(const float *pts4, int n, const float *dt, int w
         LMOrder order;
         const bool done = lm_step(lm, trial, cur, rec, speculate && !first, specin[(seq - 1) & 1], specin[seq & 1], order, *oc, lvl, first,
                                   &te, &traced);
-        if (order.propose) lm_propose(rec[order.acc], lm.q[order.pacc], lm.t[order.pacc], order.lambda, trial[order.slot]);
+        if (order.propose) lm_propose(recs[order.acc], lm.q[order.pacc], lm.t[order.pacc], order.lambda, trial[order.slot]);
         first = false;
         if (done || evals > 10000) break;
     }
@@ -193,8 +199,10 @@ def device_parts():
     LM_SPECIALISATIONS = _lm_spec(common)
     i = common.index("#ifdef REVO_LM_DOUBLE")
     LM_TYPEDEF = common[i:common.index("#endif", i) + len("#endif")] + "\n"
-    return [_grab(pyr, r"^__device__ __forceinline__ float4 opt_texel"), _grab(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
-            _grab(pyr, r"^__device__ __forceinline__ void store_quad"), _grab(common, r"^__device__ __forceinline__ void unpack_grad"),
+    internal = open(os.path.join(ROOT, "revo_b200", "csrc", "internal.h")).read()
+    return [_grab(internal, r"^__host__ __device__ inline unsigned opt_texel_index"),
+            _grab(pyr, r"^__device__ __forceinline__ float4 opt_texel"), _grab(pyr, r"^__device__ __forceinline__ uint32_t pack_grad"),
+            _grab(pyr, r"^__device__ __forceinline__ uint2 pack_texel"), _grab(common, r"^__device__ __forceinline__ void unpack_grad"),
             _grab(common, r"^struct ProjB \{"), _grab(common, r"^struct LevelConst \{"),
             _grab(common, r"^__device__ __forceinline__ ProjB project_b"), _grab(common, r"^__device__ __forceinline__ void finish_point_b"),
             LM_TYPEDEF,
@@ -203,7 +211,7 @@ def device_parts():
             _grab(common, r"^__device__ __forceinline__ void quat_to_R"),
             _grab(common, r"^__device__ inline void quat_from_R"), _grab(common, r"^__device__ __forceinline__ void se3_exp"),
             _grab(common, r"^__device__ __forceinline__ void se3_mul"), _grab(common, r"^__device__ __forceinline__ void solve6\("),
-            _grab(common, r"^__device__ __forceinline__ void lm_pose_from_inc"), _grab(common, r"^__device__ __forceinline__ void lm_propose\("),
+            _grab(common, r"^__device__ __forceinline__ void lm_pose_from_inc"), _grab(common, r"^__device__ __forceinline__ lmreal lm_scaled"), _grab(common, r"^__device__ __forceinline__ void lm_propose\("),
             _grab(common, r"^__device__ __forceinline__ float lm_reject_lambda"),
             _grab(common, r"^__device__ __forceinline__ bool lm_step"), _grab(common, r"^__device__ __forceinline__ float cost_point")]
 

@@ -38,7 +38,7 @@ def run_pyramid(lib, bgr, depth, cam, n_levels, n_frames=1, keyframe=True, n_per
         a = dict(gray=np.zeros((h, w), np.uint8), depth=np.zeros((h, w), np.float32), edges=np.zeros((h, w), np.uint8),
                  edges_orig=np.zeros((h, w), np.uint8), hist=np.zeros((max(1, h // patch), max(1, w // patch)), np.uint8),
                  pts=np.zeros((cap, 4), np.float32), n_pts=np.zeros(2, np.int32), nz_patches=np.zeros(2, np.int32),
-                 dt=np.zeros((h, w), np.float32), opt=np.zeros((h, w, 8), np.uint32), pts_ref=np.zeros((w * h, 4), np.float32),
+                 dt=np.zeros((h, w), np.float32), opt=np.zeros((((h + 3) // 4) * ((w + 3) // 4) * 16, 2), np.uint32), pts_ref=np.zeros((w * h, 4), np.float32),
                  n_ref=np.zeros(2, np.int32), opt_f4=np.zeros((h, w, 4), np.float32))
         arrays.append(a)
         o = outs[l]
@@ -76,14 +76,15 @@ def compare(arrays, po, n_levels, keyframe=True):
             assert np.array_equal(a["dt"].view(np.uint32), np.asarray(po.dt[l], np.float32).view(np.uint32)), l
             ow = np.asarray(po.opt[l], np.float32)
             assert np.array_equal(a["opt_f4"][1:-1, :, :3].view(np.uint32), ow[1:-1, :, :3].view(np.uint32)), l
-            # quad records: the structure's dt (0 in rows 0 and h-1, like the gradients) of the four texels as float32,
-            # gradients as snorm16 with step 1/32764
-            q = a["opt"]
-            z = a["opt_f4"][..., 2].view(np.uint32)
-            assert np.array_equal(q[:-1, :-1, 0], z[:-1, :-1]) and np.array_equal(q[:-1, :-1, 1], z[:-1, 1:])
-            assert np.array_equal(q[:-1, :-1, 2], z[1:, :-1]) and np.array_equal(q[:-1, :-1, 3], z[1:, 1:])
-            gx = (q[..., 4] & 0xffff).astype(np.uint16).view(np.int16).astype(np.float32) / 32764.0
-            gy = (q[..., 4] >> 16).astype(np.uint16).view(np.int16).astype(np.float32) / 32764.0
+            # device layout: 8-byte texels {dt float32 bits | snorm16 gx, gy with step 1/32764} in 4x4 tiles (internal.h: opt_texel_index);
+            # dt is 0 in rows 0 and h-1 like the gradients
+            hh, ww = a["opt_f4"].shape[:2]
+            ys, xs = np.mgrid[0:hh, 0:ww]
+            idx = (((ys >> 2) * ((ww + 3) // 4) + (xs >> 2)) << 4) + ((ys & 3) << 2) + (xs & 3)
+            q = a["opt"][idx]                                   # (h, w, 2)
+            assert np.array_equal(q[..., 0], a["opt_f4"][..., 2].view(np.uint32))
+            gx = (q[..., 1] & 0xffff).astype(np.uint16).view(np.int16).astype(np.float32) / 32764.0
+            gy = (q[..., 1] >> 16).astype(np.uint16).view(np.int16).astype(np.float32) / 32764.0
             assert np.abs(gx[1:-1] - np.clip(ow[1:-1, :, 0], -1, 1)).max() <= 0.5 / 32764 + 1e-7
             assert np.abs(gy[1:-1] - np.clip(ow[1:-1, :, 1], -1, 1)).max() <= 0.5 / 32764 + 1e-7
 
