@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=128, help="independent streams (frames per step) per GPU")
+    ap.add_argument("--streams", type=int, default=256, help="independent streams (frames per step) per GPU")
     ap.add_argument("--ref-streams", type=int, default=64, help="streams per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=480)
@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-pipeline", action="store_true", help="e2e run without the second (upload/build) stream")
     ap.add_argument("--ctas-per-pair", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the single_stream / config3 / edge_split blocks")
     return ap.parse_args()
 
 
@@ -113,8 +114,15 @@ class OracleBackend:
     def __init__(self, cam, n_levels):
         from oracle import oracle as O
 
+        import cv2
+
         self.O = O
         self.orc = O.Oracle("f32")
+        # all host threads, explicitly: torch.distributed.run exports OMP_NUM_THREADS=1, which would throttle this arm ~3x
+        self.cores = os.cpu_count() or 1
+        self.omp_threads = self.orc.set_num_threads(self.cores)
+        cv2.setNumThreads(self.cores)
+        self.cv2_threads = cv2.getNumThreads()
         self.cfg = O.PyrCfg(n_levels=n_levels)
         self.cam = cam
         self.n_levels = n_levels
@@ -151,6 +159,7 @@ def run_cpu(args, bgr_h, depth_h, cam, n_streams, steps, warmup, fidx=lambda i: 
 
     be = OracleBackend(cam, args.levels)
     st = StreamTracker(be, n_streams, args.kf_interval)
+    st.keep_history = True
     st.start(bgr_h[0, :n_streams], depth_h[0, :n_streams])
     for i in range(1, warmup + 1):
         st.step(bgr_h[fidx(i), :n_streams], depth_h[fidx(i), :n_streams])
@@ -159,7 +168,8 @@ def run_cpu(args, bgr_h, depth_h, cam, n_streams, steps, warmup, fidx=lambda i: 
     for i in range(warmup + 1, warmup + 1 + steps):
         st.step(bgr_h[fidx(i), :n_streams], depth_h[fidx(i), :n_streams])
     dt = time.perf_counter() - t0
-    return dict(seconds=dt, frames=steps * n_streams, evals=st.total_evals - ev0, T_w_c=st.T_w_c.copy())
+    return dict(seconds=dt, frames=steps * n_streams, evals=st.total_evals - ev0, T_w_c=st.T_w_c.copy(), history=st.history,
+                omp_threads=be.omp_threads, cv2_threads=be.cv2_threads)
 
 
 def pose_errors(T_est, poses_gt, frame):
@@ -174,6 +184,155 @@ def pose_errors(T_est, poses_gt, frame):
         er.append(synth.rot_angle(D[:3, :3]))
         et.append(float(np.linalg.norm(D[:3, 3])))
     return float(np.mean(er)), float(np.mean(et))
+
+
+def _render_pair(torch, synth_torch, local_rank, w, h, seed, gap=1):
+    dev = torch.device("cuda", local_rank)
+    bgr = torch.empty((gap + 1, 1, h, w, 3), dtype=torch.uint8, device=dev)
+    depth = torch.empty((gap + 1, 1, h, w), dtype=torch.float32, device=dev)
+    cam, poses = synth_torch.render_streams([seed], gap + 1, w, h, dev, bgr, depth)
+    return cam, poses, bgr, depth
+
+
+def extra_single_pair(torch, api, synth_torch, ctx, local_rank, w, h, levels, seed, reps, label):
+    """One frame pair at a time (BASELINE configs[0] / configs[2]): latency of a frame = pyramid construction + coarse-to-fine
+    tracking against a keyframe, inputs resident in HBM, and the tracking kernel's microseconds per evaluation."""
+    cam, poses, bgr, depth = _render_pair(torch, synth_torch, local_rank, w, h, seed)
+    fx, fy, cx, cy, _, _ = cam
+    st = api.ImgPyramidSettings(PYR_MIN_LVL=levels - 1, PYR_MAX_LVL=0, width=w, height=h, fx=fx, fy=fy, cx=cx, cy=cy)
+    trk = api.TrackerNew(ctx, api.TrackerSettings(), st)
+    kf = api.PyramidBatch(ctx, st, bgr[0], depth[0], 1)
+    t0 = time.perf_counter()
+    kf.makeKeyframes()
+    ctx.synchronize()
+    kf_first_ms = (time.perf_counter() - t0) * 1e3
+    I, Z = np.eye(3, dtype=np.float32)[None], np.zeros((1, 3), np.float32)
+    frame_ms, build_ms, k_ms, evals = [], [], [], []
+    out = None
+    for r in range(reps + 3):
+        t0 = time.perf_counter()
+        cur = api.PyramidBatch(ctx, st, bgr[1], depth[1], 1)
+        out = trk.trackFramesBatch(I, Z, kf, cur)            # synchronous: returns the pose
+        dt_ms = (time.perf_counter() - t0) * 1e3
+        p_ms, _, t_ms = ctx.last_timings()
+        cur.destroy()
+        if r >= 3:
+            frame_ms.append(dt_ms); build_ms.append(p_ms); k_ms.append(t_ms); evals.append(int(out["n_evals"].sum()))
+    t0 = time.perf_counter()
+    kf2 = api.PyramidBatch(ctx, st, bgr[1], depth[1], 1)
+    kf2.makeKeyframes()
+    ctx.synchronize()
+    kf2.destroy()
+    kf.destroy()
+    med = lambda a: float(np.median(a))      # noqa: E731
+    ev = med(evals)
+    return {"workload": label, "levels": levels, "edge_points_per_level": [int(x) for x in out["n_pts"][0][:levels]],
+            "evals_per_pair": ev, "frame_latency_ms": med(frame_ms), "frames_per_sec_single_stream": 1e3 / med(frame_ms),
+            "pyramid_build_ms": med(build_ms), "track_kernel_ms": med(k_ms), "us_per_eval": 1e3 * med(k_ms) / ev,
+            "gn_iters_per_sec": ev / (med(frame_ms) * 1e-3), "gn_iters_per_sec_tracking_kernel": ev / (med(k_ms) * 1e-3),
+            "keyframe_promotion_ms_first_call": kf_first_ms,
+            "note": "latency = host wall clock of create + track through the API with a synchronous result (device-resident input); the "
+                    "working set of one pair is L2-resident, so these are latency figures, not roofline ones"}
+
+
+def extra_edge_split(torch, dist, api, synth_torch, ctx, rank, world, local_rank):
+    """BASELINE configs[4]: ONE 1920x1080 pair, 3 levels, the edge-point set split over the ranks (rank r evaluates its share of
+    every level's list) with one 32-value exchange per evaluation over NVLink inside the persistent kernel."""
+    w, h, levels = 1920, 1080, 3
+    cam, poses, bgr, depth = _render_pair(torch, synth_torch, local_rank, w, h, 5)
+    fx, fy, cx, cy, _, _ = cam
+    st = api.ImgPyramidSettings(PYR_MIN_LVL=levels - 1, PYR_MAX_LVL=0, width=w, height=h, fx=fx, fy=fy, cx=cx, cy=cy)
+    trk = api.TrackerNew(ctx, api.TrackerSettings(), st)
+    kf = api.PyramidBatch(ctx, st, bgr[0], depth[0], 1)
+    kf.makeKeyframes()
+    cur = api.PyramidBatch(ctx, st, bgr[1], depth[1], 1)
+    ctx.synchronize()
+    I, Z = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+    # the same pair on one GPU (every rank does it; rank 0 reports)
+    single_ms, single_ev = [], 0
+    for r in range(6):
+        trk.trackFrames(I, Z, kf[0], cur[0])
+        if r >= 2:
+            single_ms.append(ctx.last_timings()[2])
+        single_ev = int(sum(trk.last_result.n_evals))
+    R1, T1 = api._R_from_c(np.array(trk.last_result.R)), np.array(trk.last_result.t)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, trk.splitExport(rank, world))
+    trk.splitOpen(b"".join(blobs))
+    dist.barrier()
+    split_ms, split_ev, rc = [], 0, 0
+    R2 = T2 = None
+    try:
+        for r in range(8):
+            dist.barrier()
+            _, R2, T2, _ = trk.trackFramesSplit(I, Z, kf[0], cur[0])
+            if r >= 3:
+                split_ms.append(ctx.last_timings()[2])
+            split_ev = int(sum(trk.last_result.n_evals))
+    except api.RevoError as e:      # REVO_ERR_COMM: a peer did not answer
+        rc = e.code
+    t = torch.tensor([float(np.median(split_ms)) if split_ms else 0.0, float(rc)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    poses_all = [None] * world
+    dist.all_gather_object(poses_all, None if R2 is None else (np.asarray(R2, np.float32).tobytes(), np.asarray(T2, np.float32).tobytes()))
+    kf.destroy()
+    cur.destroy()
+    if rank != 0:
+        return None
+    from revo_b200 import synth
+
+    ms, s_ms = float(t[0].item()), float(np.median(single_ms))
+    same = all(p is not None and p == poses_all[0] for p in poses_all)
+    d_rot = d_trn = None
+    if R2 is not None:
+        d_rot = synth.rot_angle(np.asarray(R1, np.float64).T @ np.asarray(R2, np.float64))
+        d_trn = float(np.linalg.norm(np.asarray(T1, np.float64) - np.asarray(T2, np.float64)))
+    return {"workload": "BASELINE.json configs[4]: one 1920x1080 pair, 3 levels, edge-point set split over the ranks, one 32-value "
+                        "exchange per evaluation over NVLink inside the persistent kernel (peer-mapped mailboxes, no NCCL call, no host "
+                        "round trip)",
+            "ranks": world, "edge_points_per_level": [int(x) for x in trk.last_result.n_pts[:levels]], "rc_max_over_ranks": int(t[1].item()),
+            "evals_split": split_ev, "evals_single_gpu": single_ev,
+            "kernel_ms_split_max_over_ranks": ms, "us_per_eval_split": 1e3 * ms / max(split_ev, 1),
+            "kernel_ms_single_gpu": s_ms, "us_per_eval_single_gpu": 1e3 * s_ms / max(single_ev, 1),
+            "evals_per_sec_split": split_ev / (ms * 1e-3) if ms > 0 else None,
+            "speedup_vs_single_gpu": (s_ms / max(single_ev, 1)) / (ms / max(split_ev, 1)) if ms > 0 else None,
+            "bit_identical_across_ranks": bool(same), "pose_vs_single_gpu": {"rot_rad": d_rot, "trans_m": d_trn},
+            "limiter": "latency of the per-evaluation exchange: every rank posts 256 B into every peer's mailbox (st.release.sys) and spins "
+                       "on its own (ld.acquire.sys); a 1080p level-0 evaluation on one GPU is ~10 us of gather, so the NVLink round "
+                       "trip (~2-4 us) bounds the speed-up, not bandwidth"}
+
+
+def parity_block(gpu_hist, cpu_hist, n_streams):
+    """GPU vs float32 CPU oracle on the SAME streams, frames and keyframe schedule: distance of the tracker outputs (pose of the
+    frame relative to its keyframe) per stream and step.  Step 1 starts from identical inputs on both sides (identity
+    initial guess); later steps chain each side's own previous result through the motion model."""
+    from revo_b200 import synth
+
+    n = min(len(gpu_hist), len(cpu_hist))
+    rot, trn, same = [], [], []
+    for k in range(n):
+        Tg, Tc = gpu_hist[k][1][:n_streams].astype(np.float64), cpu_hist[k][1][:n_streams].astype(np.float64)
+        eg, ec = gpu_hist[k][2][:n_streams], cpu_hist[k][2][:n_streams]
+        for s_ in range(n_streams):
+            D = np.linalg.inv(Tc[s_]) @ Tg[s_]
+            rot.append(synth.rot_angle(D[:3, :3]))
+            trn.append(float(np.linalg.norm(D[:3, 3])))
+            same.append(bool((eg[s_] == ec[s_]).all()))
+    rot, trn, same = np.array(rot), np.array(trn), np.array(same)
+    first = slice(0, n_streams)
+    q = lambda a, p_: float(np.percentile(a, p_))      # noqa: E731
+    out = {"n_streams": n_streams, "n_frames": n, "reference": "float32 CPU oracle (reference-as-is arithmetic), same frames and keyframe schedule",
+           "rot_rad": {"median": q(rot, 50), "p95": q(rot, 95), "max": float(rot.max())},
+           "trans_m": {"median": q(trn, 50), "p95": q(trn, 95), "max": float(trn.max())},
+           "same_evals_fraction": float(same.mean()),
+           "first_frame": {"rot_rad_median": q(rot[first], 50), "rot_rad_max": float(rot[first].max()), "trans_m_median": q(trn[first], 50),
+                           "trans_m_max": float(trn[first].max()), "same_evals_fraction": float(same[first].mean())},
+           "note": "default termination rules: the accept / convergence tests of the LM loop sit on float-rounding knife edges, so the "
+                   "evaluation counts agree on a fraction of the pairs only (the float32 and float64 oracles differ from each other the "
+                   "same way, tests/test_gpu_parity_population.py); where they agree the poses match to ~1e-6"}
+    if same.any():
+        out["same_evals"] = {"rot_rad_max": float(rot[same].max()), "trans_m_max": float(trn[same].max())}
+    return out
 
 
 def main():
@@ -224,9 +383,10 @@ def main():
                                    f"keyframe every {args.kf_interval} frames; bounded sample: {S} streams x {K} frames per run",
                        "streams_per_step": S},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "omp_threads": r["omp_threads"], "cv2_threads": r["cv2_threads"],
                              "sample": f"{S} streams x {K} timed frames ({r['frames']} frames); OpenCV kernels via cv2 "
-                                       f"{cv2.__version__} ({cv2.getNumThreads()} threads), loops + tracker = C port of the "
-                                       f"reference (OpenMP over independent pairs)"},
+                                       f"{cv2.__version__} ({r['cv2_threads']} threads), loops + tracker = C port of the "
+                                       f"reference (OpenMP over independent pairs, {r['omp_threads']} threads, set explicitly)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "pose_error_vs_ground_truth": {"rot_rad": er, "trans_m": et},
         }
@@ -275,9 +435,10 @@ def main():
 
     build_ctx = api.Context(local_rank)    # second stream: upload + pyramid build of frame k+1 overlap tracking of frame k
 
-    def timed_run(src_bgr, src_depth, sample_clocks, pipelined=False, K=K):
+    def timed_run(src_bgr, src_depth, sample_clocks, pipelined=False, K=K, keep_history=False):
         be = CudaBackend(ctx, settings, build_ctx=build_ctx if pipelined else None)
         st = StreamTracker(be, B, args.kf_interval)
+        st.keep_history = keep_history
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
             sampler.start()     # sampled from the warm-up on: the GPU is under the same load throughout
@@ -325,7 +486,7 @@ def main():
             ms = float(t.item())
         res = dict(ms=ms, wall=wall, evals=st.total_evals - ev0, point_evals=st.total_point_evals - pe0,
                    launches=ctx.launch_count + build_ctx.launch_count - l0, step_wall=step_wall, upload_ms=upload_ms, k9_ms=k9_ms, pyr_ms=pyr_ms, kf_ms=kf_ms, T_w_c=st.T_w_c.copy(), clocks=clocks,
-                   n_pts=st.last["n_pts"].mean(axis=0).tolist(), n_evals=st.last["n_evals"].mean(axis=0).tolist())
+                   n_pts=st.last["n_pts"].mean(axis=0).tolist(), n_evals=st.last["n_evals"].mean(axis=0).tolist(), history=st.history)
         st.close()
         return res
 
@@ -336,7 +497,7 @@ def main():
 
     note(f"inputs rendered: {n_frames} frames x {B} streams")
     # inputs resident in HBM; the same two-stream pipeline as the end-to-end run (build of frame k+1 overlaps tracking of k)
-    dev_run = timed_run(bgr_d, depth_d, sample_clocks=True, pipelined=not args.no_pipeline)
+    dev_run = timed_run(bgr_d, depth_d, sample_clocks=True, pipelined=not args.no_pipeline, keep_history=True)
     note("device-resident run done; host ms per step: " + " ".join(f"{x:.2f}" for x in dev_run["step_wall"]))
     # pinned host inputs, H2D inside the timed region; the upload + pyramid build of frame k+1 run on a second stream
     # while frame k is tracked (same public API, two contexts)
@@ -388,6 +549,11 @@ def main():
         except Exception:
             traffic = None
 
+    edge_split = None
+    if world > 1 and not args.no_extras:
+        edge_split = extra_edge_split(torch, dist, api, synth_torch, ctx, rank, world, local_rank)
+        note("edge-split block done")
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -428,6 +594,30 @@ def main():
         "clocks": dev_run["clocks"],
     }
 
+    # pyramid build against ITS roofline: SURVEY 8(d) algorithmic bytes per frame / CUDA-event time of the build phase
+    lv_px = [(w >> l) * (h >> l) for l in range(args.levels)]
+    pts_per_frame = float(sum(dev_run["n_pts"][:args.levels]))
+    pyr_bytes_frame = 16.0 * lv_px[0] + 12.0 * sum(lv_px[1:]) + 16.0 * pts_per_frame
+    kf_bytes_frame = 25.0 * sum(lv_px)
+    pyr_s, kf_s = iso_run["pyr_ms"] / K_iso * 1e-3, iso_run["kf_ms"] / max(1, sum(1 for i in range(W + 1, W + 1 + K_iso) if i % args.kf_interval == 0)) * 1e-3
+    line["roofline_pyramid"] = {
+        "bound": "hbm", "unit": "GB/s", "peak": peak,
+        "build": {"algorithmic_bytes_per_frame": pyr_bytes_frame, "achieved": pyr_bytes_frame * B / pyr_s / 1e9 if pyr_s > 0 else None,
+                  "frac": pyr_bytes_frame * B / pyr_s / 1e9 / peak if pyr_s > 0 else None, "ms_per_batch": pyr_s * 1e3},
+        "keyframe": {"algorithmic_bytes_per_frame": kf_bytes_frame, "achieved": kf_bytes_frame * B / kf_s / 1e9 if kf_s > 0 else None,
+                     "frac": kf_bytes_frame * B / kf_s / 1e9 / peak if kf_s > 0 else None, "ms_per_promotion": kf_s * 1e3},
+        "note": "bytes: 16 B/px level 0, 12 B/px levels >= 1, 16 B per edge point; keyframe promotion 25 B/px (SURVEY.md 8d)"}
+
+    if edge_split is not None:
+        line["edge_split"] = edge_split
+
+    if world == 1 and not args.no_extras:
+        line["single_stream"] = extra_single_pair(torch, api, synth_torch, ctx, local_rank, 640, 480, 3, seed=1, reps=30,
+                                                  label="BASELINE.json configs[0]: one 640x480 pair stream, 3-level pyramid")
+        line["config3"] = extra_single_pair(torch, api, synth_torch, ctx, local_rank, 1280, 960, 5, seed=3, reps=10,
+                                            label="BASELINE.json configs[2]: one 1280x960 pair, 5-level pyramid, Huber weights")
+        note("single-pair extras done")
+
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
 
@@ -437,9 +627,13 @@ def main():
         S = min(args.ref_streams, B)
         r = run_cpu(args, bgr_h.numpy(), depth16_h.numpy().view(np.uint16), cam, S, min(K, 40), 1, fidx)
         line["cpu_baseline"] = {"value": r["frames"] / r["seconds"], "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                "omp_threads": r["omp_threads"], "cv2_threads": r["cv2_threads"],
                                 "gn_iters_per_sec": r["evals"] / r["seconds"],
                                 "sample": f"{S} of the {B} streams x {min(K, 40)} frames ({r['frames']} frames, {r['seconds']:.1f} s); "
-                                          f"cv2 {cv2.__version__} ({cv2.getNumThreads()} threads) + C port of the reference loops/tracker"}
+                                          f"cv2 {cv2.__version__} ({r['cv2_threads']} threads) + C port of the reference loops/tracker "
+                                          f"(OpenMP over pairs, {r['omp_threads']} threads, set explicitly)"}
+        # parity on the benchmarked workload: the GPU's poses against the CPU oracle's on the shared streams
+        line["parity"] = parity_block(dev_run["history"], r["history"], S)
     print(json.dumps(line))
     sys.stderr.write(f"[bench] {value:.0f} frames/s (e2e {e2e:.0f}), {line['gn_iters_per_sec']:.0f} GN-iters/s, step {dev_run['ms'] / K:.2f} ms = "
                      f"pyr {iso_run['pyr_ms'] / K_iso:.2f} + kf {iso_run['kf_ms'] / K_iso:.2f} + track {iso_run['k9_ms'] / K_iso:.2f} ms (serial {iso_run['ms'] / K_iso:.2f}), "

@@ -117,6 +117,11 @@ class Oracle:
         L.orc_edges3d.restype = C.c_int
         L.orc_track_frames.restype = C.c_int
 
+    def set_num_threads(self, n: int) -> int:
+        """Threads of the OpenMP batch harness (``track_frames_batch``); returns the count in effect."""
+        self.lib.orc_set_num_threads.restype = C.c_int
+        return int(self.lib.orc_set_num_threads(C.c_int(int(n))))
+
     # -- helpers ---------------------------------------------------------
     def _r(self, a):
         return np.ascontiguousarray(np.asarray(a, dtype=self.np_real))

@@ -644,6 +644,21 @@ ORC_API int orc_track_frames_traced(const orc_level *levels, int min_lvl, int ma
     return 0;
 }
 
+/* Thread count of the OpenMP batch harness (bench.py pins it explicitly: torch.distributed.run exports OMP_NUM_THREADS=1). */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+ORC_API int orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 /* Batch of independent frame pairs over OpenMP threads: the CPU-baseline
  * harness ("all host threads the reference path can use": the reference
  * tracker itself is single-threaded per pair). levels is n_pairs*6 entries. */

@@ -47,6 +47,8 @@ class StreamTracker:
         self.total_evals = 0
         self.total_point_evals = 0          # sum over pairs/levels of n_pts * n_evals (roofline numerator / 60 B)
         self.last = None
+        self.keep_history = False           # bench.py parity block: per-step world poses and evaluation counts
+        self.history = []
         self._pending = []                  # batches whose upload + build are in flight, oldest first
 
     def start(self, bgr, depth):
@@ -88,6 +90,8 @@ class StreamTracker:
         self.total_evals += int(out["n_evals"].sum())
         self.total_point_evals += int((out["n_evals"].astype(np.int64) * out["n_pts"].astype(np.int64)).sum())
         self.last = out
+        if self.keep_history:
+            self.history.append((self.T_w_c.copy(), T_kf_n.copy(), np.asarray(out["n_evals"]).copy()))
         if self.prev is not None:
             self.be.destroy(self.prev)
         if self.frame % self.kf_interval == 0:
