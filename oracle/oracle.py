@@ -9,7 +9,7 @@ orchestration of the reference's pyramid constructor
   reference pins "OpenCV 3", ``CMakeLists.txt:46``), the hand-written loops go
   to the C restatement.  This is the parity anchor.
 * ``backend="c"``    -- everything through the dependency-free C restatement;
-  ``tests/test_oracle_cv2.py`` proves it bit-identical to the cv2 flavour.
+  ``tests/test_oracle.py`` proves it bit-identical to the cv2 flavour.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs may import this module.

@@ -12,7 +12,7 @@
  * reference tree is restated from the published algorithm:
  *   - OpenCV imgproc (reference pins "OpenCV 3", CMakeLists.txt:46): cvtColor,
  *     pyrDown, Canny(aperture 3, L2gradient), distanceTransform(L2, PRECISE).
- *     Parity target is python cv2 4.13 in this image; tests/test_oracle_cv2.py
+ *     Parity target is python cv2 4.13 in this image; tests/test_oracle.py
  *     pins each restatement bit-exactly against cv2.
  *   - Eigen >=3.3 (CMakeLists.txt:128, README.md:20): fixed-size products,
  *     LDLT<Matrix6f> (pivoted), Quaternion<->Matrix3 conversions.
@@ -25,11 +25,15 @@
  * REAL=double -> "truth".  Inputs (point lists, lookup structure) are float32
  * in both, as in the reference.
  *
- * PARITY STATUS: REVO itself ships no tests and cannot be compiled in this
- * image (needs Eigen/OpenCV C++/Boost).  The optimizer/tracker part of this
- * oracle is therefore "parity unpinned" by reference tests; it is pinned only
- * (a) for SE3 exp / product by Sophus' KATs and sympy, (b) for the OpenCV
- * kernels against cv2 outputs, (c) for LDLT against numpy.linalg.solve.
+ * PARITY STATUS: REVO ships no tests and its build (CMake, Eigen, OpenCV C++, Boost) cannot run in this image, but
+ * its hot-path SOURCES compile from where they lie: `make -C oracle ref` builds imgpyramidrgbd.cpp, optimizer.cpp,
+ * tracker.cpp, LGSX.h (+ Logging.cpp) verbatim against the API shims of oracle/shim/ into oracle/_ref/librevo_ref.so.
+ * tests/test_oracle_ref.py pins this restatement to that library -- every pyramid array, Optimizer::trackFrames
+ * (evaluation count, LM trace, pose, residual info), the evaluation record, TrackerNew::trackFrames, evalCostFunction, the
+ * quality vote -- BIT FOR BIT in float32, and tests/golden/ref_golden.npz (tests/golden/make_ref_golden.py) carries the
+ * same outputs to machines without /root/reference.  What the shims themselves supply (not reference code) is pinned
+ * separately: (a) SE3 exp / product by Sophus' KATs and sympy, (b) the four OpenCV kernels against cv2 4.13 outputs,
+ * (c) LDLT (Eigen's published algorithm, restated) against numpy.linalg.solve.
  */
 #include <math.h>
 #include <stdint.h>

@@ -1,0 +1,1 @@
+#include "../mini_cv.h"

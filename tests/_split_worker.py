@@ -36,6 +36,19 @@ def main():
     dist.all_gather_object(blobs, blob)
     trk.splitOpen(b"".join(blobs))
     dist.barrier()
+    absent = os.environ.get("REVO_SPLIT_TEST_ABSENT_RANK")
+    if absent is not None:
+        # watchdog test: one rank never launches; the others must return REVO_ERR_COMM after the watchdog period
+        comm_rc = 0
+        if rank != int(absent):
+            try:
+                trk.trackFramesSplit(np.eye(3), np.zeros(3), key, cur)
+            except api.RevoError as e:
+                comm_rc = e.code
+        np.savez(os.path.join(out_dir, f"split{rank}.npz"), comm_rc=np.array(comm_rc))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     s2, R2, T2, e2 = trk.trackFramesSplit(np.eye(3), np.zeros(3), key, cur)
     ev2 = list(trk.last_result.n_evals)
     # a second launch re-uses the mailboxes (sequence numbers must keep them apart)

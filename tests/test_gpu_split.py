@@ -20,18 +20,39 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("w,h", [(640, 480)])
-def test_edge_split_two_gpus(tmp_path, w, h):
+@pytest.mark.parametrize("world,w,h", [(2, 640, 480), (2, 1920, 1080), (4, 1920, 1080), (8, 1920, 1080)])
+def test_edge_split(tmp_path, world, w, h):
+    """BASELINE configs[4] at 2 / 4 / 8 ranks (1920x1080: the configuration itself; VGA: the small case)."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = str(29551 + world)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", port, os.path.join(ROOT, "tests", "_split_worker.py"), str(tmp_path), str(w), str(h)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = [np.load(tmp_path / f"split{k}.npz") for k in range(world)]
+    a = res[0]
+    for b in res[1:]:
+        assert np.array_equal(a["R2"], b["R2"]) and np.array_equal(a["T2"], b["T2"])      # ranks agree bit for bit
+        assert list(a["s"]) == list(b["s"]) and list(a["ev2"]) == list(b["ev2"])
+    assert np.array_equal(a["R2"], a["R3"]) and np.array_equal(a["T2"], a["T3"])          # second launch identical
+    # the split only changes the summation order of the record: same optimum, possibly another LM trace
+    assert rot_angle(a["R1"], a["R2"]) <= 3e-4 and np.linalg.norm(a["T1"] - a["T2"]) <= 1e-3
+    if list(a["ev1"]) == list(a["ev2"]):
+        assert rot_angle(a["R1"], a["R2"]) <= 1e-5 and np.linalg.norm(a["T1"] - a["T2"]) <= 1e-5
+    print("evals single", a["ev1"], "split", a["ev2"])
+
+
+def test_edge_split_reports_a_missing_peer(tmp_path):
+    """A rank whose peer never launches must come back with REVO_ERR_COMM (watchdog in k_track), not hang and not return a
+    pose computed from a partial record."""
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29551")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29571", REVO_SPLIT_TEST_ABSENT_RANK="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29551", os.path.join(ROOT, "tests", "_split_worker.py"), str(tmp_path), str(w), str(h)]
+           "--master-port", "29571", os.path.join(ROOT, "tests", "_split_worker.py"), str(tmp_path), "320", "240"]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    a, b = [np.load(tmp_path / f"split{k}.npz") for k in range(2)]
-    assert np.array_equal(a["R2"], b["R2"]) and np.array_equal(a["T2"], b["T2"])          # ranks agree bit for bit
-    assert np.array_equal(a["R2"], a["R3"]) and np.array_equal(a["T2"], a["T3"])          # second launch identical
-    assert rot_angle(a["R1"], a["R2"]) <= 2e-4 and np.linalg.norm(a["T1"] - a["T2"]) <= 2e-4
-    assert list(a["s"]) == list(b["s"])
-    print("evals single", a["ev1"], "split", a["ev2"])
+    a = np.load(tmp_path / "split0.npz")
+    assert int(a["comm_rc"]) == 9, a["comm_rc"]
