@@ -863,7 +863,10 @@ static int launch_canny_bits(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w
         LAUNCH_CHECK(ctx);
     }
     {
-        int warps = cdiv(h, 8);
+        // a warp owns a band of up to 30 rows (16 warps at VGA: two CTAs per SM, so 256 images run in ONE wave on 148 SMs and
+        // an SM always has a second image to work on while the first sits at its round barrier)
+        static const int band = getenv("REVO_HYST_BAND") ? atoi(getenv("REVO_HYST_BAND")) : 30;
+        int warps = cdiv(h, band);
         warps = warps < 1 ? 1 : (warps > 32 ? 32 : warps);
         const size_t smem = (size_t)2 * wp64 * 8 * h;
         if (smem <= 200 * 1024 && cdiv(h, warps) <= 32) {

@@ -221,6 +221,14 @@ int revo_ctx_create(int device, revo_ctx **out)
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (auto &st : ctx->lvl_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->depth_stream, cudaStreamNonBlocking);
+    for (auto &e : ctx->lvl_gray) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : ctx->lvl_depth) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->lvl_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->lvl_canny0, cudaEventDisableTiming);
+    for (auto &e : ctx->lvl_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : ctx->lvl_fill) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->pinned_kf_read, cudaEventDisableTiming);
     for (auto &e : ctx->stage_consumed) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     (void)cudaGetLastError();
@@ -242,6 +250,15 @@ int revo_ctx_destroy(revo_ctx *ctx)
     cudaEventDestroy(ctx->pinned_kf_read);
     for (int i = 0; i < 2; ++i) { if (ctx->stage[i]) cudaFree(ctx->stage[i]); cudaEventDestroy(ctx->stage_consumed[i]); }
     for (auto &e : ctx->ev) cudaEventDestroy(e);
+    for (auto &st : ctx->lvl_stream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    cudaStreamSynchronize(ctx->depth_stream);
+    cudaStreamDestroy(ctx->depth_stream);
+    for (auto &e : ctx->lvl_gray) cudaEventDestroy(e);
+    for (auto &e : ctx->lvl_depth) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->lvl_fork);
+    cudaEventDestroy(ctx->lvl_canny0);
+    for (auto &e : ctx->lvl_done) cudaEventDestroy(e);
+    for (auto &e : ctx->lvl_fill) cudaEventDestroy(e);
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
@@ -396,6 +413,15 @@ static int create_batch_impl(revo_ctx *ctx, const revo_pyr_config *cfg, const re
     uint8_t *base = (uint8_t *)slab->mem;
     auto chunk = [&](size_t o, size_t per_frame, int f) { return base + o + align_up(per_frame, 256) * (size_t)f; };
 
+    size_t lbl_off[REVO_MAX_LEVELS];
+    const size_t cnt_region = align_up((size_t)w0 * h0 / 64 + 256, 256);      // >= 4 (w/P)(h/P) bytes on every level (P = 20 >> l)
+    {
+        size_t o = 0;
+        for (int l = 0; l < NL; ++l) { lbl_off[l] = o; o += align_up((size_t)g[l].w * g[l].h / 2 + 4096, 256); }
+        bool fits = lbl_off[NL - 1] + (size_t)g[NL - 1].w * g[NL - 1].h * 4 <= (size_t)w0 * h0 * 4 && (size_t)NL * cnt_region <= (size_t)w0 * h0;
+        for (int l = 0; l < NL; ++l) fits = fits && (size_t)std::max(1, g[l].hist_w * g[l].hist_h) * 4 <= cnt_region;
+        if (!fits) return REVO_ERR_UNSUPPORTED;      // tiny images with many levels
+    }
     std::vector<revo_pyr *> pyrs(n);
     std::vector<ImgLevel> host_desc((size_t)NL * n);
     for (int f = 0; f < n; ++f) {
@@ -414,8 +440,12 @@ static int create_batch_impl(revo_ctx *ctx, const revo_pyr_config *cfg, const re
             L.n_pts = (int *)(base + o_counters) + ((size_t)f * NL + l) * 2;
             L.nz_patches = L.n_pts + 1;
             L.tile_off = (int *)chunk(o_toff[l], ((size_t)g[l].n_tiles + 1) * 4, f);
-            L.labels = (int *)chunk(o_labels, (size_t)w0 * h0 * 4, f);
-            L.flags = chunk(o_flags, (size_t)w0 * h0, f);
+            // every level owns its part of the frame's scratch planes, so that the levels' chains can run concurrently: the
+            // label plane (4 B per level-0 pixel) holds the Canny bit masks and the compaction's group counts (< w h / 2 bytes
+            // per level) and, for keyframes, the EDT column distances (4 w h bytes, level by level); the flags plane the integer
+            // patch counters of the histogram (w0 h0 / 64 bytes per level)
+            L.labels = (int *)(chunk(o_labels, (size_t)w0 * h0 * 4, f) + lbl_off[l]);
+            L.flags = chunk(o_flags, (size_t)w0 * h0, f) + (size_t)l * cnt_region;
             L.dt = nullptr; L.opt = nullptr;
             L.w = g[l].w; L.h = g[l].h; L.pts_cap = g[l].cap; L.patch = g[l].patch;
             L.hist_w = g[l].hist_w; L.hist_h = g[l].hist_h;
@@ -496,27 +526,62 @@ static int create_batch_impl(revo_ctx *ctx, const revo_pyr_config *cfg, const re
     if (hi > 0) hi *= hi;
     const int low = (int)floor(lo), high = (int)floor(hi);
 
-    cudaEventRecord(ctx->ev[0], ctx->stream);
-    rc = launch_gray(ctx, d_bgr, (size_t)w0 * channels, channels, bgr_frame, slab->d_desc[0], n, w0, h0);
-    if (!rc && depth16) rc = launch_depth_u16(ctx, depth16, (size_t)w0 * h0, depth_scale, slab->d_desc[0], n, w0 * h0);
+    // Launch structure: the level-0 Canny -> compaction chain (the longest) starts right behind the gray kernel; the gray
+    // pyramid continues on the main stream and releases the chain of every level as its image appears; the depth pyramid runs
+    // on its own stream (only the compaction of a level needs it).  Everything joins the main stream at the end.
+    static const int serial_levels = getenv("REVO_PYR_SERIAL") ? atoi(getenv("REVO_PYR_SERIAL")) : 0;
+    const bool fork = NL > 1 && !serial_levels;
+    cudaStream_t main_stream = ctx->stream;
+    cudaEventRecord(ctx->ev[0], main_stream);
+    if (depth16) rc = launch_depth_u16(ctx, depth16, (size_t)w0 * h0, depth_scale, slab->d_desc[0], n, w0 * h0);
+    if (fork) {
+        cudaEventRecord(ctx->lvl_fork, main_stream);           // inputs (and the level-0 depth) are on the device
+        ctx->stream = ctx->depth_stream;
+        cudaStreamWaitEvent(ctx->stream, ctx->lvl_fork, 0);
+        for (int l = 1; l < NL && !rc; ++l) {
+            rc = launch_depth_half(ctx, slab->d_desc[l - 1], slab->d_desc[l], n, g[l].w, g[l].h, g[l - 1].w);
+            cudaEventRecord(ctx->lvl_depth[l], ctx->stream);
+        }
+        ctx->stream = main_stream;
+    }
+    if (!rc) rc = launch_gray(ctx, d_bgr, (size_t)w0 * channels, channels, bgr_frame, slab->d_desc[0], n, w0, h0);
     if (stage_slot >= 0) {
-        cudaEventRecord(ctx->stage_consumed[stage_slot], ctx->stream);
+        cudaEventRecord(ctx->stage_consumed[stage_slot], main_stream);     // (the depth stream read the staging buffer before lvl_fork)
         ctx->stage_used[stage_slot] = true;
     }
     for (int l = 0; l < NL && !rc; ++l) {
-        if (l > 0) rc = launch_pyrdown_depth(ctx, slab->d_desc[l - 1], slab->d_desc[l], n, g[l].w, g[l].h, g[l - 1].w, g[l - 1].h);
+        if (l > 0) {
+            if (fork) rc = launch_pyrdown(ctx, slab->d_desc[l - 1], slab->d_desc[l], n, g[l].w, g[l].h, g[l - 1].w, g[l - 1].h);
+            else rc = launch_pyrdown_depth(ctx, slab->d_desc[l - 1], slab->d_desc[l], n, g[l].w, g[l].h, g[l - 1].w, g[l - 1].h);
+        }
+        if (fork) {
+            cudaEventRecord(ctx->lvl_gray[l], main_stream);
+            ctx->stream = ctx->lvl_stream[l];          // the launchers enqueue on ctx->stream
+            cudaStreamWaitEvent(ctx->stream, ctx->lvl_gray[l], 0);
+        }
         if (!rc) {
             alignas(64) unsigned char tmap[128];
             const bool tma = make_gray_tensor_map(tmap, base + o_gray[l], g[l].w, g[l].h, n, align_up((size_t)g[l].w * g[l].h, 256));
-            rc = launch_canny(ctx, slab->d_desc[l], n, g[l].w, g[l].h, low, high, tma ? tmap : nullptr, g[l].patch, base + o_flags,
-                              align_up((size_t)w0 * h0, 256));
+            rc = launch_canny(ctx, slab->d_desc[l], n, g[l].w, g[l].h, low, high, tma ? tmap : nullptr, g[l].patch,
+                              base + o_flags + (size_t)l * cnt_region, align_up((size_t)w0 * h0, 256));
         }
-        // fill-in is only defined for the reference's 3 patch sizes (levels 1,2); see SURVEY D5
+        // fill-in is only defined for the reference's 3 patch sizes (levels 1,2); see SURVEY D5.  It reads the FINAL edge map
+        // of the level above (after that level's own fill-in).
         const bool fill = cfg->use_edge_hist && l >= 1 && l <= 2;
+        if (fork && l == 0) cudaEventRecord(ctx->lvl_canny0, ctx->stream);
+        if (fork && fill) cudaStreamWaitEvent(ctx->stream, l == 1 ? ctx->lvl_canny0 : ctx->lvl_fill[l - 1], 0);
         if (!rc) rc = launch_hist_fill(ctx, slab->d_desc[l], l > 0 ? slab->d_desc[l - 1] : nullptr, n, g[l].w, g[l].h,
                                       g[l].patch, l > 0 ? g[l - 1].patch : g[l].patch, fill, cfg->n_percentage);
+        if (fork && l >= 1) {
+            cudaEventRecord(ctx->lvl_fill[l], ctx->stream);
+            cudaStreamWaitEvent(ctx->stream, ctx->lvl_depth[l], 0);        // the compaction reads the level's depth image
+        }
         if (!rc) rc = launch_compact(ctx, slab->d_desc[l], n, g[l].w, g[l].h, cfg->depth_min, cfg->depth_max);
+        if (fork) cudaEventRecord(ctx->lvl_done[l], ctx->stream);
+        ctx->stream = main_stream;
     }
+    if (fork)
+        for (int l = 0; l < NL; ++l) cudaStreamWaitEvent(main_stream, ctx->lvl_done[l], 0);
     if (rc) return fail(rc);
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->ev_valid[0] = true;

@@ -93,6 +93,10 @@ struct revo_ctx {
     int stage_next;
     int track_ctas_per_pair;
     int track_threads;
+    // pyramid construction: the Canny / compaction chains of the levels run on their own streams between a fork after the gray /
+    // depth pyramids and a join before the build-complete event (the small levels hide under level 0)
+    cudaStream_t lvl_stream[REVO_MAX_LEVELS], depth_stream;
+    cudaEvent_t lvl_fork, lvl_done[REVO_MAX_LEVELS], lvl_canny0, lvl_fill[REVO_MAX_LEVELS], lvl_gray[REVO_MAX_LEVELS], lvl_depth[REVO_MAX_LEVELS];
     cudaEvent_t ev[8];      // pyramid begin/end, keyframe begin/end, track kernel begin/end, upload begin/end (copy stream)
     bool ev_valid[4];
     // split mode (multi-GPU single pair)
@@ -134,6 +138,8 @@ int launch_gray(revo_ctx *ctx, const uint8_t *d_bgr, size_t stride, int ch, size
 int launch_depth_u16(revo_ctx *ctx, const uint16_t *d_raw, size_t frame_px, float scale, const ImgLevel *d_desc, int n, int px);
 int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst,
                          int w_src, int h_src);
+int launch_pyrdown(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst, int w_src, int h_src);
+int launch_depth_half(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst, int w_src);
 // gray_tmap: host pointer to a CUtensorMap made by make_gray_tensor_map (nullptr = plain loads)
 // Also produces the patch histogram (hist, nz_patches) of the Canny output; d_counts0/counts_stride: the per-frame
 // scratch (ImgLevel::flags of frame 0, byte stride between frames) used for the integer counters.

@@ -224,15 +224,28 @@ __global__ void __launch_bounds__(256) k_depth_half(const ImgLevel *__restrict__
     }
 }
 
-int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst,
-                         int w_src, int h_src)
+int launch_pyrdown(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst, int w_src, int h_src)
 {
     dim3 block(32, 8), grid(cdiv(cdiv(w_dst, 4), 32), cdiv(h_dst, 8), n);
     k_pyrdown<<<grid, block, 0, ctx->stream>>>(d_src, d_dst, w_src, h_src, w_dst, h_dst);
     LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
+int launch_depth_half(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst, int w_src)
+{
+    dim3 block(32, 8), grid(cdiv(cdiv(w_dst, 4), 32), cdiv(h_dst, 8), n);
     k_depth_half<<<grid, block, 0, ctx->stream>>>(d_src, d_dst, w_src, w_dst, h_dst);
     LAUNCH_CHECK(ctx);
     return REVO_OK;
+}
+
+int launch_pyrdown_depth(revo_ctx *ctx, const ImgLevel *d_src, const ImgLevel *d_dst, int n, int w_dst, int h_dst,
+                         int w_src, int h_src)
+{
+    int rc = launch_pyrdown(ctx, d_src, d_dst, n, w_dst, h_dst, w_src, h_src);
+    if (!rc) rc = launch_depth_half(ctx, d_src, d_dst, n, w_dst, h_dst, w_src);
+    return rc;
 }
 
 // K2 (Canny) lives in canny.cu.

@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_pyramid.py tests/test_gpu_vs_reference.py tests/test_gpu_parity_population.py -m gpu -q -x > gpurun_out/s16_pytest.log 2>&1
+echo "rc=$?"; tail -3 gpurun_out/s16_pytest.log
+for v in "REVO_PYR_SERIAL=1 REVO_HYST_BAND=15" "REVO_PYR_SERIAL=1" "REVO_HYST_BAND=15" ""; do
+  echo "== $v"
+  env $v timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras 2>&1 >/dev/null | tail -1 | cut -c1-260
+done

@@ -181,9 +181,6 @@ def test_canny_tile_fallback_path(ctx, orc32):
         _compare(pg, po, 1)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("REVO_RUN_UNVALIDATED") != "1",
-                    reason="written after the round-1 GPU budget was spent: passes on the emulated library (tests/test_library_on_host.py), "
-                           "not yet run on hardware (set REVO_RUN_UNVALIDATED=1)")
 def test_colored_point_cloud_from_device_arrays(ctx, orc32):
     """ImgPyramidRGBD.generateColoredPcl (viewer export, imgpyramidrgbd.cpp:279-327) over the device's depth / edge arrays
     against the loop restatement over the oracle pyramid, levels 0..2 (colour reduced with pyrDown like the reference)."""

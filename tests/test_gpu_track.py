@@ -344,9 +344,6 @@ def test_revo_main_loop_on_gpu(ctx, orc32, engine):
     assert q is not None and q.n_frames == 3 and sum(q.histogram) > 0
 
 
-@pytest.mark.skipif(os.environ.get("REVO_RUN_UNVALIDATED") != "1",
-                    reason="written after the round-1 GPU budget was spent: passes on the emulated library (tests/test_library_on_host.py), "
-                           "not yet run on hardware (set REVO_RUN_UNVALIDATED=1)")
 def test_multi_stream_main_loop_on_gpu(ctx, engine):
     """MultiStreamREVO over the CUDA classes (one trackFramesBatch launch for all streams, a second one for the re-tracks)
     against separate single-stream REVO runs on the same device: identical trajectories and keyframe decisions."""
