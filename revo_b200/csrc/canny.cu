@@ -738,22 +738,29 @@ __global__ void __launch_bounds__(1024) k_canny_hyst(const ImgLevel *__restrict_
 // DIRTY-ROW worklist instead of blind sweeps.  A row is dirty when one of its two neighbour rows has gained strong bits
 // that hand it a seed it does not have yet (all rows are dirty at the start).  A warp walks the dirty rows of its band
 // downwards, then upwards; visiting a row floods it from its own strong bits and the 8-connected bits of both neighbour
-// rows, and a row that changed marks its neighbours (across band boundaries through a per-warp word in shared memory,
-// taken at the next block barrier).  The first round costs about two floods per row, every later round only touches
-// the handful of rows a weak chain is still creeping along.  wp = row pitch in words of type W.
+// rows, and a row that changed marks its neighbours.  Marks that cross a band boundary are MESSAGES to the neighbour warp
+// (a flag per direction in shared memory); there is no block-wide barrier between rounds: a warp that runs out of dirty rows
+// sleeps on its two flags.  Termination is detected with a token count: every active warp and every raised flag holds one
+// token, a sender adds the token before it raises the flag (and gives it back if the flag was already up), a receiver that
+// was asleep takes the flag's token over, one that was awake destroys it, a warp that falls asleep destroys its own; zero
+// tokens = nobody awake and nothing in flight, for good.  (The round barrier of the previous version was 44 % of this
+// kernel's warp time: profiles/r2_pyramid_kernels_ncu.txt.)  wp = row pitch in words of type W.
 template <typename W>
 __global__ void __launch_bounds__(1024) k_canny_hyst_smem(const ImgLevel *__restrict__ desc, int w, int h, int wp)
 {
     extern __shared__ unsigned long long hs_mem[];
-    __shared__ unsigned incoming[2][32];
+    __shared__ unsigned flag_from_above[32];             // "your first row got a new seed" (from the warp above)
+    __shared__ unsigned flag_from_below[32];             // "your last row got a new seed" (from the warp below)
+    __shared__ int tokens;
     const ImgLevel &L = desc[blockIdx.x];
     const size_t nw = (size_t)wp * h;
     W *gC = (W *)L.labels, *gS = gC + nw;
     W *C = (W *)hs_mem, *S = C + nw;
     for (size_t i = threadIdx.x; i < nw; i += blockDim.x) { C[i] = gC[i]; S[i] = gS[i]; }
-    if (threadIdx.x < 64) incoming[threadIdx.x >> 5][threadIdx.x & 31] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    if (threadIdx.x < 32) { flag_from_above[threadIdx.x] = 0; flag_from_below[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) tokens = n_warps;
+    __syncthreads();
     const int R = (h + n_warps - 1) / n_warps;          // <= 32 (launcher)
     const int y_lo = warp * R, y_hi = min(h, y_lo + R);
     const int n_rows = y_hi > y_lo ? y_hi - y_lo : 0;
@@ -761,13 +768,47 @@ __global__ void __launch_bounds__(1024) k_canny_hyst_smem(const ImgLevel *__rest
     const int col = act ? lane : 0;
     unsigned dirty = n_rows >= 32 ? 0xffffffffu : ((1u << n_rows) - 1u);
     unsigned fresh = dirty;                               // rows not yet flooded from their own strong bits
-    auto row = [&](const W *M, int y) -> W { return act ? M[(size_t)y * wp + col] : (W)0; };
-    for (int it = 0;; ++it) {
-        const int par = it & 1;
-        unsigned inc = 0;
-        if (lane == 0) inc = atomicExch(&incoming[par][warp], 0u);
-        dirty |= __shfl_sync(0xffffffffu, inc, 0);
-        int sent = 0;
+    auto row = [&](const W *M, int y) -> W { return act ? ((const volatile W *)M)[(size_t)y * wp + col] : (W)0; };
+    // raise a flag of a neighbour warp (lane 0): token first, handed back if the flag was already up
+    auto send = [&](unsigned *flag) {
+        __threadfence_block();                            // the strong bits just written are visible before the flag
+        if (lane == 0) {
+            atomicAdd(&tokens, 1);
+            if (atomicExch(flag, 1u)) atomicSub(&tokens, 1);
+        }
+    };
+    bool awake = true;                                    // holds a token
+    while (true) {
+        // mail (lane 0 looks, everybody learns)
+        unsigned mail = 0;
+        if (lane == 0) {
+            if (n_rows > 0) {
+                if (atomicExch(&flag_from_above[warp], 0u)) mail |= 1u;
+                if (atomicExch(&flag_from_below[warp], 0u)) mail |= 2u;
+            }
+        }
+        mail = __shfl_sync(0xffffffffu, mail, 0);
+        if (mail) {
+            __threadfence_block();
+            const int n_tok = ((mail & 1u) ? 1 : 0) + ((mail & 2u) ? 1 : 0);
+            // asleep: one of the flags' tokens becomes this warp's own; every other one is destroyed
+            if (lane == 0 && n_tok - (awake ? 0 : 1) > 0) atomicSub(&tokens, n_tok - (awake ? 0 : 1));
+            awake = true;
+            if (mail & 1u) dirty |= 1u;
+            if (mail & 2u) dirty |= 1u << (n_rows - 1);
+        }
+        if (!dirty) {
+            if (awake) {
+                if (lane == 0) atomicSub(&tokens, 1);
+                awake = false;
+            }
+            int t = 0;
+            if (lane == 0) t = *(volatile int *)&tokens;
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t == 0) break;
+            __nanosleep(40);
+            continue;
+        }
         for (int pass = 0; pass < 2; ++pass) {
             int pos = pass == 0 ? 0 : 32;                 // down: next row >= pos ; up: next row < pos
             while (true) {
@@ -789,35 +830,41 @@ __global__ void __launch_bounds__(1024) k_canny_hyst_smem(const ImgLevel *__rest
                 const W s2 = flood_row<W>(c, s0 | seeds, lane);
                 const W delta = s2 & ~s0;
                 if (!__any_sync(0xffffffffu, delta != 0)) continue;
-                if (delta) S[(size_t)y * wp + col] = s2;
+                if (delta) ((volatile W *)S)[(size_t)y * wp + col] = s2;
+                __syncwarp();
                 // a neighbour row must be (re)visited only if the new bits hand it a seed it does not have yet
                 const W sp = spread_row<W>(delta, lane);
                 if (y > 0 && __any_sync(0xffffffffu, (sp & row(C, y - 1) & ~row(S, y - 1)) != 0)) {
                     if (r > 0) dirty |= 1u << (r - 1);
-                    else { if (lane == 0) atomicOr(&incoming[par ^ 1][warp - 1], 1u << (R - 1)); sent = 1; }
+                    else send(&flag_from_below[warp - 1]);
                 }
                 if (y + 1 < h && __any_sync(0xffffffffu, (sp & row(C, y + 1) & ~row(S, y + 1)) != 0)) {
                     if (r + 1 < n_rows) dirty |= 1u << (r + 1);
-                    else { if (lane == 0) atomicOr(&incoming[par ^ 1][warp + 1], 1u); sent = 1; }
+                    else send(&flag_from_above[warp + 1]);
                 }
             }
         }
-        if (!__syncthreads_or((dirty != 0u) || sent)) break;
     }
+    __syncthreads();
     for (size_t i = threadIdx.x; i < nw; i += blockDim.x) gS[i] = S[i];
 }
 
 // ---- (3) bit mask -> byte maps + patch counters ------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_canny_expand(const ImgLevel *__restrict__ desc, int w, int h, int wp32, int P)
+// One thread -> 16 pixels of a row (half a mask word): one 128-bit store per byte map.  Threads are numbered over the
+// (row, 16-pixel chunk) pairs of the image, so no thread is idle whatever the width.  On the levels that never run the edge
+// fill-in (level 0, levels >= 3) edges_orig IS edges (one plane, one store).
+__global__ void __launch_bounds__(256) k_canny_expand(const ImgLevel *__restrict__ desc, int w, int h, int wp32, int P, int chunks_x)
 {
     const int f = blockIdx.z;
     const ImgLevel &L = desc[f];
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (y >= h || x0 >= w) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = t / chunks_x;
+    const int x0 = (t - y * chunks_x) * 16;
+    if (y >= h) return;
     const unsigned *__restrict__ maskS = (const unsigned *)L.labels + (size_t)wp32 * h;
     const unsigned bits = (__ldcg(maskS + (size_t)y * wp32 + (x0 >> 5)) >> (x0 & 31)) & 0xffffu;
     uint8_t *e = L.edges + (size_t)y * w + x0, *eo = L.edges_orig + (size_t)y * w + x0;
+    const bool two = eo != e;
     unsigned o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -828,11 +875,12 @@ __global__ void __launch_bounds__(256) k_canny_expand(const ImgLevel *__restrict
     if (x0 + 16 <= w && ((((uintptr_t)e) & 15) == 0) && ((((uintptr_t)eo) & 15) == 0)) {
         const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
         *(uint4 *)e = v;
-        *(uint4 *)eo = v;
+        if (two) *(uint4 *)eo = v;
     } else {
         for (int k = 0; k < 16 && x0 + k < w; ++k) {
             const uint8_t v = (bits >> k) & 1u ? 255 : 0;
-            e[k] = v; eo[k] = v;
+            e[k] = v;
+            if (two) eo[k] = v;
         }
     }
     if (bits && L.hist_w > 0 && L.hist_h > 0) {
@@ -884,8 +932,9 @@ static int launch_canny_bits(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w
         LAUNCH_CHECK(ctx);
     }
     {
-        dim3 block(32, 8), grid(cdiv(cdiv(w, 16), 32), cdiv(h, 8), n);
-        k_canny_expand<<<grid, block, 0, ctx->stream>>>(d_desc, w, h, wp32, patch);
+        const int chunks_x = cdiv(w, 16);
+        dim3 grid(cdiv(chunks_x * h, 256), 1, n);
+        k_canny_expand<<<grid, 256, 0, ctx->stream>>>(d_desc, w, h, wp32, patch, chunks_x);
         LAUNCH_CHECK(ctx);
     }
     if (hist_w > 0 && hist_h > 0) {

@@ -434,7 +434,9 @@ static int create_batch_impl(revo_ctx *ctx, const revo_pyr_config *cfg, const re
             L.gray = chunk(o_gray[l], px, f);
             L.depth = (float *)chunk(o_depth[l], px * 4, f);
             L.edges = chunk(o_edges[l], px, f);
-            L.edges_orig = chunk(o_eorig[l], px, f);
+            // edgesOrigPyr differs from edgesPyr only where the edge fill-in may run (levels 1 and 2 with USE_EDGE_HIST,
+            // imgpyramidrgbd.cpp:185-195): elsewhere both names are ONE plane
+            L.edges_orig = (cfg->use_edge_hist && l >= 1 && l <= 2) ? chunk(o_eorig[l], px, f) : L.edges;
             L.hist = chunk(o_hist[l], (size_t)std::max(1, g[l].hist_w * g[l].hist_h), f);
             L.pts = (float4 *)chunk(o_pts[l], (size_t)g[l].cap * 16, f);
             L.n_pts = (int *)(base + o_counters) + ((size_t)f * NL + l) * 2;

@@ -418,13 +418,23 @@ __device__ __forceinline__ unsigned tile_edge_mask(const ImgLevel &L, int tx, in
         for (int c = 0; c < kTileW; ++c)
             if ((e8 >> (8 * c)) & 0xffull) m |= 1u << (r * kTileW + c);
     }
-    // depth test only where an edge pixel is (isfinite, dmin < Z < dmax: imgpyramidrgbd.cpp:210-214)
+    // depth test only where an edge pixel is (isfinite, dmin < Z < dmax: imgpyramidrgbd.cpp:210-214); four loads in flight
+    // per lane (the loop is latency-bound: one dependent global load per set bit otherwise)
     unsigned keep = 0;
+    const float *__restrict__ dp = L.depth + (size_t)y0 * w + x0;
     for (unsigned mm = m; mm;) {
-        const int b = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const float Z = L.depth[(size_t)(y0 + (b >> 3)) * w + x0 + (b & 7)];
-        if (isfinite(Z) && Z > dmin && Z < dmax) keep |= 1u << b;
+        int b[4];
+        float Z[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            b[k] = mm ? __ffs(mm) - 1 : -1;
+            mm &= mm - 1;       // 0 stays 0
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Z[k] = b[k] >= 0 ? __ldg(dp + (size_t)(b[k] >> 3) * w + (b[k] & 7)) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (b[k] >= 0 && isfinite(Z[k]) && Z[k] > dmin && Z[k] < dmax) keep |= 1u << b[k];
     }
     return keep;
 }
@@ -471,15 +481,25 @@ __global__ void __launch_bounds__(256) k_group_scatter(const ImgLevel *__restric
     }
     int o = before + incl - c;
     const int x0 = tx * kTileW, y0 = ty * kTileH;
-    for (unsigned mm = keep; mm; ++o) {
-        const int b = __ffs(mm) - 1;
-        mm &= mm - 1;
-        if (o >= L.pts_cap) break;
-        const int x = x0 + (b & 7), y = y0 + (b >> 3);
-        const float Z = L.depth[(size_t)y * w + x];
-        const float X = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)x, L.cx)), L.fx);
-        const float Y = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)y, L.cy)), L.fy);
-        L.pts[o] = make_float4(X, Y, Z, 1.0f);
+    const float *__restrict__ dp = L.depth + (size_t)y0 * w + x0;
+    for (unsigned mm = keep; mm;) {      // four depth loads in flight per lane
+        int b[4];
+        float Z[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            b[k] = mm ? __ffs(mm) - 1 : -1;
+            mm &= mm - 1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Z[k] = b[k] >= 0 ? __ldg(dp + (size_t)(b[k] >> 3) * w + (b[k] & 7)) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (b[k] < 0 || o >= L.pts_cap) continue;
+            const int x = x0 + (b[k] & 7), y = y0 + (b[k] >> 3);
+            const float X = __fdiv_rn(__fmul_rn(Z[k], __fsub_rn((float)x, L.cx)), L.fx);
+            const float Y = __fdiv_rn(__fmul_rn(Z[k], __fsub_rn((float)y, L.cy)), L.fy);
+            L.pts[o++] = make_float4(X, Y, Z[k], 1.0f);
+        }
     }
     if (g == n_groups - 1) {
         const int total = before + __shfl_sync(0xffffffffu, incl, 31);

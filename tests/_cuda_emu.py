@@ -196,6 +196,9 @@ using std::max;
 using std::min;
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); }
+static inline int atomicSub(int *p, int v) { return __sync_fetch_and_sub(p, v); }
+static inline void __nanosleep(unsigned) { sched_yield(); }
+static inline void __threadfence_block() { __sync_synchronize(); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __sync_fetch_and_add(p, v); }
 static inline long long clock64() { return 0; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
