@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--levels", type=int, default=4)
     ap.add_argument("--kf-interval", type=int, default=10)
+    ap.add_argument("--kf-policy", choices=("interval", "vote"), default="interval",
+                    help="interval: a keyframe every --kf-interval frames (the fixed workload of BASELINE.json configs[1]); vote: the "
+                         "reference's own policy (assessTrackingQuality after every alignment, promote the previous frame and align "
+                         "again on NEW_KF, system.cpp:199-239)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e run without the second (upload/build) stream")
     ap.add_argument("--ctas-per-pair", type=int, default=0)
@@ -107,58 +111,13 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU oracle backend (reference arm / cpu_baseline ONLY -- never on the product path)
 # ---------------------------------------------------------------------------------------------
-class OracleBackend:
-    """The reference's CPU path restated (oracle/): OpenCV kernels through cv2 (all cores), the hand-written
-    loops and the tracker through the C port (tracker: OpenMP over independent pairs)."""
-
-    def __init__(self, cam, n_levels):
-        from oracle import oracle as O
-
-        import cv2
-
-        self.O = O
-        self.orc = O.Oracle("f32")
-        # all host threads, explicitly: torch.distributed.run exports OMP_NUM_THREADS=1, which would throttle this arm ~3x
-        self.cores = os.cpu_count() or 1
-        self.omp_threads = self.orc.set_num_threads(self.cores)
-        cv2.setNumThreads(self.cores)
-        self.cv2_threads = cv2.getNumThreads()
-        self.cfg = O.PyrCfg(n_levels=n_levels)
-        self.cam = cam
-        self.n_levels = n_levels
-        self.ocfg = self.orc.default_cfg()
-
-    def create(self, bgr, depth, n):
-        if depth.dtype == np.uint16:     # the reference's reader: depth.convertTo(CV_32FC1, 1.0f / DEPTH_SCALE_FACTOR), iowrapperRGBD.cpp:327
-            depth = depth.astype(np.float32) * (np.float32(1.0) / np.float32(5000.0))
-        return [self.O.build_pyramid(self.orc, self.cfg, self.cam, bgr[i], depth[i]) for i in range(n)]
-
-    def wait_created(self):
-        pass
-
-    def make_keyframes(self, handles):
-        for p in handles:
-            if not p.dt:
-                self.O.make_keyframe(self.orc, p)
-
-    def track(self, Rs, Ts, refs, curs):
-        r = self.orc.track_frames_batch(refs, curs, list(Rs), list(Ts), self.ocfg, self.n_levels - 1, 0, True)
-        n_pts = np.zeros((len(refs), 6), np.int64)
-        for i, c in enumerate(curs):
-            for l in range(self.n_levels):
-                n_pts[i, l] = len(c.edges3d[l])
-        return dict(R=r["R"].astype(np.float32), T=r["T"].astype(np.float32), status=r["status"], n_evals=r["evals"], n_pts=n_pts)
-
-    def destroy(self, handles):
-        pass
-
-
 def run_cpu(args, bgr_h, depth_h, cam, n_streams, steps, warmup, fidx=lambda i: i):
     """Times `steps` steps of `n_streams` streams on the host cores. bgr_h/depth_h: numpy (F, S, ...)."""
+    from oracle.stream_backend import OracleBackend      # reference arm / cpu_baseline ONLY -- never on the product path
     from revo_b200.stream import StreamTracker
 
     be = OracleBackend(cam, args.levels)
-    st = StreamTracker(be, n_streams, args.kf_interval)
+    st = StreamTracker(be, n_streams, args.kf_interval, args.kf_policy)
     st.keep_history = True
     st.start(bgr_h[0, :n_streams], depth_h[0, :n_streams])
     for i in range(1, warmup + 1):

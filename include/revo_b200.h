@@ -211,6 +211,22 @@ REVO_API int revo_pyr_download(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int 
 REVO_API int revo_pyr_upload_level(revo_ctx *ctx, revo_pyr *pyr, int lvl, const float *pts4, int n,
                                    const float *dt, const float *opt4);
 
+/* generateColoredPcl(lvl, clrPcl, densePcl) -- imgpyramidrgbd.cpp:279-327: the viewer's coloured cloud of level lvl, one column
+ * (X, Y, Z, 1, r, g, b, 1) per pixel with a valid depth (and, unless dense, an edge label), in the reference's column-major scan
+ * order; out receives N columns of 8 floats (Eigen::MatrixXf(8, N)::data()).  bgr: the full-resolution colour image the pyramid
+ * was built from (host or device pointer, `channels` = 3|4): the reference keeps its own clone (rgbFullSize), here the caller
+ * keeps it; it is brought to level lvl by cv::pyrDown like the reference does (levels > 2 give an empty cloud, as there).
+ * *n_out receives N; with out == NULL only the count is produced.  REVO_ERR_BUFFER_TOO_SMALL if capacity_points < N (the
+ * reference sizes its matrix cam.area / 5 for the edge cloud and writes past its end when more points turn up). */
+REVO_API int revo_pyr_colored_pcl(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int dense, const uint8_t *bgr, int channels,
+                                  float *out, size_t capacity_points, int *n_out);
+
+/* TrackerNew::addOldPclAndPose(pcl, worldPose, ts) -- system/tracker.cpp:209-224 keeps a COPY of return3DEdges(histogramLevel)
+ * per past frame: out[i] becomes a handle that owns only a copy of pyrs[i]'s level-`lvl` 3-D edge list (cameras and sizes of all
+ * levels are kept; every other array is absent, downloads of them answer REVO_ERR_UNSUPPORTED), so that the vote's history does
+ * not keep whole frame batches alive.  Valid as `past` of revo_track_quality*; release with revo_pyr_destroy. */
+REVO_API int revo_pyr_copy_points_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs, int lvl, revo_pyr **out);
+
 /* ---- Optimizer / TrackerNew --------------------------------------------- */
 /* One fused evaluation at pose (R,t): PASS A + PASS B of system/optimizer.cpp:74-234.
  * record32: [0..20] upper triangle of sum(w v v^T) in LGS6 slot order (0,0..5),(1,1..5),..,(5,5)
@@ -247,6 +263,12 @@ typedef struct revo_quality_result {
 REVO_API int revo_track_quality(revo_ctx *ctx, const revo_pyr *cur, int hist_level, int n_past, revo_pyr *const *past,
                                 const float *past_world_poses16, const float *estimated_pose16, int n_frames_voting,
                                 revo_quality_result *out);
+/* The same vote for n streams in one launch pair (MultiStreamREVO's keyframe policy): curs[i] is voted on by n_past[i] (<= 3
+ * used) past frames past[3*i + f] with world poses past_world_poses16[(3*i + f)*16 ..], under estimated_poses16[16*i ..].
+ * All current frames must have one size.  One device->host read of n x 16 counters. */
+REVO_API int revo_track_quality_batch(revo_ctx *ctx, int n, revo_pyr *const *curs, int hist_level, const int *n_past,
+                                      revo_pyr *const *past, const float *past_world_poses16, const float *estimated_poses16,
+                                      int n_frames_voting, revo_quality_result *out);
 
 /* Launch-shape override for revo_track_batch (0 = automatic): CTAs per pair (cluster size 1,2,4,8,16)
  * and threads per CTA. */

@@ -100,6 +100,7 @@ EXPORTED_SYMBOLS = [
     "revo_pyr_timestamp", "revo_pyr_num_edges", "revo_pyr_download", "revo_pyr_upload_level", "revo_eval",
     "revo_track_level", "revo_track", "revo_track_batch", "revo_ctx_set_track_shape", "revo_split_export",
     "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve", "revo_ctx_last_upload_ms", "revo_pyr_create_batch_u16", "revo_track_quality", "revo_quat_to_R9", "revo_R9_to_quat",
+    "revo_pyr_colored_pcl", "revo_pyr_copy_points_batch", "revo_track_quality_batch",
 ]
 
 
@@ -141,6 +142,7 @@ def load_library():
     lib.revo_pyr_num_edges.argtypes = [vp, vp, i32, C.POINTER(i32)]
     lib.revo_pyr_download.argtypes = [vp, vp, i32, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.revo_pyr_upload_level.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+    lib.revo_pyr_colored_pcl.argtypes = [vp, vp, i32, i32, vp, i32, vp, C.c_size_t, C.POINTER(i32)]
     lib.revo_eval.argtypes = [vp, C.POINTER(revo_opt_config), vp, vp, i32, vp, vp, vp]
     lib.revo_track_level.argtypes = [vp, C.POINTER(revo_opt_config), vp, vp, i32, vp, vp, C.POINTER(revo_residual_info),
                                      C.POINTER(C.c_float), C.POINTER(i32)]
@@ -149,6 +151,8 @@ def load_library():
                                      i32, vp]
     lib.revo_ctx_set_track_shape.argtypes = [vp, i32, i32]
     lib.revo_track_quality.argtypes = [vp, vp, i32, i32, C.POINTER(vp), vp, vp, i32, C.POINTER(revo_quality_result)]
+    lib.revo_track_quality_batch.argtypes = [vp, i32, C.POINTER(vp), i32, vp, C.POINTER(vp), vp, vp, i32, C.POINTER(revo_quality_result)]
+    lib.revo_pyr_copy_points_batch.argtypes = [vp, i32, C.POINTER(vp), i32, C.POINTER(vp)]
     lib.revo_ctx_set_track_engine.argtypes = [vp, i32, i32]
     lib.revo_ctx_reserve.argtypes = [vp, C.c_size_t]
     lib.revo_ctx_last_upload_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -523,22 +527,22 @@ class ImgPyramidRGBD:
     def isPointOkDepth(self, z) -> bool:
         return bool(np.isfinite(z) and self.mSettings.DEPTH_MIN < z < self.mSettings.DEPTH_MAX)
 
-    def generateColoredPcl(self, lvl: int, densePcl: bool = False) -> np.ndarray:
-        """``generateColoredPcl(lvl, clrPcl, densePcl)`` (imgpyramidrgbd.cpp:279-327): the viewer's coloured cloud, an
-        (8, N) float32 matrix of columns ``(X, Y, Z, 1, r, g, b, 1)``.  Host-side like the reference (not on the hot path):
-        depth and edges come from the device through the accessors, the colour image is the one kept at construction."""
-        if self.rgbFullSize is None:
-            raise RevoError(REVO_ERR_UNSUPPORTED, "generateColoredPcl needs the colour image (pyramid built from a batch handle)")
-        import cv2
-
-        rgb = self.rgbFullSize[:, :, :3]
-        if lvl > 2:                                  # the reference only fills `rgb` for levels 0..2: empty cloud
-            return np.zeros((8, 0), np.float32)
-        for _ in range(lvl):
-            rgb = cv2.pyrDown(rgb)
-        c = self._cam(lvl)
-        return colored_pcl_from_arrays(rgb, self.returnDepth(lvl), self.returnEdges(lvl), c.fx, c.fy, c.cx, c.cy,
-                                       self.mSettings.DEPTH_MIN, self.mSettings.DEPTH_MAX, densePcl)
+    def generateColoredPcl(self, lvl: int, densePcl: bool = False, rgb=None) -> np.ndarray:
+        """``generateColoredPcl(lvl, clrPcl, densePcl)`` (imgpyramidrgbd.cpp:279-327): the viewer's coloured cloud, an (8, N)
+        float32 matrix of columns ``(X, Y, Z, 1, r, g, b, 1)`` in the reference's column-major scan order, compacted on the
+        device (``revo_pyr_colored_pcl``).  ``rgb``: the full-resolution colour image (default: the one kept at construction,
+        like the reference's ``rgbFullSize`` clone; pyramids taken from a batch must pass it)."""
+        rgb = self.rgbFullSize if rgb is None else np.ascontiguousarray(rgb, np.uint8)
+        if rgb is None:
+            raise RevoError(REVO_ERR_INVALID_ARG, "generateColoredPcl needs the colour image (pyramid built from a batch handle)")
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.revo_pyr_colored_pcl(self.ctx.h, self.h, lvl, int(densePcl), rgb.ctypes.data, rgb.shape[2], None, 0,
+                                                         C.byref(n)))
+        out = np.zeros((n.value, 8), np.float32)
+        if n.value:
+            self.ctx.check(self.ctx.lib.revo_pyr_colored_pcl(self.ctx.h, self.h, lvl, int(densePcl), rgb.ctypes.data, rgb.shape[2],
+                                                             out.ctypes.data, n.value, C.byref(n)))
+        return out.T.copy()
 
     # -- test hook -----------------------------------------------------------
     def uploadLevel(self, lvl, pts4=None, dt=None, opt4=None):
@@ -620,6 +624,9 @@ def _handles(frames):
     """(n, ctypes handle array) of a PyramidBatch or a sequence of ImgPyramidRGBD."""
     if isinstance(frames, PyramidBatch):
         return frames.n, frames.arr
+    if isinstance(frames, np.ndarray):        # raw handle values (uint64), see stream.CudaBackend.take
+        assert frames.dtype == np.uint64 and frames.flags.c_contiguous
+        return int(frames.size), frames.ctypes.data_as(C.POINTER(C.c_void_p))
     n = len(frames)
     return n, (C.c_void_p * n)(*[p.h for p in frames])
 
@@ -751,30 +758,39 @@ class TrackerNew:
         return out
 
     # -- tracking-quality vote (tracker.cpp:118-257) -----------------------------------
-    def addOldPclAndPose(self, pyr: ImgPyramidRGBD, worldPose, timeStamp: float = 0.0):
-        """``addOldPclAndPose(pcl, worldPose, ts)`` (tracker.cpp:209-224).  The reference copies ``return3DEdges(histogramLevel)``
-        of the frame; here the frame's pyramid is kept (its list stays on the device) -- it must outlive the vote."""
-        self.mPastPcl.append((pyr, np.asarray(worldPose, np.float32).reshape(4, 4).copy(), float(timeStamp)))
+    def addOldPclAndPose(self, pyr, worldPose, timeStamp: float = 0.0):
+        """``addOldPclAndPose(pcl, worldPose, ts)`` (tracker.cpp:209-224).  Like the reference, which stores
+        ``return3DEdges(histogramLevel)`` by value, the tracker keeps a COPY of that one list (a :class:`PointList` on the
+        device), not the pyramid: the frame and the batch it belongs to can be released.  ``pyr`` may also be a
+        :class:`PointList` made earlier (``copy_point_lists`` copies the lists of many streams in one call)."""
+        pl = pyr if isinstance(pyr, PointList) else copy_point_lists(self.ctx, [pyr], self.histogramLevel)[0]
+        self.mPastPcl.append((pl, np.asarray(worldPose, np.float32).reshape(4, 4).copy(), float(timeStamp)))
+        # The reference's lists grow until the next keyframe (the pop in addOldPclAndPose is commented out there), but only the
+        # FIRST nFramesHistogramVoting entries ever vote (tracker.cpp:138) and clearUpPastLists keeps the LAST ones: entries
+        # in between can never be read again and are dropped here.
+        nv = self.mSettings.nFramesHistogramVoting
+        while len(self.mPastPcl) > 2 * nv:
+            self.mPastPcl.pop(nv)[0].destroy()
 
     def clearUpPastLists(self):
         """tracker.cpp:249-257"""
         while len(self.mPastPcl) > self.mSettings.nFramesHistogramVoting:
-            self.mPastPcl.pop(0)
+            self.mPastPcl.pop(0)[0].destroy()
+
+    def _vote_inputs(self, estimatedPose):
+        """The past lists / world poses that vote (column-major poses, three slots) and the estimated pose."""
+        nv = min(len(self.mPastPcl), self.mSettings.nFramesHistogramVoting, 3)
+        hs = [self.mPastPcl[f][0].h for f in range(nv)] + [None] * (3 - nv)
+        poses = np.zeros((3, 16), np.float32)
+        for f in range(nv):
+            poses[f] = self.mPastPcl[f][1].T.reshape(-1)
+        est = np.asarray(estimatedPose, np.float32).reshape(4, 4).T.reshape(-1)
+        return len(self.mPastPcl), hs, poses, est
 
     def assessTrackingQuality(self, estimatedPose, currFrame: ImgPyramidRGBD) -> int:
         """``TrackerStatus assessTrackingQuality(estimatedPose, currFrame)`` (tracker.cpp:118-201); the counts are kept in
         ``self.last_quality``."""
-        if not self.mPastPcl or not self.mSettings.CHECK_TRACKING_RESULTS:
-            return TRACKER_STATE_OK
-        n = len(self.mPastPcl)
-        arr = (C.c_void_p * n)(*[p[0].h for p in self.mPastPcl])
-        poses = np.ascontiguousarray(np.stack([p[1].T.reshape(-1) for p in self.mPastPcl]), np.float32)   # column-major
-        est = np.ascontiguousarray(np.asarray(estimatedPose, np.float32).reshape(4, 4).T.reshape(-1))
-        res = revo_quality_result()
-        self.ctx.check(self.ctx.lib.revo_track_quality(self.ctx.h, currFrame.h, self.histogramLevel, n, arr, poses.ctypes.data,
-                                                       est.ctypes.data, self.mSettings.nFramesHistogramVoting, C.byref(res)))
-        self.last_quality = res
-        return int(res.status)
+        return assess_tracking_quality_batch([self], [estimatedPose], [currFrame])[0]
 
     # -- multi-GPU split (one process per GPU) ------------------------------------
     def splitExport(self, rank: int, world: int) -> bytes:
@@ -793,6 +809,75 @@ class TrackerNew:
                                                      Tc.ctypes.data, C.byref(res)))
         self.last_result = res
         return int(res.status), _R_from_c(Rc), Tc, float(res.error)
+
+
+class PointList:
+    """A device copy of one level's 3-D edge list (what ``TrackerNew::addOldPclAndPose`` stores, tracker.cpp:209-224)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+
+    def download(self, lvl: int) -> np.ndarray:
+        """(N, 4) float32 in device (tile-major) order."""
+        n = C.c_size_t(0)
+        self.ctx.check(self.ctx.lib.revo_pyr_download(self.ctx.h, self.h, lvl, EDGES3D_DEVICE_ORDER, None, 0, C.byref(n)))
+        out = np.zeros((n.value // 16, 4), np.float32)
+        if n.value:
+            self.ctx.check(self.ctx.lib.revo_pyr_download(self.ctx.h, self.h, lvl, EDGES3D_DEVICE_ORDER, out.ctypes.data, n.value, None))
+        return out
+
+    def destroy(self):
+        if self.h:
+            self.ctx.lib.revo_pyr_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def copy_point_lists(ctx: Context, pyrs, lvl: int) -> List["PointList"]:
+    """``revo_pyr_copy_points_batch``: device copies of the level-``lvl`` 3-D edge lists of many pyramids (one allocation, one
+    launch)."""
+    n, hs = _handles(pyrs)
+    out = (C.c_void_p * n)()
+    ctx.check(ctx.lib.revo_pyr_copy_points_batch(ctx.h, n, hs, lvl, out))
+    return [PointList(ctx, out[i]) for i in range(n)]
+
+
+def assess_tracking_quality_batch(trackers: Sequence["TrackerNew"], estimatedPoses, currFrames) -> List[int]:
+    """``assessTrackingQuality`` of many streams in one launch pair (``revo_track_quality_batch``): tracker ``i`` votes on
+    ``currFrames[i]`` under ``estimatedPoses[i]`` with its own history.  Returns the statuses; every tracker's
+    ``last_quality`` is set like the single call does."""
+    n = len(trackers)
+    status = [TRACKER_STATE_OK] * n
+    todo = [i for i in range(n) if trackers[i].mPastPcl and trackers[i].mSettings.CHECK_TRACKING_RESULTS]
+    if not todo:
+        return status
+    t0 = trackers[todo[0]]
+    ctx = t0.ctx
+    m = len(todo)
+    curs = (C.c_void_p * m)(*[currFrames[i].h for i in todo])
+    past = (C.c_void_p * (3 * m))()
+    n_past = np.zeros(m, np.int32)
+    poses = np.zeros((m, 3, 16), np.float32)
+    est = np.zeros((m, 16), np.float32)
+    for k, i in enumerate(todo):
+        n_past[k], hs, poses[k], est[k] = trackers[i]._vote_inputs(estimatedPoses[i])
+        for f in range(3):
+            past[3 * k + f] = hs[f]
+    res = (revo_quality_result * m)()
+    ctx.check(ctx.lib.revo_track_quality_batch(ctx.h, m, curs, t0.histogramLevel, n_past.ctypes.data, past, poses.ctypes.data,
+                                               est.ctypes.data, t0.mSettings.nFramesHistogramVoting, res))
+    for k, i in enumerate(todo):
+        r = revo_quality_result()
+        C.memmove(C.byref(r), C.byref(res[k]), C.sizeof(revo_quality_result))
+        trackers[i].last_quality = r
+        status[i] = int(r.status)
+    return status
 
 
 def result_R(res_row) -> np.ndarray:

@@ -630,6 +630,9 @@ int revo_pyr_create(revo_ctx *ctx, const revo_pyr_config *cfg, const revo_camera
 }
 
 // A pyramid built on another context's stream: order this context's stream after the build (no host sync).
+// handles made by revo_pyr_copy_points_batch own one point list and nothing else
+static bool points_only(const revo_pyr *p) { return p && !p->lv[0].gray; }
+
 static void wait_for_build(revo_ctx *ctx, const revo_pyr *p)
 {
     if (p && p->slab && p->slab->ready && p->slab->stream != ctx->stream) cudaStreamWaitEvent(ctx->stream, p->slab->ready, 0);
@@ -676,6 +679,7 @@ int revo_pyr_make_keyframe_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs)
     std::vector<revo_pyr *> todo;
     for (int i = 0; i < n; ++i) {
         if (!pyrs[i]) return REVO_ERR_INVALID_ARG;
+        if (points_only(pyrs[i])) return REVO_ERR_UNSUPPORTED;
         if (!pyrs[i]->is_keyframe && std::find(todo.begin(), todo.end(), pyrs[i]) == todo.end()) todo.push_back(pyrs[i]);
     }
     if (todo.empty()) return REVO_OK;
@@ -760,6 +764,67 @@ int revo_pyr_destroy_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs)
     return REVO_OK;
 }
 
+int revo_pyr_copy_points_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs, int lvl, revo_pyr **out)
+{
+    if (!ctx || n < 0 || (n > 0 && (!pyrs || !out))) return REVO_ERR_INVALID_ARG;
+    if (n == 0) return REVO_OK;
+    for (int i = 0; i < n; ++i) {
+        if (!pyrs[i]) return REVO_ERR_INVALID_ARG;
+        if (lvl < 0 || lvl >= pyrs[i]->n_levels || !pyrs[i]->lv[lvl].pts) return REVO_ERR_BAD_LEVEL;
+    }
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    // The lists' lengths live on the device; read them once (the caller is between two frames here, the vote that follows
+    // reads counters back anyway) so that the copies take the lists' size and not their capacity.
+    std::vector<int> cnt((size_t)n);
+    for (int i = 0; i < n; ++i) wait_for_build(ctx, pyrs[i]);
+    {
+        // gather the counts with one kernel-free pass: they sit in the slabs' counter blocks, 2 ints apart per level
+        int rc = ensure_scratch(ctx, align_up(sizeof(PointListCopy) * (size_t)n, 256) + 4 * (size_t)n);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < n; ++i)
+        REVO_CUDA(ctx, cudaMemcpyAsync(&cnt[i], pyrs[i]->lv[lvl].n_pts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<size_t> off((size_t)n + 1);
+    off[0] = align_up(8 * (size_t)n, 256);
+    for (int i = 0; i < n; ++i) off[i + 1] = off[i] + align_up((size_t)std::max(cnt[i], 1) * 16, 256);
+    Slab *slab = new (std::nothrow) Slab();
+    if (!slab) return REVO_ERR_INVALID_ARG;
+    memset(slab, 0, sizeof(*slab));
+    slab->n_frames = n; slab->live = n; slab->bytes = off[n]; slab->stream = ctx->stream;
+    cudaError_t e = cudaMallocAsync(&slab->mem, slab->bytes, ctx->stream);
+    if (e != cudaSuccess) { delete slab; return cuda_fail(ctx, e, "cudaMallocAsync(point lists)"); }
+    std::vector<PointListCopy> tab((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        revo_pyr *p = new revo_pyr();
+        memset(p->lv, 0, sizeof(p->lv));
+        p->slab = slab; p->index_in_slab = i; p->n_levels = pyrs[i]->n_levels; p->cfg = pyrs[i]->cfg; p->cam0 = pyrs[i]->cam0;
+        p->timestamp = pyrs[i]->timestamp; p->kf_slab = nullptr; p->is_keyframe = false;
+        for (int l = 0; l < p->n_levels; ++l) {     // cameras and sizes of every level; arrays only at `lvl`
+            const ImgLevel &S = pyrs[i]->lv[l];
+            ImgLevel &L = p->lv[l];
+            L.w = S.w; L.h = S.h; L.fx = S.fx; L.fy = S.fy; L.cx = S.cx; L.cy = S.cy; L.patch = S.patch; L.hist_w = S.hist_w; L.hist_h = S.hist_h;
+        }
+        ImgLevel &L = p->lv[lvl];
+        L.pts = (float4 *)((uint8_t *)slab->mem + off[i]);
+        L.n_pts = (int *)slab->mem + 2 * i;
+        L.pts_cap = std::max(cnt[i], 1);
+        tab[i] = PointListCopy{pyrs[i]->lv[lvl].pts, pyrs[i]->lv[lvl].n_pts, L.pts, L.n_pts, cnt[i]};
+        out[i] = p;
+    }
+    PointListCopy *d_tab = (PointListCopy *)ctx->scratch;
+    e = cudaMemcpyAsync(d_tab, tab.data(), sizeof(PointListCopy) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = e == cudaSuccess ? launch_copy_point_lists(ctx, d_tab, n) : cuda_fail(ctx, e, "memcpy(point list table)");
+    if (rc) {
+        for (int i = 0; i < n; ++i) { delete out[i]; out[i] = nullptr; }
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeAsync(slab->mem, ctx->stream);
+        delete slab;
+        return rc;
+    }
+    return REVO_OK;
+}
+
 int revo_pyr_is_keyframe(const revo_pyr *pyr) { return pyr && pyr->is_keyframe; }
 double revo_pyr_timestamp(const revo_pyr *pyr) { return pyr ? pyr->timestamp : 0.0; }
 
@@ -776,6 +841,7 @@ int revo_pyr_num_edges(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int *n_out)
 {
     if (!ctx || !pyr || !n_out) return REVO_ERR_INVALID_ARG;
     if (lvl < 0 || lvl >= pyr->n_levels) return REVO_ERR_BAD_LEVEL;
+    if (!pyr->lv[lvl].n_pts) return REVO_ERR_UNSUPPORTED;
     REVO_CUDA(ctx, cudaSetDevice(ctx->device));
     REVO_CUDA(ctx, cudaMemcpyAsync(n_out, pyr->lv[lvl].n_pts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -791,6 +857,7 @@ int revo_pyr_download(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int which, vo
     const size_t px = (size_t)L.w * L.h;
     const void *src = nullptr;
     size_t bytes = 0;
+    if (points_only(pyr) && !(which == REVO_ARRAY_EDGES3D_DEVICE_ORDER && L.pts)) return REVO_ERR_UNSUPPORTED;
     switch (which) {
         case REVO_ARRAY_GRAY: src = L.gray; bytes = px; break;
         case REVO_ARRAY_DEPTH: src = L.depth; bytes = px * 4; break;
@@ -843,6 +910,52 @@ int revo_pyr_download(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int which, vo
     return REVO_OK;
 }
 
+int revo_pyr_colored_pcl(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int dense, const uint8_t *bgr, int channels, float *out,
+                         size_t capacity_points, int *n_out)
+{
+    if (!ctx || !pyr || !bgr || !n_out || (channels != 3 && channels != 4)) return REVO_ERR_INVALID_ARG;
+    if (lvl < 0 || lvl >= pyr->n_levels) return REVO_ERR_BAD_LEVEL;
+    if (points_only(pyr)) return REVO_ERR_UNSUPPORTED;
+    *n_out = 0;
+    if (lvl > 2) return REVO_OK;      // the reference only has a colour image for levels 0..2 (imgpyramidrgbd.cpp:288-297)
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const ImgLevel &L = pyr->lv[lvl];
+    const int w0 = pyr->lv[0].w, h0 = pyr->lv[0].h;
+    // scratch: colour pyramid (two ping-pong planes of the level-0 size) | column offsets | count | descriptor | cloud
+    const size_t b_img = align_up((size_t)w0 * h0 * channels, 256), b_col = align_up((size_t)(L.w + 4) * 4, 256);
+    const size_t b_out = align_up((size_t)L.w * L.h * 32, 256);
+    int rc = ensure_scratch(ctx, 2 * b_img + b_col + 256 + 256 + b_out);
+    if (rc) return rc;
+    uint8_t *s = (uint8_t *)ctx->scratch;
+    uint8_t *img[2] = {s, s + b_img};
+    int *d_col = (int *)(s + 2 * b_img), *d_n = (int *)(s + 2 * b_img + b_col);
+    ImgLevel *d_desc = (ImgLevel *)(s + 2 * b_img + b_col + 256);
+    float *d_out = (float *)(s + 2 * b_img + b_col + 512);
+    wait_for_build(ctx, pyr);
+    REVO_CUDA(ctx, cudaMemcpyAsync(img[0], bgr, (size_t)w0 * h0 * channels, cudaMemcpyDefault, ctx->stream));
+    int cur = 0, cw = w0, chh = h0;
+    for (int l = 0; l < lvl && !rc; ++l) {
+        rc = launch_pyrdown_color(ctx, img[cur], img[cur ^ 1], cw, chh, channels);
+        cw = (cw + 1) / 2; chh = (chh + 1) / 2;
+        cur ^= 1;
+    }
+    if (rc) return rc;
+    if (cw != L.w || chh != L.h) return REVO_ERR_UNSUPPORTED;
+    REVO_CUDA(ctx, cudaMemcpyAsync(d_desc, &L, sizeof(ImgLevel), cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_colored_pcl(ctx, d_desc, L.w, L.h, dense, pyr->cfg.depth_min, pyr->cfg.depth_max, img[cur], channels, out ? d_out : nullptr,
+                            L.w * L.h, d_n, d_col);
+    if (rc) return rc;
+    int n = 0;
+    REVO_CUDA(ctx, cudaMemcpyAsync(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    if (!out) return REVO_OK;
+    if ((size_t)n > capacity_points) return REVO_ERR_BUFFER_TOO_SMALL;
+    if (n) REVO_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)n * 32, cudaMemcpyDefault, ctx->stream));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return REVO_OK;
+}
+
 int revo_pyr_upload_level(revo_ctx *ctx, revo_pyr *pyr, int lvl, const float *pts4, int n, const float *dt, const float *opt4)
 {
     if (!ctx || !pyr) return REVO_ERR_INVALID_ARG;
@@ -880,6 +993,7 @@ static int fill_pair(const revo_pyr *ref, const revo_pyr *cur, int min_lvl, int 
 {
     if (!ref || !cur) return REVO_ERR_INVALID_ARG;
     if (!ref->is_keyframe) return REVO_ERR_NOT_KEYFRAME;
+    if (points_only(cur)) return REVO_ERR_UNSUPPORTED;
     if (min_lvl < max_lvl || max_lvl < 0 || min_lvl >= cur->n_levels || min_lvl >= ref->n_levels) return REVO_ERR_BAD_LEVEL;
     memset(d, 0, sizeof(*d));
     for (int l = max_lvl; l <= min_lvl; ++l) {
@@ -1061,30 +1175,32 @@ static bool invert4(const double *m /* column-major */, double *inv)
     return true;
 }
 
-int revo_track_quality(revo_ctx *ctx, const revo_pyr *cur, int hist_level, int n_past, revo_pyr *const *past,
-                       const float *past_world_poses16, const float *estimated_pose16, int n_frames_voting, revo_quality_result *out)
+// One vote's host half: transforms inv(estimatedPose) * pastWorldPose (tracker.cpp:147), pointers; false = bad argument.
+static int quality_prepare(revo_ctx *ctx, const revo_pyr *cur, int hist_level, int n_past, revo_pyr *const *past, const float *past_world_poses16,
+                           const float *estimated_pose16, int n_frames_voting, QualityArgs &a, revo_quality_result *out)
 {
-    if (!ctx || !cur || !out || n_past < 0 || (n_past > 0 && (!past || !past_world_poses16)) || !estimated_pose16)
-        return REVO_ERR_INVALID_ARG;
-    if (hist_level < 0 || hist_level >= cur->n_levels) return REVO_ERR_BAD_LEVEL;
     memset(out, 0, sizeof(*out));
+    memset(&a, 0, sizeof(a));
     out->status = REVO_TRACKER_STATE_OK;
+    if (!cur || n_past < 0 || (n_past > 0 && (!past || !past_world_poses16)) || !estimated_pose16) return REVO_ERR_INVALID_ARG;
+    if (hist_level < 0 || hist_level >= cur->n_levels) return REVO_ERR_BAD_LEVEL;
     int nf = n_past < n_frames_voting ? n_past : n_frames_voting;
     if (nf > 3) nf = 3;                        // histWeights has four entries (tracker.cpp:231-234)
     out->n_frames = nf > 0 ? nf : 0;
-    if (nf <= 0) return REVO_OK;               // tracker.cpp:121: nothing to vote with
-    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
     const ImgLevel &L = cur->lv[hist_level];
-    QualityArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n_frames = nf; a.fx = L.fx; a.fy = L.fy; a.cx = L.cx; a.cy = L.cy; a.w = L.w; a.h = L.h;
+    a.n_frames = out->n_frames; a.fx = L.fx; a.fy = L.fy; a.cx = L.cx; a.cy = L.cy; a.w = L.w; a.h = L.h;
+    if (points_only(cur)) return REVO_ERR_UNSUPPORTED;
+    a.depth = L.depth;
+    // returnOrigEdges(histogramLevel): the Canny output before the fill-in (imgpyramidrgbd.h:69-77)
+    a.edges = (cur->cfg.use_edge_hist && hist_level > 0) ? L.edges_orig : L.edges;
+    if (nf <= 0) return REVO_OK;               // tracker.cpp:121: nothing to vote with
     double est[16], est_inv[16];
     for (int i = 0; i < 16; ++i) est[i] = estimated_pose16[i];
     if (!invert4(est, est_inv)) return REVO_ERR_INVALID_ARG;
     for (int f = 0; f < nf; ++f) {
-        if (!past[f] || hist_level >= past[f]->n_levels) return REVO_ERR_INVALID_ARG;
+        if (!past[f] || hist_level >= past[f]->n_levels || !past[f]->lv[hist_level].pts) return REVO_ERR_INVALID_ARG;
         const float *pw = past_world_poses16 + 16 * (size_t)f;
-        double tr[16];                          // inv(estimatedPose) * pastWorldPose   (tracker.cpp:147)
+        double tr[16];
         for (int c = 0; c < 4; ++c)
             for (int r = 0; r < 4; ++r) {
                 double s = 0;
@@ -1099,19 +1215,13 @@ int revo_track_quality(revo_ctx *ctx, const revo_pyr *cur, int hist_level, int n
         wait_for_build(ctx, past[f]);
     }
     wait_for_build(ctx, cur);
-    const size_t words = ((size_t)L.w * L.h + 3) / 4;
-    int rc = ensure_scratch(ctx, words * 4 + 256);
-    if (rc) return rc;
-    unsigned *d_mbits = (unsigned *)ctx->scratch;
-    int *d_counters = (int *)((uint8_t *)ctx->scratch + align_up(words * 4, 64));
-    // returnOrigEdges(histogramLevel): the Canny output before the fill-in (imgpyramidrgbd.h:69-77)
-    const uint8_t *d_edges = (cur->cfg.use_edge_hist && hist_level > 0) ? L.edges_orig : L.edges;
-    rc = launch_quality(ctx, a, L.depth, d_edges, cur->cfg.depth_min, cur->cfg.depth_max, d_mbits, d_counters);
-    if (rc) return rc;
-    int c[16];
-    REVO_CUDA(ctx, cudaMemcpyAsync(c, d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
-    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return REVO_OK;
+}
+
+static void quality_finish(const int *c, revo_quality_result *out)
+{
     static const float kHistWeights[4] = {0.f, 1.f, 1.25f, 1.5f};
+    const int nf = out->n_frames;
     float measure = 0.f;
     for (int k = 0; k < 4; ++k) { out->histogram[k] = c[k]; out->overlaps[k] = c[4 + k]; }
     for (int k = 1; k <= nf; ++k) measure += (float)c[4 + k] * kHistWeights[k];     // tracker.cpp:176-181
@@ -1119,7 +1229,56 @@ int revo_track_quality(revo_ctx *ctx, const revo_pyr *cur, int hist_level, int n
     out->out_of_bounds = c[8];
     // tracker.cpp:183: histogram.size() = 1 + frames that took part
     out->status = (measure >= (float)c[4] || nf + 1 < 4) ? REVO_TRACKER_STATE_OK : REVO_TRACKER_STATE_NEW_KF;
+}
+
+int revo_track_quality_batch(revo_ctx *ctx, int n, revo_pyr *const *curs, int hist_level, const int *n_past, revo_pyr *const *past,
+                             const float *past_world_poses16, const float *estimated_poses16, int n_frames_voting, revo_quality_result *out)
+{
+    if (!ctx || n < 0 || (n > 0 && (!curs || !n_past || !estimated_poses16 || !out))) return REVO_ERR_INVALID_ARG;
+    if (n == 0) return REVO_OK;
+    REVO_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<QualityArgs> args((size_t)n);
+    int any = 0;
+    for (int i = 0; i < n; ++i) {
+        int rc = quality_prepare(ctx, curs[i], hist_level, n_past[i], past ? past + 3 * (size_t)i : nullptr,
+                                 past_world_poses16 ? past_world_poses16 + 48 * (size_t)i : nullptr, estimated_poses16 + 16 * (size_t)i,
+                                 n_frames_voting, args[i], &out[i]);
+        if (rc) return rc;
+        if (args[i].w != args[0].w || args[i].h != args[0].h) return REVO_ERR_INVALID_ARG;
+        any |= out[i].n_frames > 0;
+    }
+    if (!any) return REVO_OK;
+    const int w = args[0].w, h = args[0].h;
+    const size_t words = ((size_t)w * h + 3) / 4, b_args = align_up(sizeof(QualityArgs) * (size_t)n, 256), b_cnt = align_up(64 * (size_t)n, 256);
+    int rc = ensure_scratch(ctx, b_args + b_cnt + words * 4 * n);
+    if (rc) return rc;
+    QualityArgs *d_args = (QualityArgs *)ctx->scratch;
+    int *d_counters = (int *)((uint8_t *)ctx->scratch + b_args);
+    unsigned *d_mbits = (unsigned *)((uint8_t *)ctx->scratch + b_args + b_cnt);
+    REVO_CUDA(ctx, cudaMemcpyAsync(d_args, args.data(), sizeof(QualityArgs) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_quality(ctx, d_args, n, w, h, curs[0]->cfg.depth_min, curs[0]->cfg.depth_max, d_mbits, d_counters);
+    if (rc) return rc;
+    std::vector<int> c(16 * (size_t)n);
+    REVO_CUDA(ctx, cudaMemcpyAsync(c.data(), d_counters, 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; ++i)
+        if (out[i].n_frames > 0) quality_finish(c.data() + 16 * (size_t)i, &out[i]);
     return REVO_OK;
+}
+
+int revo_track_quality(revo_ctx *ctx, const revo_pyr *cur, int hist_level, int n_past, revo_pyr *const *past,
+                       const float *past_world_poses16, const float *estimated_pose16, int n_frames_voting, revo_quality_result *out)
+{
+    if (!ctx || !cur || !out) return REVO_ERR_INVALID_ARG;
+    // one vote = a batch of one; the batch entry expects three past slots per vote
+    revo_pyr *slots[3] = {nullptr, nullptr, nullptr};
+    float poses[48] = {0};
+    const int np = n_past < 0 ? n_past : (n_past < 3 ? n_past : 3);
+    if (n_past > 0 && (!past || !past_world_poses16)) return REVO_ERR_INVALID_ARG;
+    for (int f = 0; f < np; ++f) { slots[f] = past[f]; memcpy(poses + 16 * f, past_world_poses16 + 16 * f, 64); }
+    revo_pyr *c = const_cast<revo_pyr *>(cur);
+    const int npast = n_past;
+    return revo_track_quality_batch(ctx, 1, &c, hist_level, &npast, slots, poses, estimated_pose16, n_frames_voting, out);
 }
 
 // ---------------------------------------------------------------------------------------------------

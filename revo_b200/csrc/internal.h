@@ -152,21 +152,35 @@ int launch_hist_fill(revo_ctx *ctx, const ImgLevel *d_desc, const ImgLevel *d_to
                      int patch_low, bool do_fill, float n_percentage);
 int launch_compact(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h, float dmin, float dmax);
 int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h);
+// generateColoredPcl: channel-wise cv::pyrDown of a colour image; the cloud of one level (count -> scan -> [scatter if d_out])
+int launch_pyrdown_color(revo_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, int ws, int hs, int ch);
+int launch_colored_pcl(revo_ctx *ctx, const ImgLevel *d_desc_one, int w, int h, int dense, float dmin, float dmax, const uint8_t *d_bgr, int ch,
+                       float *d_out, int cap, int *d_n, int *d_col_off);
 // tracking-quality vote (revo_track_quality): the past frames' 3-D lists with the transform into the current frame
 struct QualityFrame {
     const float4 *pts;
     const int *n_pts;
     float R[9], T[3];     // column-major R, as Eigen::Matrix3f
 };
-struct QualityArgs {
+struct QualityArgs {      // one current frame and the (up to 3) past frames that vote on it
     QualityFrame fr[4];
     int n_frames;
     float fx, fy, cx, cy;
     int w, h;
+    const float *depth;   // level `hist_level` of the current frame
+    const uint8_t *edges; // returnOrigEdges(hist_level)
 };
-// d_counters: 16 ints = histogram[4], overlaps[4], out_of_bounds, ...
-int launch_quality(revo_ctx *ctx, const QualityArgs &args, const float *d_depth, const uint8_t *d_edges, float dmin, float dmax,
-                   unsigned *d_mbits, int *d_counters);
+// n votes in one launch pair (all current frames of one size w x h).  d_args: n QualityArgs on the device; d_mbits: n planes of
+// (w*h+3)/4 words; d_counters: n x 16 ints = histogram[4], overlaps[4], out_of_bounds, ...
+int launch_quality(revo_ctx *ctx, const QualityArgs *d_args, int n, int w, int h, float dmin, float dmax, unsigned *d_mbits, int *d_counters);
+struct PointListCopy {
+    const float4 *src;
+    const int *src_n;
+    float4 *dst;
+    int *dst_n;
+    int cap;
+};
+int launch_copy_point_lists(revo_ctx *ctx, const PointListCopy *d_tab, int n);
 int launch_opt_struct_f4(revo_ctx *ctx, const float *d_dt, int w, int h, float4 *d_out);
 int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uint2 *d_out);
 // reference-order (column-major scan) 3-D edge list into d_out (capacity w*h float4); *d_n receives the count

@@ -577,6 +577,91 @@ int launch_edges3d_reference_order(revo_ctx *ctx, const ImgLevel *d_desc_one, in
 }
 
 // ---------------------------------------------------------------------------
+// generateColoredPcl (imgpyramidrgbd.cpp:279-327): the viewer's coloured cloud of one level, columns
+// (X, Y, Z, 1, r, g, b, 1) in the reference's column-major scan order.  The colour image of the level is cv::pyrDown of the
+// full-resolution one, channel by channel (k_pyrdown_color: plain version of K3, not on the hot path); the compaction is
+// K6's reference-order path (count per column -> scan -> scatter) with the depth test of isPointOkDepth and, unless the
+// dense cloud is asked for, the edge label.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pyrdown_color(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int ws, int hs, int wd, int hd,
+                                                       int ch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= wd) return;
+    constexpr int kw[5] = {1, 4, 6, 4, 1};
+    for (int c = 0; c < ch; ++c) {
+        int s = 0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const uint8_t *row = in + (size_t)reflect101(2 * y - 2 + r, hs) * ws * ch;
+            int hsum = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) hsum += kw[k] * row[(size_t)reflect101(2 * x - 2 + k, ws) * ch + c];
+            s += kw[r] * hsum;
+        }
+        out[((size_t)y * wd + x) * ch + c] = (uint8_t)((s + 128) >> 8);
+    }
+}
+
+__device__ __forceinline__ bool pcl_point_ok(const ImgLevel &L, int x, int y, int w, bool dense, float dmin, float dmax, float &Z)
+{
+    Z = L.depth[(size_t)y * w + x];
+    if (!(isfinite(Z) && Z > dmin && Z < dmax)) return false;      // isPointOkDepth, imgpyramidrgbd.h:163-166
+    return dense || L.edges[(size_t)y * w + x] > 0;
+}
+__global__ void k_pcl_col_count(const ImgLevel *__restrict__ desc, int w, int h, int dense, float dmin, float dmax, int *col_off)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    int c = 0;
+    float Z;
+    for (int y = 0; y < h; ++y) c += pcl_point_ok(desc[0], x, y, w, dense != 0, dmin, dmax, Z);
+    col_off[x] = c;
+}
+__global__ void k_pcl_col_scatter(const ImgLevel *__restrict__ desc, int w, int h, int dense, float dmin, float dmax, const int *col_off,
+                                  const uint8_t *__restrict__ bgr, int ch, float *__restrict__ out, int cap)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const ImgLevel &L = desc[0];
+    int o = col_off[x];
+    float Z;
+    for (int y = 0; y < h; ++y)
+        if (pcl_point_ok(L, x, y, w, dense != 0, dmin, dmax, Z)) {
+            if (o >= cap) return;
+            const float X = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)x, L.cx)), L.fx);
+            const float Y = __fdiv_rn(__fmul_rn(Z, __fsub_rn((float)y, L.cy)), L.fy);
+            const uint8_t *c = bgr + ((size_t)y * w + x) * ch;
+            float4 *q = (float4 *)(out + (size_t)o * 8);
+            q[0] = make_float4(X, Y, Z, 1.0f);
+            q[1] = make_float4(__fdiv_rn((float)c[2], 255.0f), __fdiv_rn((float)c[1], 255.0f), __fdiv_rn((float)c[0], 255.0f), 1.0f);
+            ++o;
+        }
+}
+
+int launch_pyrdown_color(revo_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, int ws, int hs, int ch)
+{
+    const int wd = (ws + 1) / 2, hd = (hs + 1) / 2;
+    k_pyrdown_color<<<dim3(cdiv(wd, 256), hd), 256, 0, ctx->stream>>>(d_in, d_out, ws, hs, wd, hd, ch);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
+int launch_colored_pcl(revo_ctx *ctx, const ImgLevel *d_desc_one, int w, int h, int dense, float dmin, float dmax, const uint8_t *d_bgr, int ch,
+                       float *d_out, int cap, int *d_n, int *d_col_off)
+{
+    k_pcl_col_count<<<cdiv(w, 128), 128, 0, ctx->stream>>>(d_desc_one, w, h, dense, dmin, dmax, d_col_off);
+    LAUNCH_CHECK(ctx);
+    k_col_scan<<<1, 32, 0, ctx->stream>>>(d_col_off, w, d_n);
+    LAUNCH_CHECK(ctx);
+    if (d_out) {
+        k_pcl_col_scatter<<<cdiv(w, 128), 128, 0, ctx->stream>>>(d_desc_one, w, h, dense, dmin, dmax, d_col_off, d_bgr, ch, d_out, cap);
+        LAUNCH_CHECK(ctx);
+    }
+    return REVO_OK;
+}
+
+// ---------------------------------------------------------------------------
 // K7: exact Euclidean distance transform to the nearest edge pixel, out = sqrtf(d2).
 //  (a) column pass: vertical distance g(x,y) to the nearest edge in the column (int, kEdtInf if none)
 //  (b) row pass: d2(x,y) = min_j (x-j)^2 + g(j,y)^2 by an outward search that stops once r^2 >= best
@@ -704,9 +789,14 @@ int launch_opt_pack_from_f4(revo_ctx *ctx, const float4 *d_in, int w, int h, uin
 //  k_quality_hist: one thread per pixel of the current frame: valid depth -> histogram[M]++, and overlaps[M]++ if the pixel
 //      is a Canny edge; block-level shared counters, one global atomic per counter and block.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_quality_scatter(const QualityArgs a, unsigned *__restrict__ mbits, int *__restrict__ counters)
+__global__ void __launch_bounds__(256) k_quality_scatter(const QualityArgs *__restrict__ args, unsigned *__restrict__ mbits_all, size_t words,
+                                                         int *__restrict__ counters_all)
 {
+    const QualityArgs &a = args[blockIdx.z];
+    if ((int)blockIdx.y >= a.n_frames) return;
     const QualityFrame &F = a.fr[blockIdx.y];
+    unsigned *mbits = mbits_all + words * blockIdx.z;
+    int *counters = counters_all + 16 * blockIdx.z;
     const int n = *F.n_pts;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = __ldg(F.pts + i);
@@ -725,39 +815,51 @@ __global__ void __launch_bounds__(256) k_quality_scatter(const QualityArgs a, un
     }
 }
 
-__global__ void __launch_bounds__(256) k_quality_hist(const float *__restrict__ depth, const uint8_t *__restrict__ edges,
-                                                      const unsigned *__restrict__ mbits, int n_px, float dmin, float dmax,
-                                                      int *__restrict__ counters)
+__global__ void __launch_bounds__(256) k_quality_hist(const QualityArgs *__restrict__ args, const unsigned *__restrict__ mbits_all, size_t words,
+                                                      int n_px, float dmin, float dmax, int *__restrict__ counters_all)
 {
     __shared__ int sc[8];
     if (threadIdx.x < 8) sc[threadIdx.x] = 0;
     __syncthreads();
+    const QualityArgs &a = args[blockIdx.y];
+    const unsigned *mbits = mbits_all + words * blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_px) {
-        const float Z = depth[i];
+        const float Z = a.depth[i];
         if (isfinite(Z) && Z > dmin && Z < dmax) {     // ImgPyramidRGBD::isPointOkDepth
             const int val = __popc((mbits[i >> 2] >> ((i & 3) * 8)) & 0xffu);
             atomicAdd(&sc[val & 3], 1);
-            if (edges[i]) atomicAdd(&sc[4 + (val & 3)], 1);
+            if (a.edges[i]) atomicAdd(&sc[4 + (val & 3)], 1);
         }
     }
     __syncthreads();
-    if (threadIdx.x < 8 && sc[threadIdx.x]) atomicAdd(counters + threadIdx.x, sc[threadIdx.x]);
+    if (threadIdx.x < 8 && sc[threadIdx.x]) atomicAdd(counters_all + 16 * blockIdx.y + threadIdx.x, sc[threadIdx.x]);
 }
 
-int launch_quality(revo_ctx *ctx, const QualityArgs &a, const float *d_depth, const uint8_t *d_edges, float dmin, float dmax,
-                   unsigned *d_mbits, int *d_counters)
+int launch_quality(revo_ctx *ctx, const QualityArgs *d_args, int n, int w, int h, float dmin, float dmax, unsigned *d_mbits, int *d_counters)
 {
-    const int w = a.w, h = a.h;
     const size_t words = ((size_t)w * h + 3) / 4;
-    REVO_CUDA(ctx, cudaMemsetAsync(d_mbits, 0, words * 4, ctx->stream));
-    REVO_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 16 * sizeof(int), ctx->stream));
-    if (a.n_frames > 0) {
-        dim3 grid(64, a.n_frames);
-        k_quality_scatter<<<grid, 256, 0, ctx->stream>>>(a, d_mbits, d_counters);
-        LAUNCH_CHECK(ctx);
-    }
-    k_quality_hist<<<cdiv(w * h, 256), 256, 0, ctx->stream>>>(d_depth, d_edges, d_mbits, w * h, dmin, dmax, d_counters);
+    REVO_CUDA(ctx, cudaMemsetAsync(d_mbits, 0, words * 4 * n, ctx->stream));
+    REVO_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 16 * sizeof(int) * (size_t)n, ctx->stream));
+    k_quality_scatter<<<dim3(n > 16 ? 8 : 64, 3, n), 256, 0, ctx->stream>>>(d_args, d_mbits, words, d_counters);
+    LAUNCH_CHECK(ctx);
+    k_quality_hist<<<dim3(cdiv(w * h, 256), n), 256, 0, ctx->stream>>>(d_args, d_mbits, words, w * h, dmin, dmax, d_counters);
+    LAUNCH_CHECK(ctx);
+    return REVO_OK;
+}
+
+// Copies of 3-D edge lists (TrackerNew::addOldPclAndPose keeps `return3DEdges(histogramLevel)` by value, tracker.cpp:209-224):
+// block (x, f) copies a share of list f and block (0, f) its count.
+__global__ void __launch_bounds__(256) k_copy_point_lists(const PointListCopy *__restrict__ tab)
+{
+    const PointListCopy c = tab[blockIdx.y];
+    const int n = min(*c.src_n, c.cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c.dst[i] = __ldg(c.src + i);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *c.dst_n = n;
+}
+int launch_copy_point_lists(revo_ctx *ctx, const PointListCopy *d_tab, int n)
+{
+    k_copy_point_lists<<<dim3(4, n), 256, 0, ctx->stream>>>(d_tab);
     LAUNCH_CHECK(ctx);
     return REVO_OK;
 }

@@ -215,6 +215,15 @@ public:
         ctx_->check(revo_pyr_num_edges(ctx_->handle(), h_, (int)lvl, &n));
         return n;
     }
+    // generateColoredPcl(lvl, clrPcl, densePcl), imgpyramidrgbd.cpp:279-327: 8 x N column-major, compacted on the device.  The
+    // reference reads its own clone of the colour image (rgbFullSize); here the caller hands the same image in again.
+    std::vector<float> generateColoredPcl(unsigned lvl, const uint8_t *rgb, int channels, bool densePcl = false) const {
+        int n = 0;
+        ctx_->check(revo_pyr_colored_pcl(ctx_->handle(), h_, (int)lvl, densePcl, rgb, channels, nullptr, 0, &n));
+        std::vector<float> pcl((size_t)n * 8);
+        if (n) ctx_->check(revo_pyr_colored_pcl(ctx_->handle(), h_, (int)lvl, densePcl, rgb, channels, pcl.data(), (size_t)n, &n));
+        return pcl;
+    }
     // pose bookkeeping of the keyframe (row-major 4x4 here; the reference keeps Eigen::Matrix4f)
     void setTwf(const float T[16]) { std::memcpy(T_w_f, T, sizeof(T_w_f)); }
     const float *getTransKFtoWorld() const { return T_w_f; }

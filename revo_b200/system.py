@@ -19,6 +19,12 @@ import numpy as np
 TRACKER_STATE_OK, TRACKER_STATE_LOST, TRACKER_STATE_NEW_KF, TRACKER_STATE_UNKNOWN = range(4)
 
 
+class VoteRequest(tuple):
+    """``(estimatedPose, currPyr)``: an ``assessTrackingQuality`` request of the per-frame coroutine (a ``trackFrames`` request is
+    a plain 4-tuple ``(R, T, refPyr, currPyr)``)."""
+    __slots__ = ()
+
+
 def transformFromRT(R, T) -> np.ndarray:
     M = np.eye(4, dtype=np.float32)
     M[:3, :3] = np.asarray(R, np.float32).reshape(3, 3)
@@ -76,11 +82,15 @@ class REVO:
         self.error = 0.0
         self.retracked: List[int] = []               # frame ids at which the previous frame was promoted and tracking repeated
 
-    def _frame(self, currPyr):
+    def _frame(self, currPyr, pcl=None):
         """One iteration of the ``while`` loop (system.cpp:147-275) as a coroutine: it YIELDS every ``trackFrames`` request
-        ``(R_init, T_init, refPyr, currPyr)`` and is sent the result ``(status, R, T, error)``, so that a driver can
-        batch the requests of many streams into one launch (:class:`MultiStreamREVO`).  Returns the frame's world pose."""
+        ``(R_init, T_init, refPyr, currPyr)`` and is sent the result ``(status, R, T, error)``, and every
+        ``assessTrackingQuality`` request (:class:`VoteRequest`) and is sent the status, so that a driver can batch the
+        requests of many streams into one launch each (:class:`MultiStreamREVO`).  ``pcl``: what to hand to
+        ``addOldPclAndPose`` for this frame (default: the pyramid; a driver may have copied the lists of all streams in one
+        call).  Returns the frame's world pose."""
         trk = self.mTracker
+        pcl = currPyr if pcl is None else pcl
         currPyr.frameId = self.noFrames
         if self.noFrames == 0:                       # first frame -> keyframe (system.cpp:151-175)
             self.kfPyr = self.prevPyr = currPyr
@@ -90,13 +100,13 @@ class REVO:
             self.nKeyFrames += 1
             self.noFrames += 1
             self.justAddedNewKeyframe = True
-            trk.addOldPclAndPose(currPyr, np.eye(4, dtype=np.float32), currPyr.returnTimestamp())
+            trk.addOldPclAndPose(pcl, np.eye(4, dtype=np.float32), currPyr.returnTimestamp())
             return np.eye(4, dtype=np.float32)
         self.noFrames += 1
         status, R, T, self.error = yield (self.R, self.T, self.kfPyr, currPyr)                           # :188
         T_KF_N = transformFromRT(R, T)
         currPoseInWorld = (self.kfPyr.getTransKFtoWorld().astype(np.float32) @ T_KF_N).astype(np.float32)   # :192
-        status = trk.assessTrackingQuality(currPoseInWorld, currPyr)                                     # :199
+        status = yield VoteRequest((currPoseInWorld, currPyr))                                           # :199
         if status == TRACKER_STATE_NEW_KF and not self.justAddedNewKeyframe:
             # tracking gets inaccurate: take the previous frame as keyframe and optimise again (:203-239)
             self.kfPyr = self.prevPyr
@@ -108,7 +118,7 @@ class REVO:
             _, R, T, self.error = yield (self.T_NM1_N[:3, :3], self.T_NM1_N[:3, 3], self.kfPyr, currPyr)   # :225
             T_KF_N = transformFromRT(R, T)
             currPoseInWorld = (self.kfPyr.getTransKFtoWorld().astype(np.float32) @ T_KF_N).astype(np.float32)
-            status = trk.assessTrackingQuality(currPoseInWorld, currPyr)
+            status = yield VoteRequest((currPoseInWorld, currPyr))
             self.justAddedNewKeyframe = True
             self.retracked.append(currPyr.frameId)
         else:
@@ -116,7 +126,7 @@ class REVO:
         self.trackerStatus = status
         # add the frame to the pose graph, remember its edge cloud for the vote (:253-254)
         self.mPoseGraph.append(Pose(T_KF_N, currPyr.returnTimestamp(), self.kfPyr))
-        trk.addOldPclAndPose(currPyr, currPoseInWorld, currPyr.returnTimestamp())
+        trk.addOldPclAndPose(pcl, currPoseInWorld, currPyr.returnTimestamp())
         # relative motion N-1 -> N and the constant-velocity guess for the next frame (:262-271)
         self.T_NM1_N = (self.mPoseGraph[-2].T_N_W() @ self.mPoseGraph[-1].T_W_N()).astype(np.float32)
         T_init = (self.mPoseGraph[-1].T_kf_N() @ self.T_NM1_N).astype(np.float32)
@@ -130,7 +140,10 @@ class REVO:
         try:
             req = next(g)
             while True:
-                req = g.send(self.mTracker.trackFrames(*req))
+                if isinstance(req, VoteRequest):
+                    req = g.send(self.mTracker.assessTrackingQuality(*req))
+                else:
+                    req = g.send(self.mTracker.trackFrames(*req))
         except StopIteration as done:
             return done.value
 
@@ -149,16 +162,24 @@ class MultiStreamREVO:
                  ``clearUpPastLists``)
     track_batch: ``f(requests) -> results`` with ``requests = [(R, T, refPyr, currPyr), ...]`` and
                  ``results = [(status, R, T, error), ...]`` in the same order
+    vote_batch:  optional ``f(trackers, estimatedPoses, currPyrs) -> statuses`` (``api.assess_tracking_quality_batch``: the votes
+                 of all streams in one launch pair); default: every tracker's own ``assessTrackingQuality``
+    pcl_batch:   optional ``f(currPyrs) -> objects`` handed to ``addOldPclAndPose`` in place of the pyramids (one batched copy
+                 of the level-``histogramLevel`` lists, ``api.copy_point_lists``)
     """
 
-    def __init__(self, trackers, track_batch):
+    def __init__(self, trackers, track_batch, vote_batch=None, pcl_batch=None):
         self.streams: List[REVO] = [REVO(t) for t in trackers]
         self.track_batch = track_batch
-        self.batch_sizes: List[int] = []             # requests per launch, for tests / diagnostics
+        self.vote_batch = vote_batch
+        self.pcl_batch = pcl_batch
+        self.batch_sizes: List[int] = []             # trackFrames requests per launch, for tests / diagnostics
+        self.vote_batch_sizes: List[int] = []
 
     def processFrames(self, currPyrs) -> List[np.ndarray]:
         assert len(currPyrs) == len(self.streams)
-        gens = [s._frame(p) for s, p in zip(self.streams, currPyrs)]
+        pcls = self.pcl_batch(currPyrs) if self.pcl_batch else [None] * len(currPyrs)
+        gens = [s._frame(p, c) for s, p, c in zip(self.streams, currPyrs, pcls)]
         poses: List[Optional[np.ndarray]] = [None] * len(gens)
         pending = {}
         for i, g in enumerate(gens):
@@ -167,11 +188,22 @@ class MultiStreamREVO:
             except StopIteration as done:
                 poses[i] = done.value
         while pending:
-            idx = sorted(pending)
-            results = self.track_batch([pending[i] for i in idx])
-            self.batch_sizes.append(len(idx))
+            tracks = sorted(i for i in pending if not isinstance(pending[i], VoteRequest))
+            votes = sorted(i for i in pending if isinstance(pending[i], VoteRequest))
+            answers = {}
+            if tracks:
+                answers.update(zip(tracks, self.track_batch([pending[i] for i in tracks])))
+                self.batch_sizes.append(len(tracks))
+            if votes:
+                trks = [self.streams[i].mTracker for i in votes]
+                if self.vote_batch:
+                    st = self.vote_batch(trks, [pending[i][0] for i in votes], [pending[i][1] for i in votes])
+                else:
+                    st = [t.assessTrackingQuality(*pending[i]) for t, i in zip(trks, votes)]
+                answers.update(zip(votes, st))
+                self.vote_batch_sizes.append(len(votes))
             pending = {}
-            for i, r in zip(idx, results):
+            for i, r in answers.items():
                 try:
                     pending[i] = gens[i].send(r)
                 except StopIteration as done:

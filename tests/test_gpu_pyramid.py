@@ -181,25 +181,39 @@ def test_canny_tile_fallback_path(ctx, orc32):
         _compare(pg, po, 1)
 
 
-def test_colored_point_cloud_from_device_arrays(ctx, orc32):
-    """ImgPyramidRGBD.generateColoredPcl (viewer export, imgpyramidrgbd.cpp:279-327) over the device's depth / edge arrays
-    against the loop restatement over the oracle pyramid, levels 0..2 (colour reduced with pyrDown like the reference)."""
+def test_colored_point_cloud_device_kernel(ctx, orc32):
+    """revo_pyr_colored_pcl (ImgPyramidRGBD::generateColoredPcl, viewer export, imgpyramidrgbd.cpp:279-327): colour pyrDown +
+    count / scan / scatter on the device against the loop restatement over the oracle pyramid, levels 0..2, edge and dense
+    clouds, 3- and 4-channel colour images; the count-only call and the capacity check of the C ABI."""
+    import ctypes as C
+
     import cv2
 
     from oracle import oracle as O
     from revo_b200 import api
 
-    p = synth_pair(4, 320, 240)
-    bgr, depth = p["key"]
-    st = _settings(p["cam"], 3)
-    pg = api.ImgPyramidRGBD(ctx, st, None, bgr, depth)
-    po = _oracle_pyr(orc32, p["cam"], 3, bgr, depth, keyframe=False)
-    rgb = bgr
-    for lvl in range(3):
-        if lvl:
-            rgb = cv2.pyrDown(rgb)
-        c = po.cams[lvl]
-        for dense in (False, True):
-            want = O.generate_colored_pcl(rgb, po.depth[lvl], po.edges[lvl], (c.fx, c.fy, c.cx, c.cy, c.w, c.h), 0.1, 5.2, dense)
-            assert np.array_equal(pg.generateColoredPcl(lvl, dense), want)
-    assert pg.generateColoredPcl(3).shape == (8, 0)
+    for seed, (w, h) in ((4, (320, 240)), (9, (640, 480))):
+        p = synth_pair(seed, w, h)
+        bgr, depth = p["key"]
+        st = _settings(p["cam"], 3)
+        pg = api.ImgPyramidRGBD(ctx, st, None, bgr, depth)
+        po = _oracle_pyr(orc32, p["cam"], 3, bgr, depth, keyframe=False)
+        bgra = np.concatenate([bgr, np.full(bgr.shape[:2] + (1,), 255, np.uint8)], axis=2)
+        rgb = bgr
+        for lvl in range(3):
+            if lvl:
+                rgb = cv2.pyrDown(rgb)
+            c = po.cams[lvl]
+            for dense in (False, True):
+                want = O.generate_colored_pcl(rgb, po.depth[lvl], po.edges[lvl], (c.fx, c.fy, c.cx, c.cy, c.w, c.h), 0.1, 5.2, dense)
+                got = pg.generateColoredPcl(lvl, dense)
+                assert got.shape == want.shape and np.array_equal(got, want), (seed, lvl, dense)
+                assert np.array_equal(pg.generateColoredPcl(lvl, dense, rgb=bgra), want)
+            # the edge cloud is the 3-D edge list with colours
+            assert np.array_equal(pg.generateColoredPcl(lvl)[:4].T, pg.return3DEdges(lvl))
+        assert pg.generateColoredPcl(3).shape == (8, 0)
+        n = C.c_int(0)
+        small = np.zeros((4, 8), np.float32)
+        rc = ctx.lib.revo_pyr_colored_pcl(ctx.h, pg.h, 0, 1, bgr.ctypes.data, 3, small.ctypes.data, 4, C.byref(n))
+        assert rc == api.REVO_ERR_BUFFER_TOO_SMALL and n.value == int(np.isfinite(po.depth[0]).sum() - (po.depth[0] <= 0.1).sum()
+                                                                      - (po.depth[0] >= 5.2).sum())

@@ -185,3 +185,45 @@ def test_cuda_track_batch_adapter_conventions():
     assert [r[0] for r in res] == [0, 2] and [r[3] for r in res] == [0.5, 1.5]
     assert np.array_equal(res[0][1], R_true) and np.array_equal(res[1][1], R_true + 1)
     assert np.array_equal(res[1][2], [2, 2, 2])
+
+
+def test_stream_tracker_vote_policy_equals_the_per_stream_main_loop():
+    """StreamTracker(kf_policy="vote") -- the reference's keyframe policy (system.cpp:199-239) vectorised over the streams with
+    handle arrays, batched votes and batched point-list copies -- against B separate REVO main loops over the same oracle
+    objects: same keyframe decisions, same re-tracks, same world poses (up to the rigid vs general 4x4 inverse in float32)."""
+    from _oracle_system import OraclePyr, OracleTracker
+    from oracle import oracle as O
+    from oracle.stream_backend import OracleBackend
+    from revo_b200 import synth
+    from revo_b200.stream import StreamTracker
+    from revo_b200.system import REVO
+
+    w, h, n, B = 160, 120, 9, 3
+    cam = synth.intrinsics(w, h)
+    streams = [synth.make_stream(300 + b, n, w, h, max_trans=0.01 + 0.04 * (b == 1), max_rot_deg=0.5 + 2.5 * (b == 1)) for b in range(B)]
+    orc = O.Oracle("f32")
+    cfg = O.PyrCfg(n_levels=3)
+    single = [REVO(OracleTracker(orc, 3)) for _ in range(B)]
+    for b in range(B):
+        for i in range(n):
+            single[b].processFrame(OraclePyr(orc, cfg, cam, *streams[b]["frames"][i], timestamp=0.033 * i))
+
+    be = OracleBackend(cam, 3)
+    st = StreamTracker(be, B, kf_policy="vote")
+    st.keep_history = True
+    frames = lambda i: (np.stack([streams[b]["frames"][i][0] for b in range(B)]), np.stack([streams[b]["frames"][i][1] for b in range(B)]))
+    st.start(*frames(0))
+    kf_flags = []
+    for i in range(1, n):
+        st.step(*frames(i))
+        kf_flags.append(st.just_added.copy())
+    assert st.n_retracks == sum(len(s.retracked) for s in single) >= 1
+    for b in range(B):
+        assert [i + 1 for i, f in enumerate(kf_flags) if f[b]] == single[b].retracked
+        traj = single[b].trajectory()
+        for i in range(1, n):
+            assert np.allclose(st.history[i - 1][0][b], traj[i], atol=2e-6), (b, i)
+    # the vote history stays bounded (first three entries vote, last three survive a clear-up)
+    assert st.n_past.max() <= 6 and len(be._reg) <= B * (2 + 6)
+    st.close()
+    assert not be._reg
