@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--levels", type=int, default=4)
     ap.add_argument("--kf-interval", type=int, default=10)
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--kf-policy", choices=("interval", "vote"), default="interval",
                     help="interval: a keyframe every --kf-interval frames (the fixed workload of BASELINE.json configs[1]); vote: the "
                          "reference's own policy (assessTrackingQuality after every alignment, promote the previous frame and align "
@@ -294,8 +295,34 @@ def parity_block(gpu_hist, cpu_hist, n_streams):
     return out
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process (and therefore its pinned host buffers, allocated first-touch afterwards) to the NUMA node the rank's GPU
+    hangs off, so that the host->device copies of the end-to-end run do not cross the socket interconnect.  Returns a dict for
+    the JSON line (node, cpus) or the reason it did nothing."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip().lower()
+        dom, rest = out.split(":", 1)
+        dev = f"{dom[-4:]}:{rest}"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        if node < 0:
+            return {"bound": False, "why": "numa_node = -1 (single node or not reported)"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": f"no allowed cpu on node {node}"}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "node": node, "cpus": len(cpus), "gpu_pci": dev}
+    except Exception as e:      # no nvidia-smi / sysfs entry: run unbound
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
+
+
 def main():
     args = parse_args()
+    numa = bind_to_gpu_numa_node(int(os.environ.get("LOCAL_RANK", "0"))) if args.impl != "reference" and not args.no_numa else {"bound": False, "why": "disabled"}
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -394,9 +421,9 @@ def main():
 
     build_ctx = api.Context(local_rank)    # second stream: upload + pyramid build of frame k+1 overlap tracking of frame k
 
-    def timed_run(src_bgr, src_depth, sample_clocks, pipelined=False, K=K, keep_history=False):
+    def timed_run(src_bgr, src_depth, sample_clocks, pipelined=False, K=K, keep_history=False, policy=None):
         be = CudaBackend(ctx, settings, build_ctx=build_ctx if pipelined else None)
-        st = StreamTracker(be, B, args.kf_interval)
+        st = StreamTracker(be, B, args.kf_interval, policy or args.kf_policy)
         st.keep_history = keep_history
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
@@ -429,7 +456,7 @@ def main():
                 p, kf, k9 = ctx.last_timings()
                 pyr_ms += p
                 k9_ms += k9
-                if st.frame % args.kf_interval == 0:
+                if st.kf_policy == "interval" and st.frame % args.kf_interval == 0:
                     kf_ms += kf
             step_wall.append((time.perf_counter() - ts) * 1e3)
         build_ctx.synchronize()     # the uploads / builds enqueued by the last steps are part of the timed region
@@ -445,7 +472,8 @@ def main():
             ms = float(t.item())
         res = dict(ms=ms, wall=wall, evals=st.total_evals - ev0, point_evals=st.total_point_evals - pe0,
                    launches=ctx.launch_count + build_ctx.launch_count - l0, step_wall=step_wall, upload_ms=upload_ms, k9_ms=k9_ms, pyr_ms=pyr_ms, kf_ms=kf_ms, T_w_c=st.T_w_c.copy(), clocks=clocks,
-                   n_pts=st.last["n_pts"].mean(axis=0).tolist(), n_evals=st.last["n_evals"].mean(axis=0).tolist(), history=st.history)
+                   n_pts=st.last["n_pts"].mean(axis=0).tolist(), n_evals=st.last["n_evals"].mean(axis=0).tolist(), history=st.history,
+                   n_keyframes=st.n_keyframes, n_retracks=st.n_retracks)
         st.close()
         return res
 
@@ -470,15 +498,22 @@ def main():
     note("isolated-kernel pass done")
 
     # what the host link can do: one pinned -> device copy of a batch of bgr frames, timed alone
+    # host link: every rank copies pinned frames at the same time (behind a barrier), the way the end-to-end run loads the box
     tmp = torch.empty_like(bgr_d[0])
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tmp.copy_(bgr_h[0], non_blocking=True)
-    torch.cuda.synchronize()
+    barrier()
     c0.record()
-    tmp.copy_(bgr_h[1], non_blocking=True)
+    for r in range(4):
+        tmp.copy_(bgr_h[1 + r % (n_frames - 1)], non_blocking=True)
     c1.record()
     torch.cuda.synchronize()
-    h2d_gbs = bgr_h[1].numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    h2d_ms = c0.elapsed_time(c1)
+    if dist is not None:
+        t = torch.tensor([h2d_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d_ms = float(t.item())
+    h2d_gbs = 4 * bgr_h[1].numel() / (h2d_ms * 1e-3) / 1e9        # per rank, all ranks copying concurrently
     del tmp
 
     frames_rank = K * B
@@ -543,7 +578,11 @@ def main():
                 "float_depth": {"value": frames_all / (host_run_f32["ms"] * 1e-3), "unit": "frames/s",
                                 "h2d_bytes_per_step": int(B * w * h * 7), "ms_per_step": host_run_f32["ms"] / K},
                 "ms_per_step": host_run["ms"] / K, "h2d_link_gbs_measured": h2d_gbs, "upload_ms_last_batch": host_run["upload_ms"],
-                "h2d_floor_ms_per_step": B * w * h * 5 / (h2d_gbs * 1e9) * 1e3},
+                "h2d_floor_ms_per_step": B * w * h * 5 / (h2d_gbs * 1e9) * 1e3,
+                "h2d_aggregate_gbs_all_ranks": h2d_gbs * world, "h2d_achieved_gbs_all_ranks": world * B * w * h * 5 / (host_run["ms"] / K * 1e-3) / 1e9,
+                "host_link_note": "h2d_link_gbs_measured = pinned-host -> device copy rate per rank with ALL ranks copying at once "
+                                  "(slowest rank); the end-to-end step cannot be shorter than h2d_floor_ms_per_step, whatever the kernels do",
+                "numa": numa},
         "roofline": {"kernel": "k_track (persistent residual/Jacobian/6x6 reduce + LM)", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "algorithmic_bytes": 60.0 * iso_run["point_evals"] / K_iso,
@@ -569,6 +608,20 @@ def main():
 
     if edge_split is not None:
         line["edge_split"] = edge_split
+
+    if world == 1 and not args.no_extras and args.kf_policy != "vote":
+        # the reference's own keyframe policy (vote after every alignment, promote the previous frame + align again on NEW_KF)
+        # on the same streams, device-resident inputs, same pipeline: batched votes / promotions / re-alignments
+        Kv = min(K, 20)
+        vr = timed_run(bgr_d, depth_d, sample_clocks=False, pipelined=not args.no_pipeline, K=Kv, policy="vote")
+        line["kf_policy_vote"] = {
+            "value": B * Kv / (vr["ms"] * 1e-3), "unit": "frames/s", "ms_per_step": vr["ms"] / Kv, "steps": Kv,
+            "gn_iters_per_sec": vr["evals"] / (vr["ms"] * 1e-3),
+            "keyframe_switches_per_frame": vr["n_keyframes"] / float(B * (Kv + W)),
+            "policy": "assessTrackingQuality for all streams in one launch pair (revo_track_quality_batch); streams voting NEW_KF "
+                      "promote their previous frame, are aligned again and vote again in a second, smaller launch of each kind "
+                      "(system.cpp:199-239); one device->host read of the counters per vote"}
+        note("vote-policy run done")
 
     if world == 1 and not args.no_extras:
         line["single_stream"] = extra_single_pair(torch, api, synth_torch, ctx, local_rank, 640, 480, 3, seed=1, reps=30,

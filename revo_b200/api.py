@@ -733,9 +733,13 @@ class TrackerNew:
         return int(res.status), _R_from_c(Rc), Tc, float(res.error)
 
     def trackFramesBatch(self, Rs, Ts, refFrames: Sequence[ImgPyramidRGBD], currFrames: Sequence[ImgPyramidRGBD],
-                         trace_cap: int = 0):
+                         trace_cap: int = 0, check: bool = True):
         """n independent pairs in one persistent-kernel launch.  Rs: (n,3,3), Ts: (n,3).
-        Returns a structured array (TRACK_RESULT_DTYPE; R column-major) and, if trace_cap>0, the LM traces."""
+        Returns a structured array (TRACK_RESULT_DTYPE; R column-major) and, if trace_cap>0, the LM traces.
+        ``revo_track_batch`` answers REVO_OK when the launch worked even if single pairs were refused (their ``rc`` field says
+        why, e.g. REVO_ERR_NOT_ORTHOGONAL for a bad initial rotation; such a pair comes back untracked).  With ``check`` (the
+        default) a refused pair raises :class:`RevoError` naming it, like the single-pair call does; pass ``check=False`` to
+        inspect ``out["rc"]`` yourself."""
         n, refs = _handles(refFrames)
         n2, curs = _handles(currFrames)
         assert n == n2
@@ -750,6 +754,11 @@ class TrackerNew:
         self.ctx.check(self.ctx.lib.revo_track_batch(self.ctx.h, C.byref(cfg), n, refs, curs, Rc.ctypes.data, Tc.ctypes.data,
                                                      out.ctypes.data, C.addressof(trace) if trace is not None else None,
                                                      trace_cap, _ptr(counts)))
+        if check and out["rc"].any():
+            i = int(np.nonzero(out["rc"])[0][0])
+            rc = int(out["rc"][i])
+            raise RevoError(rc, f"pair {i} of {n} was not tracked: {self.ctx.lib.revo_strerror(rc).decode()} "
+                                f"({int((out['rc'] != 0).sum())} pairs refused in this batch)")
         if trace_cap > 0:
             traces = [[(trace[i * trace_cap + k].error, trace[i * trace_cap + k].lam, trace[i * trace_cap + k].accepted,
                         trace[i * trace_cap + k].good, trace[i * trace_cap + k].bad, trace[i * trace_cap + k].level)

@@ -406,14 +406,22 @@ public:
         return s;
     }
 #endif
-    // void addOldPclAndPose(pcl, worldPose, timeStamp)   tracker.h:77 / tracker.cpp:209-224.  The reference copies
-    // return3DEdges(histogramLevel) of the frame; here the frame itself is kept (its list stays on the device).
-    // worldPose: column-major 4x4 (Eigen::Matrix4f::data()).
+    // void addOldPclAndPose(pcl, worldPose, timeStamp)   tracker.h:77 / tracker.cpp:209-224.  Like the reference, which stores
+    // return3DEdges(histogramLevel) BY VALUE, the tracker keeps a device copy of that one list (revo_pyr_copy_points_batch), not the
+    // frame: the pyramid (and the batch slab it may live in) can be released.  worldPose: column-major 4x4 (Eigen::Matrix4f::data()).
     void addOldPclAndPose(const std::shared_ptr<ImgPyramidRGBD> &frame, const float *worldPose16, double timeStamp) {
+        revo_pyr *src = frame->handle(), *copy = nullptr;
+        ctx_->check(revo_pyr_copy_points_batch(ctx_->handle(), 1, &src, histogramLevel, &copy));
         Past p;
-        p.frame = frame; p.ts = timeStamp;
+        std::shared_ptr<revo::Context> ctx = ctx_;
+        p.list = std::shared_ptr<revo_pyr>(copy, [ctx](revo_pyr *h) { revo_pyr_destroy(ctx->handle(), h); });
+        p.ts = timeStamp;
         std::memcpy(p.pose, worldPose16, sizeof(p.pose));
         mPast.push_back(p);
+        // The reference's lists grow until the next keyframe, but only the first nFramesHistogramVoting entries ever vote
+        // (tracker.cpp:138) and clearUpPastLists keeps the last ones: what lies in between can never be read again.
+        const size_t nv = (size_t)mSettings.nFramesHistogramVoting;
+        while (mPast.size() > 2 * nv) mPast.erase(mPast.begin() + (long)nv);
     }
     void clearUpPastLists() {   // tracker.cpp:249-257
         while ((int)mPast.size() > mSettings.nFramesHistogramVoting) mPast.pop_front();
@@ -424,7 +432,7 @@ public:
         std::vector<revo_pyr *> hs;
         std::vector<float> poses;
         for (const Past &p : mPast) {
-            hs.push_back(p.frame->handle());
+            hs.push_back(p.list.get());
             poses.insert(poses.end(), p.pose, p.pose + 16);
         }
         ctx_->check(revo_track_quality(ctx_->handle(), currFrame->handle(), histogramLevel, (int)hs.size(), hs.data(), poses.data(),
@@ -443,7 +451,7 @@ public:
     revo_quality_result lastQuality{};
 private:
     struct Past {
-        std::shared_ptr<ImgPyramidRGBD> frame;
+        std::shared_ptr<revo_pyr> list;   // owns a copy of the level-histogramLevel 3-D edge list only
         float pose[16];
         double ts;
     };

@@ -50,19 +50,61 @@ struct Mat4f {
             }
         return c;
     }
-    // inverse of a rigid transform (the reference calls Eigen's general .inverse() on SE3 matrices)
-    Mat4f inverseRigid() const {
-        Mat4f r = Identity();
-        for (int j = 0; j < 3; ++j)
-            for (int i = 0; i < 3; ++i) r(i, j) = (*this)(j, i);
-        for (int i = 0; i < 3; ++i) {
-            double s = 0;
-            for (int k = 0; k < 3; ++k) s += (double)(*this)(k, i) * (*this)(k, 3);
-            r(i, 3) = (float)-s;
+    // General 4x4 inverse like the reference's Eigen::Matrix4f::inverse() (system.h:136-139), computed in double and rounded once
+    // (the same as revo_b200/system.py).  NOT the transpose shortcut of a rigid transform: world poses are float32 products
+    // chained over every keyframe and drift off orthogonality by E; with the true inverse E cancels in T_NM1_N = T_N_W * T_W_N,
+    // with the transpose it would double and eventually trip the tracker's orthogonality gate on long sequences.
+    Mat4f inverse() const {
+        double a[4][8];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) { a[i][j] = (*this)(i, j); a[i][4 + j] = i == j ? 1.0 : 0.0; }
+        for (int k = 0; k < 4; ++k) {
+            int piv = k;
+            for (int i = k + 1; i < 4; ++i)
+                if (std::fabs(a[i][k]) > std::fabs(a[piv][k])) piv = i;
+            if (piv != k)
+                for (int j = 0; j < 8; ++j) std::swap(a[piv][j], a[k][j]);
+            const double d = 1.0 / a[k][k];
+            for (int j = 0; j < 8; ++j) a[k][j] *= d;
+            for (int i = 0; i < 4; ++i) {
+                if (i == k) continue;
+                const double f = a[i][k];
+                if (f != 0.0)
+                    for (int j = 0; j < 8; ++j) a[i][j] -= f * a[k][j];
+            }
         }
+        Mat4f r;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) r(i, j) = (float)a[i][4 + j];
         return r;
     }
+    Mat4f inverseRigid() const { return inverse(); }   // old name
 };
+
+// Eigen::Quaternionf(R) (what REVO::writePose prints, system.cpp:75-79): the trace / largest-diagonal rule, no orthogonality
+// requirement and no normalisation -- it never fails, unlike revo_R9_to_quat's Sophus-style gate.
+inline void quaternionFromMatrix(const Mat3f &R, float q_xyzw[4]) {
+    float t = R(0, 0) + R(1, 1) + R(2, 2);
+    if (t > 0.f) {
+        t = std::sqrt(t + 1.0f);
+        q_xyzw[3] = 0.5f * t;
+        t = 0.5f / t;
+        q_xyzw[0] = (R(2, 1) - R(1, 2)) * t;
+        q_xyzw[1] = (R(0, 2) - R(2, 0)) * t;
+        q_xyzw[2] = (R(1, 0) - R(0, 1)) * t;
+    } else {
+        int i = 0;
+        if (R(1, 1) > R(0, 0)) i = 1;
+        if (R(2, 2) > R(i, i)) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(R(i, i) - R(j, j) - R(k, k) + 1.0f);
+        q_xyzw[i] = 0.5f * t;
+        t = 0.5f / t;
+        q_xyzw[3] = (R(k, j) - R(j, k)) * t;
+        q_xyzw[j] = (R(j, i) + R(i, j)) * t;
+        q_xyzw[k] = (R(k, i) + R(i, k)) * t;
+    }
+}
 
 enum { STATE_OK = 0, STATE_LOST = 1, STATE_NEW_KF = 2, STATE_UNKNOWN = 3 };   // TrackerNew::TrackerStatus, tracker.h:60-65
 
@@ -74,7 +116,7 @@ public:
         : T_kf_curr_(T_kf_curr), timestamp_(timestamp), kfFrame_(kfFrame) {}
     Mat4f getCurrToWorld() const { return Mat4f::fromPtr(kfFrame_->getTransKFtoWorld()) * T_kf_curr_; }   // T_W_KF * T_KF_CURR (:131-134)
     Mat4f T_W_N() const { return getCurrToWorld(); }
-    Mat4f T_N_W() const { return getCurrToWorld().inverseRigid(); }
+    Mat4f T_N_W() const { return getCurrToWorld().inverse(); }
     const Mat4f &T_kf_N() const { return T_kf_curr_; }
     // only called when the "previous frame" becomes keyframe (system.h:140-146)
     void setKfFrame(const std::shared_ptr<PyrT> &kfFrame) { kfFrame_ = kfFrame; T_kf_curr_ = Mat4f::Identity(); }
@@ -192,9 +234,7 @@ inline std::vector<Association> readAssociations(const std::string &path, int sk
 // timestamp, setprecision(9) afterwards; quaternion = Eigen::Quaternionf(R)).
 inline std::string poseToTUMString(const Mat4f &T_w_c, double timestamp) {
     float q[4];
-    const Mat3f R = T_w_c.rotation();
-    const int rc = revo_R9_to_quat(R.data(), q);
-    if (rc) throw Error(rc, revo_strerror(rc));
+    quaternionFromMatrix(T_w_c.rotation(), q);
     char buf[256];
     std::snprintf(buf, sizeof(buf), "%.6f %.9f %.9f %.9f %.9f %.9f %.9f %.9f", timestamp, (double)T_w_c(0, 3), (double)T_w_c(1, 3),
                   (double)T_w_c(2, 3), (double)q[0], (double)q[1], (double)q[2], (double)q[3]);

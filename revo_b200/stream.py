@@ -33,14 +33,9 @@ import numpy as np
 
 
 def _inv(T: np.ndarray) -> np.ndarray:
-    """Batched inverse of rigid 4x4 transforms."""
-    R = T[:, :3, :3]
-    t = T[:, :3, 3]
-    Ti = np.tile(np.eye(4, dtype=T.dtype), (T.shape[0], 1, 1))
-    Rt = R.transpose(0, 2, 1)
-    Ti[:, :3, :3] = Rt
-    Ti[:, :3, 3] = -np.einsum("nij,nj->ni", Rt, t)
-    return Ti
+    """Batched inverse of 4x4 transforms: the general inverse like the reference's ``Matrix4f::inverse()`` (system.h:136-139), in
+    float64 and rounded once, the same as revo_b200.system._inv."""
+    return np.linalg.inv(T.astype(np.float64)).astype(np.float32)
 
 
 TRACKER_STATE_OK, TRACKER_STATE_LOST, TRACKER_STATE_NEW_KF = 0, 1, 2

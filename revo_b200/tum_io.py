@@ -44,12 +44,14 @@ def load_frame(folder: str, rgb_file: str, depth_file: str):
     return bgr, raw
 
 
-def iter_frames(folder: str, assoc_file: str = "associate.txt", skip_first_n: int = 0) -> Iterator[Tuple[float, np.ndarray, np.ndarray]]:
-    """Yields (depth timestamp, bgr, raw depth) in file order (the reference stamps a pyramid with the DEPTH timestamp,
-    iowrapperRGBD.cpp:279)."""
-    for _, rgb_file, depth_ts, depth_file in read_associations(os.path.join(folder, assoc_file), skip_first_n):
+def iter_frames(folder: str, assoc_file: str = "associate.txt", skip_first_n: int = 0,
+                use_depth_timestamp: bool = False) -> Iterator[Tuple[float, np.ndarray, np.ndarray]]:
+    """Yields (timestamp, bgr, raw depth) in file order.  The timestamp a pyramid is stamped with is
+    ``useDepthTimeStamp ? depthTimeStamp : rgbTimeStamp`` (iowrapperRGBD.cpp:266); both dataset configurations the reference
+    ships (dataset_tum1.yaml, orbbec_dataset.yaml) set ``useDepthTimeStamp: 0``, so the rgb timestamp is the default here."""
+    for rgb_ts, rgb_file, depth_ts, depth_file in read_associations(os.path.join(folder, assoc_file), skip_first_n):
         bgr, raw = load_frame(folder, rgb_file, depth_file)
-        yield depth_ts, bgr, raw
+        yield (depth_ts if use_depth_timestamp else rgb_ts), bgr, raw
 
 
 def quaternion_from_R(R) -> np.ndarray:

@@ -698,14 +698,44 @@ extern "C" int emu_quality(int n_frames, const float *const *pts, const int *n_p
     revo_ctx ctx{0, 0};
     QualityArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.n_frames = n_frames; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.w = w; a.h = h;
+    a.n_frames = n_frames; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.w = w; a.h = h; a.depth = depth; a.edges = edges;
     for (int f = 0; f < n_frames; ++f) {
         a.fr[f].pts = (const float4 *)pts[f]; a.fr[f].n_pts = &n_pts[f];
         std::memcpy(a.fr[f].R, R9s + 9 * f, sizeof(float) * 9);
         std::memcpy(a.fr[f].T, T3s + 3 * f, sizeof(float) * 3);
     }
-    std::vector<unsigned> mbits(((size_t)w * h + 3) / 4 + 16);
-    return launch_quality(&ctx, a, depth, edges, dmin, dmax, mbits.data(), counters16);
+    // two votes in one launch pair: the vote asked for and an empty one (no past frames), whose counters must stay apart
+    QualityArgs two[2] = {a, a};
+    two[1].n_frames = 0;
+    const size_t words = ((size_t)w * h + 3) / 4;
+    std::vector<unsigned> mbits(2 * words + 16);
+    std::vector<int> counters(32);
+    int rc = launch_quality(&ctx, two, 2, w, h, dmin, dmax, mbits.data(), counters.data());
+    std::memcpy(counters16, counters.data(), 16 * sizeof(int));
+    for (int k = 1; k < 4; ++k)
+        if (counters[16 + k] || counters[20 + k]) rc = rc ? rc : -100;      // nothing can overlap without past frames
+    return rc;
+}
+
+// ImgPyramidRGBD::generateColoredPcl on the device: colour pyrDown to the level + count / scan / scatter (launch_colored_pcl)
+extern "C" int emu_colored_pcl(const uint8_t *bgr0, int channels, int w0, int h0, int lvl, const float *depth, const uint8_t *edges, int w, int h,
+                               float fx, float fy, float cx, float cy, int dense, float dmin, float dmax, float *out, int cap, int *n_out)
+{
+    using namespace revo;
+    revo_ctx ctx{0, 0};
+    std::vector<uint8_t> a(bgr0, bgr0 + (size_t)w0 * h0 * channels), b(a.size());
+    int cw = w0, chh = h0, rc = 0;
+    for (int l = 0; l < lvl && !rc; ++l) {
+        rc = launch_pyrdown_color(&ctx, a.data(), b.data(), cw, chh, channels);
+        cw = (cw + 1) / 2; chh = (chh + 1) / 2;
+        a.swap(b);
+    }
+    if (rc || cw != w || chh != h) return rc ? rc : -101;
+    ImgLevel L;
+    std::memset(&L, 0, sizeof(L));
+    L.depth = const_cast<float *>(depth); L.edges = const_cast<uint8_t *>(edges); L.w = w; L.h = h; L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy;
+    std::vector<int> col(w + 4);
+    return launch_colored_pcl(&ctx, &L, w, h, dense, dmin, dmax, a.data(), channels, out, cap, n_out, col.data());
 }
 '''
 
@@ -730,7 +760,7 @@ def build_pyramid(out_dir):
     src_text = (PRELUDE + CANNY_SHIMS + generic + "namespace revo {\nstatic inline int cdiv(int a, int b) { return (a + b - 1) / b; }\n"
                 + "constexpr int kTileW = 8;\nconstexpr int kTileH = 4;\n"
                 + _struct(internal, "ImgLevel") + "\n" + internal[internal.index("__host__ __device__ inline unsigned opt_texel_index"):internal.index("inline int opt_tiles_per_row")]
-                + _struct(internal, "QualityFrame") + "\n" + _struct(internal, "QualityArgs") + "\n"
+                + _struct(internal, "QualityFrame") + "\n" + _struct(internal, "QualityArgs") + "\n" + _struct(internal, "PointListCopy") + "\n"
                 + body + "}  // namespace revo\n" + PYRAMID_DRIVER)
     src, lib = os.path.join(out_dir, "pyramid_emu.cpp"), os.path.join(out_dir, "libpyramid_emu.so")
     open(src, "w").write(src_text)

@@ -19,7 +19,7 @@ def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     sys.path.insert(0, ROOT)
-    from bench import OracleBackend
+    from oracle.stream_backend import OracleBackend
     from revo_b200 import synth
     from revo_b200.stream import StreamTracker
 

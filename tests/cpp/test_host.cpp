@@ -82,7 +82,37 @@ static int selftest_main_loop(const char *self)
         if (revo::readAssociations(path, 1).size() != 1) return 65;
         std::remove(path);
     }
-    // rigid inverse
+    // long sequences: > 1000 keyframe switches chain float32 world poses; the motion-model guess handed to the tracker
+    // must stay inside the tracker's orthogonality gate (|R R^T - I|_F < 1e-5) and the trajectory line must keep printing
+    {
+        struct TurnTracker : FakeTracker {
+            float worst = 0.f;
+            int trackFrames(revo::Mat3f &R, revo::Vec3f &T, float &error, const std::shared_ptr<FakePyr> &, const std::shared_ptr<FakePyr> &) {
+                float e = 0.f;
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) {
+                        float s = 0.f;
+                        for (int k = 0; k < 3; ++k) s += R(i, k) * R(j, k);
+                        e += (s - (i == j)) * (s - (i == j));
+                    }
+                worst = std::max(worst, std::sqrt(e));
+                // 1.7 degrees about a skew axis and 1 cm per frame, rounded to float like a tracker result
+                const float q[4] = {0.008f, 0.011f, -0.006f, 0.99989f};
+                float r9[9];
+                revo_quat_to_R9(q, r9);
+                std::memcpy(R.m, r9, sizeof(r9));
+                T = revo::Vec3f{{0.01f, -0.004f, 0.002f}}; error = 0.1f;
+                return revo::STATE_OK;
+            }
+        };
+        auto turn = std::make_shared<TurnTracker>();
+        revo::REVOLoopT<FakePyr, TurnTracker> longrun(turn);
+        for (int i = 0; i < 2600; ++i) longrun.processFrame(std::make_shared<FakePyr>(0.033 * i));
+        if (longrun.nKeyFrames < 1200) return 66;
+        if (!(turn->worst < 2e-6f)) { std::printf("orthogonality of the initial guess drifted to %g\n", (double)turn->worst); return 67; }
+        if (revo::poseToTUMString(longrun.trajectory().back(), 1.0).size() < 40) return 68;
+    }
+    // 4x4 inverse
     revo::Mat4f A = revo::Mat4f::Identity();
     A(0, 0) = 0.f; A(0, 1) = -1.f; A(1, 0) = 1.f; A(1, 1) = 0.f; A(0, 3) = 1.f; A(1, 3) = 2.f; A(2, 3) = 3.f;
     const revo::Mat4f P = A * A.inverseRigid();

@@ -370,3 +370,84 @@ def test_multi_stream_main_loop_on_gpu(ctx, engine):
         assert np.array_equal(multi.trajectories()[b], single[b].trajectory())
         assert multi.streams[b].retracked == single[b].retracked
     assert multi.batch_sizes.count(B) >= n - 1
+
+
+def test_batched_vote_and_point_list_copies(ctx, engine):
+    """revo_track_quality_batch == the single-vote entry stream by stream; revo_pyr_copy_points_batch copies exactly the
+    level-2 lists, the copies outlive their frames, and what a points-only handle cannot do is refused (not crashed on)."""
+    import ctypes as C
+
+    from revo_b200 import api, synth
+
+    w, h, B, n = 320, 240, 5, 5
+    cam = synth.intrinsics(w, h)
+    st = _settings(cam, 3)
+    streams = [synth.make_stream(500 + b, n, w, h, max_trans=0.02, max_rot_deg=1.0) for b in range(B)]
+    trackers = [api.TrackerNew(ctx, api.TrackerSettings(), st) for _ in range(B)]
+    lists_ref = []
+    for i in range(n - 1):
+        pyrs = [api.ImgPyramidRGBD(ctx, st, None, *streams[b]["frames"][i], 0.033 * i) for b in range(B)]
+        pls = api.copy_point_lists(ctx, pyrs, 2)
+        for b in range(B):
+            if i == 0:
+                lists_ref.append((pls[b], pyrs[b].return3DEdgesDeviceOrder(2)))
+            if b != 3 or i < 2:            # stream 3 votes with two past frames only
+                trackers[b].addOldPclAndPose(pls[b], streams[b]["T_w_c"][i].astype(np.float32), 0.033 * i)
+        del pyrs                           # the frames go away; the copies stay
+    for pl, want in lists_ref:
+        assert np.array_equal(pl.download(2), want)
+        with pytest.raises(api.RevoError):
+            pl.download(1)
+    cur = [api.ImgPyramidRGBD(ctx, st, None, *streams[b]["frames"][n - 1], 0.0) for b in range(B)]
+    est = [streams[b]["T_w_c"][n - 1].astype(np.float32) for b in range(B)]
+    single = []
+    for b in range(B):
+        single.append((trackers[b].assessTrackingQuality(est[b], cur[b]), trackers[b].last_quality))
+    status = api.assess_tracking_quality_batch(trackers, est, cur)
+    for b in range(B):
+        q, q1 = trackers[b].last_quality, single[b][1]
+        assert status[b] == single[b][0]
+        assert list(q.histogram) == list(q1.histogram) and list(q.overlaps) == list(q1.overlaps)
+        assert q.out_of_bounds == q1.out_of_bounds and q.n_frames == q1.n_frames == (2 if b == 3 else 3)
+        assert sum(q.histogram) > 0 and sum(q.histogram[1:]) > 0
+    # a points-only handle is not a frame: no keyframe promotion, no tracking, no vote as the current frame
+    pl = lists_ref[0][0]
+    arr = (C.c_void_p * 1)(pl.h)
+    assert ctx.lib.revo_pyr_make_keyframe_batch(ctx.h, 1, arr) == api.REVO_ERR_UNSUPPORTED
+    res = api.revo_quality_result()
+    e = np.eye(4, dtype=np.float32)
+    assert ctx.lib.revo_track_quality(ctx.h, pl.h, 2, 0, None, None, e.ctypes.data, 3, C.byref(res)) == api.REVO_ERR_UNSUPPORTED
+
+
+def test_stream_tracker_vote_policy_on_gpu(ctx, engine):
+    """StreamTracker(kf_policy="vote") over the CUDA backend (batched alignment, batched vote, batched promotions, handle
+    arrays) against separate REVO main loops on the same device: same keyframe decisions and world poses; every frame
+    handle is released at the end."""
+    from revo_b200 import api, synth
+    from revo_b200.stream import CudaBackend, StreamTracker
+    from revo_b200.system import REVO
+
+    w, h, n, B = 320, 240, 9, 4
+    cam = synth.intrinsics(w, h)
+    st = _settings(cam, 3)
+    streams = [synth.make_stream(300 + b, n, w, h, max_trans=0.01 + 0.04 * (b % 2), max_rot_deg=0.5 + 2.5 * (b % 2)) for b in range(B)]
+    single = [REVO(api.TrackerNew(ctx, api.TrackerSettings(), st)) for _ in range(B)]
+    for b in range(B):
+        for i in range(n):
+            single[b].processFrame(api.ImgPyramidRGBD(ctx, st, None, *streams[b]["frames"][i], 0.033 * i))
+    be = CudaBackend(ctx, st)
+    trk = StreamTracker(be, B, kf_policy="vote")
+    trk.keep_history = True
+    frames = lambda i: (np.stack([streams[b]["frames"][i][0] for b in range(B)]), np.stack([streams[b]["frames"][i][1] for b in range(B)]))
+    trk.start(*frames(0))
+    flags = []
+    for i in range(1, n):
+        trk.step(*frames(i))
+        flags.append(trk.just_added.copy())
+    assert trk.n_retracks == sum(len(s.retracked) for s in single) >= 1
+    for b in range(B):
+        assert [i + 1 for i, f in enumerate(flags) if f[b]] == single[b].retracked
+        traj = single[b].trajectory()
+        for i in range(1, n):
+            assert np.array_equal(trk.history[i - 1][0][b], traj[i]), (b, i)
+    trk.close()

@@ -157,3 +157,37 @@ def test_quality_vote_kernels_on_host(pyr_emu, orc32):
     assert rc == 0
     assert list(counters[:4]) == list(want["histogram"]) and list(counters[4:8]) == list(want["overlaps"]), (counters[:9], want)
     assert sum(counters[:4]) > 1000 and counters[5:8].sum() > 0
+
+
+def test_colored_point_cloud_kernels_on_host(pyr_emu, orc32):
+    """k_pyrdown_color + k_pcl_col_count / k_col_scan / k_pcl_col_scatter (ImgPyramidRGBD::generateColoredPcl,
+    imgpyramidrgbd.cpp:279-327) on the emulation layer vs the loop restatement (pinned to the compiled reference in
+    tests/test_oracle_ref.py): levels 0..2, edge cloud and dense cloud, 3 and 4 colour channels, bit-exact."""
+    import cv2
+
+    from oracle import oracle as O
+
+    p = synth_pair(4, 160, 120)
+    bgr, depth = p["key"]
+    po = oracle_pyramid(orc32, p["cam"], 3, bgr, depth)
+    bgra = np.ascontiguousarray(np.concatenate([bgr, np.full(bgr.shape[:2] + (1,), 255, np.uint8)], axis=2))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
+    f = C.c_float
+    rgb = bgr
+    for lvl in range(3):
+        if lvl:
+            rgb = cv2.pyrDown(rgb)
+        c = po.cams[lvl]
+        d = np.ascontiguousarray(po.depth[lvl], np.float32)
+        e = np.ascontiguousarray(po.edges[lvl], np.uint8)
+        for dense in (0, 1):
+            want = O.generate_colored_pcl(rgb, d, e, (c.fx, c.fy, c.cx, c.cy, c.w, c.h), 0.1, 5.2, bool(dense))
+            for img in (bgr, bgra):
+                out = np.zeros((c.w * c.h, 8), np.float32)
+                n = C.c_int(0)
+                rc = pyr_emu.emu_colored_pcl(vp(np.ascontiguousarray(img)), C.c_int(img.shape[2]), C.c_int(160), C.c_int(120), C.c_int(lvl), vp(d),
+                                             vp(e), C.c_int(c.w), C.c_int(c.h), f(c.fx), f(c.fy), f(c.cx), f(c.cy), C.c_int(dense), f(0.1),
+                                             f(5.2), vp(out), C.c_int(c.w * c.h), C.byref(n))
+                assert rc == 0 and n.value == want.shape[1], (lvl, dense, n.value, want.shape)
+                assert np.array_equal(out[:n.value].T, want), (lvl, dense)
+        assert want.shape[1] > 100

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _single_process(seeds, n_frames):
     sys.path.insert(0, ROOT)
-    from bench import OracleBackend
+    from oracle.stream_backend import OracleBackend
     from revo_b200 import synth
     from revo_b200.stream import StreamTracker
 
@@ -62,7 +62,7 @@ def test_pipelined_stepping_equals_sequential():
     in the same order as step(): identical poses with the (deterministic) oracle backend, and close() releases what is
     still in flight."""
     sys.path.insert(0, ROOT)
-    from bench import OracleBackend
+    from oracle.stream_backend import OracleBackend
     from revo_b200 import synth
     from revo_b200.stream import StreamTracker
 

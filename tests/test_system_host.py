@@ -190,7 +190,7 @@ def test_cuda_track_batch_adapter_conventions():
 def test_stream_tracker_vote_policy_equals_the_per_stream_main_loop():
     """StreamTracker(kf_policy="vote") -- the reference's keyframe policy (system.cpp:199-239) vectorised over the streams with
     handle arrays, batched votes and batched point-list copies -- against B separate REVO main loops over the same oracle
-    objects: same keyframe decisions, same re-tracks, same world poses (up to the rigid vs general 4x4 inverse in float32)."""
+    objects: same keyframe decisions, same re-tracks, same world poses."""
     from _oracle_system import OraclePyr, OracleTracker
     from oracle import oracle as O
     from oracle.stream_backend import OracleBackend
@@ -222,7 +222,7 @@ def test_stream_tracker_vote_policy_equals_the_per_stream_main_loop():
         assert [i + 1 for i, f in enumerate(kf_flags) if f[b]] == single[b].retracked
         traj = single[b].trajectory()
         for i in range(1, n):
-            assert np.allclose(st.history[i - 1][0][b], traj[i], atol=2e-6), (b, i)
+            assert np.array_equal(st.history[i - 1][0][b], traj[i]), (b, i)
     # the vote history stays bounded (first three entries vote, last three survive a clear-up)
     assert st.n_past.max() <= 6 and len(be._reg) <= B * (2 + 6)
     st.close()

@@ -32,7 +32,9 @@ def test_association_list_and_frames(tmp_path):
     assert len(assoc) == 2 and assoc[0][1] == "rgb/0.png" and assoc[1][3] == "depth/1.png"
     assert len(tum_io.read_associations(str(tmp_path / "associate.txt"), skip_first_n=1)) == 1
     frames = list(tum_io.iter_frames(str(tmp_path)))
-    assert len(frames) == 2 and abs(frames[1][0] - 1305031103.160407) < 1e-6
+    # useDepthTimeStamp: 0 in the reference's dataset configurations -> the rgb timestamp (iowrapperRGBD.cpp:266)
+    assert len(frames) == 2 and abs(frames[1][0] - 1305031103.175304) < 1e-6
+    assert abs(next(tum_io.iter_frames(str(tmp_path), use_depth_timestamp=True))[0] - 1305031102.160407) < 1e-6
     for (ts, bgr, raw), ref_raw, (ref_bgr, ref_depth) in zip(frames, raws, (p["key"], p["cur"])):
         assert bgr.dtype == np.uint8 and np.array_equal(bgr, ref_bgr)
         assert raw.dtype == np.uint16 and np.array_equal(raw, ref_raw)
