@@ -618,6 +618,9 @@ def main():
             "value": B * Kv / (vr["ms"] * 1e-3), "unit": "frames/s", "ms_per_step": vr["ms"] / Kv, "steps": Kv,
             "gn_iters_per_sec": vr["evals"] / (vr["ms"] * 1e-3),
             "keyframe_switches_per_frame": vr["n_keyframes"] / float(B * (Kv + W)),
+            "note": "on these smooth synthetic streams the vote rarely (often never) asks for a new keyframe within the run, so this "
+                    "number carries the cost of voting, not of promotions; tests/test_gpu_track.py::test_stream_tracker_vote_policy_on_gpu "
+                    "drives streams that do switch and checks decisions and poses against per-stream main loops",
             "policy": "assessTrackingQuality for all streams in one launch pair (revo_track_quality_batch); streams voting NEW_KF "
                       "promote their previous frame, are aligned again and vote again in a second, smaller launch of each kind "
                       "(system.cpp:199-239); one device->host read of the counters per vote"}

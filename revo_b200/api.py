@@ -73,6 +73,11 @@ class revo_quality_result(C.Structure):
                 ("status", C.c_int32), ("out_of_bounds", C.c_int32), ("n_frames", C.c_int32)]
 
 
+QUALITY_RESULT_DTYPE = np.dtype([("histogram", np.int32, 4), ("overlaps", np.int32, 4), ("overlap_measure", np.float32), ("status", np.int32),
+                                 ("out_of_bounds", np.int32), ("n_frames", np.int32)])
+assert QUALITY_RESULT_DTYPE.itemsize == C.sizeof(revo_quality_result)
+
+
 class revo_trace_entry(C.Structure):
     _fields_ = [("error", C.c_float), ("lam", C.c_float), ("accepted", C.c_int32), ("good", C.c_int32),
                 ("bad", C.c_int32), ("level", C.c_int32)]

@@ -773,18 +773,16 @@ int revo_pyr_copy_points_batch(revo_ctx *ctx, int n, revo_pyr *const *pyrs, int 
         if (lvl < 0 || lvl >= pyrs[i]->n_levels || !pyrs[i]->lv[lvl].pts) return REVO_ERR_BAD_LEVEL;
     }
     REVO_CUDA(ctx, cudaSetDevice(ctx->device));
-    // The lists' lengths live on the device; read them once (the caller is between two frames here, the vote that follows
-    // reads counters back anyway) so that the copies take the lists' size and not their capacity.
-    std::vector<int> cnt((size_t)n);
-    for (int i = 0; i < n; ++i) wait_for_build(ctx, pyrs[i]);
+    // The lists' lengths live on the device and are not read back here (no host synchronisation between two frames): a copy is
+    // allocated at the source list's capacity (w h / 2 + 1024 points: 170 KB at level 2 of VGA) and filled to its length.
+    for (int i = 0; i < n; ++i)
+        if (i == 0 || pyrs[i]->slab != pyrs[i - 1]->slab) wait_for_build(ctx, pyrs[i]);
     {
-        // gather the counts with one kernel-free pass: they sit in the slabs' counter blocks, 2 ints apart per level
-        int rc = ensure_scratch(ctx, align_up(sizeof(PointListCopy) * (size_t)n, 256) + 4 * (size_t)n);
+        int rc = ensure_scratch(ctx, align_up(sizeof(PointListCopy) * (size_t)n, 256));
         if (rc) return rc;
     }
-    for (int i = 0; i < n; ++i)
-        REVO_CUDA(ctx, cudaMemcpyAsync(&cnt[i], pyrs[i]->lv[lvl].n_pts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    REVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int> cnt((size_t)n);
+    for (int i = 0; i < n; ++i) cnt[i] = pyrs[i]->lv[lvl].pts_cap;
     std::vector<size_t> off((size_t)n + 1);
     off[0] = align_up(8 * (size_t)n, 256);
     for (int i = 0; i < n; ++i) off[i + 1] = off[i] + align_up((size_t)std::max(cnt[i], 1) * 16, 256);
@@ -914,10 +912,11 @@ int revo_pyr_colored_pcl(revo_ctx *ctx, const revo_pyr *pyr, int lvl, int dense,
                          size_t capacity_points, int *n_out)
 {
     if (!ctx || !pyr || !bgr || !n_out || (channels != 3 && channels != 4)) return REVO_ERR_INVALID_ARG;
-    if (lvl < 0 || lvl >= pyr->n_levels) return REVO_ERR_BAD_LEVEL;
-    if (points_only(pyr)) return REVO_ERR_UNSUPPORTED;
     *n_out = 0;
+    if (lvl < 0) return REVO_ERR_BAD_LEVEL;
+    if (points_only(pyr)) return REVO_ERR_UNSUPPORTED;
     if (lvl > 2) return REVO_OK;      // the reference only has a colour image for levels 0..2 (imgpyramidrgbd.cpp:288-297)
+    if (lvl >= pyr->n_levels) return REVO_ERR_BAD_LEVEL;
     REVO_CUDA(ctx, cudaSetDevice(ctx->device));
     const ImgLevel &L = pyr->lv[lvl];
     const int w0 = pyr->lv[0].w, h0 = pyr->lv[0].h;

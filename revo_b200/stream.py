@@ -318,8 +318,8 @@ class CudaBackend:
         npast = np.ascontiguousarray(n_past, np.int32)
         poses = np.ascontiguousarray(np.asarray(past_poses, np.float32).transpose(0, 1, 3, 2))     # column-major 4x4
         e = np.ascontiguousarray(np.asarray(est, np.float32).transpose(0, 2, 1))
-        res = (self.api.revo_quality_result * n)()
+        res = np.zeros(n, self.api.QUALITY_RESULT_DTYPE)
         self.ctx.check(self.ctx.lib.revo_track_quality_batch(self.ctx.h, n, pc, HISTOGRAM_LEVEL, npast.ctypes.data, pp, poses.ctypes.data,
-                                                             e.ctypes.data, N_VOTING, res))
+                                                             e.ctypes.data, N_VOTING, res.ctypes.data_as(C.POINTER(self.api.revo_quality_result))))
         self.last_votes = res
-        return np.array([r.status for r in res], np.int64)
+        return res["status"].astype(np.int64)
