@@ -663,53 +663,122 @@ int launch_colored_pcl(revo_ctx *ctx, const ImgLevel *d_desc_one, int w, int h, 
 
 // ---------------------------------------------------------------------------
 // K7: exact Euclidean distance transform to the nearest edge pixel, out = sqrtf(d2).
-//  (a) column pass: vertical distance g(x,y) to the nearest edge in the column (int, kEdtInf if none)
+//  (a) column pass: vertical distance g(x,y) to the nearest edge in the column (u16, kEdtInf if none).  A column is cut into
+//      segments of <= 64 rows; a thread owns (column, segment), packs the segment's edge bytes into a 64-bit mask, exchanges
+//      "first / last edge row of my segment" with the other segments of its column through shared memory, and gets every row's
+//      distance to the nearest edge above / below with clz / ffs on the mask: no sequential dependency along the column (the
+//      first version walked all h rows twice per thread and was latency-bound), 1 byte read + 2 bytes written per pixel.
 //  (b) row pass: d2(x,y) = min_j (x-j)^2 + g(j,y)^2 by an outward search that stops once r^2 >= best
 //      (exact; typical DT values are small so the search is short).
-// K8: {0.5(dt[i-1]-dt[i+1]), 0.5(dt[i-w]-dt[i+w]), dt[i], 0} for rows 1..h-2, zeros elsewhere.
+// K8: {0.5(dt[i-1]-dt[i+1]), 0.5(dt[i-w]-dt[i+w]), dt[i], 0} for rows 1..h-2, zeros elsewhere (linear indices: column 0 takes
+//     its left neighbour from the end of the previous row, like the reference).  k_edt_rows_opt does (b) and K8 in one kernel
+//     for a band of rows: the distances of band + halo rows stay in shared memory, dt is written once and never read back,
+//     and the texels are stored tile by tile (full 128-byte lines).
 // ---------------------------------------------------------------------------
 constexpr int kEdtInf = 1 << 14;
 // value of every pixel when the edge map is empty: what OpenCV's own trueDistTrans returns (cv2 4.13, IPP off)
 constexpr float kEdtEmpty = 65536.0f;
 
-__global__ void k_edt_cols(const ImgLevel *__restrict__ desc, int w, int h)
+__global__ void __launch_bounds__(1024) k_edt_cols(const ImgLevel *__restrict__ desc, int w, int h, int seg_rows)
 {
+    __shared__ short first_s[32][32];                      // [segment][column of the block]: first / last edge row, -1 = none
+    __shared__ short last_s[32][32];
     const int f = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= w) return;
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, n_seg = blockDim.x >> 5;
+    const int x = blockIdx.x * 32 + lane;
+    const int y0 = seg * seg_rows, y1 = min(h, y0 + seg_rows);
+    const bool in = x < w;
     const uint8_t *__restrict__ e = desc[f].edges;
-    int *__restrict__ g = desc[f].labels;
-    int d = kEdtInf;
-    for (int y = 0; y < h; ++y) {
-        d = e[(size_t)y * w + x] ? 0 : min(d + 1, kEdtInf);
-        g[(size_t)y * w + x] = d;
+    unsigned long long m = 0;                               // bit k = edge at row y0 + k
+    if (in)
+        for (int y = y0; y < y1; ++y) m |= (unsigned long long)(e[(size_t)y * w + x] != 0) << (y - y0);
+    first_s[seg][lane] = m ? (short)(y0 + __ffsll((long long)m) - 1) : (short)-1;
+    last_s[seg][lane] = m ? (short)(y0 + 63 - __clzll((long long)m)) : (short)-1;
+    __syncthreads();
+    if (!in) return;
+    int above = -kEdtInf, below = 2 * kEdtInf;              // nearest edge rows outside the segment
+    for (int s2 = seg - 1; s2 >= 0; --s2)
+        if (last_s[s2][lane] >= 0) { above = last_s[s2][lane]; break; }
+    for (int s2 = seg + 1; s2 < n_seg; ++s2)
+        if (first_s[s2][lane] >= 0) { below = first_s[s2][lane]; break; }
+    unsigned short *__restrict__ g = (unsigned short *)desc[f].labels;
+    for (int y = y0; y < y1; ++y) {
+        const int k = y - y0;
+        const unsigned long long lo = m & (~0ull >> (63 - k));      // edges at rows <= y inside the segment
+        const unsigned long long hi = m >> k;                        // edges at rows >= y
+        const int up = lo ? k - (63 - __clzll((long long)lo)) : y - above;
+        const int dn = hi ? __ffsll((long long)hi) - 1 : below - y;
+        g[(size_t)y * w + x] = (unsigned short)min(min(up, dn), kEdtInf);
     }
-    d = kEdtInf;
-    for (int y = h - 1; y >= 0; --y) {
-        const int cur = g[(size_t)y * w + x];
-        d = min(cur, min(d + 1, kEdtInf));
-        if (d < cur) g[(size_t)y * w + x] = d;
+}
+
+// one row of (b): squared distance of pixel x from the column distances of its row
+__device__ __forceinline__ float edt_row_px(const unsigned short *__restrict__ grow, int x, int w)
+{
+    const int g0 = grow[x];
+    int best = g0 * g0;
+    const int rmax = max(x, w - 1 - x);
+    for (int r = 1; r <= rmax && r * r < best; ++r) {
+        const int r2 = r * r;
+        if (x - r >= 0) { const int gl = grow[x - r]; best = min(best, r2 + gl * gl); }
+        if (x + r < w) { const int gr = grow[x + r]; best = min(best, r2 + gr * gr); }
     }
+    return best >= kEdtInf * kEdtInf ? kEdtEmpty : sqrtf((float)best);
 }
 
 __global__ void __launch_bounds__(256) k_edt_rows(const ImgLevel *__restrict__ desc, int w, int h)
 {
-    extern __shared__ int grow[];
+    extern __shared__ unsigned short grow[];
     const int f = blockIdx.z, y = blockIdx.x;
-    const int *__restrict__ g = desc[f].labels + (size_t)y * w;
+    const unsigned short *__restrict__ g = (const unsigned short *)desc[f].labels + (size_t)y * w;
     for (int i = threadIdx.x; i < w; i += blockDim.x) grow[i] = g[i];
     __syncthreads();
     float *__restrict__ out = desc[f].dt + (size_t)y * w;
-    for (int x = threadIdx.x; x < w; x += blockDim.x) {
-        const int g0 = grow[x];
-        int best = g0 * g0;
-        const int rmax = max(x, w - 1 - x);
-        for (int r = 1; r <= rmax && r * r < best; ++r) {
-            const int r2 = r * r;
-            if (x - r >= 0) { const int gl = grow[x - r]; best = min(best, r2 + gl * gl); }
-            if (x + r < w) { const int gr = grow[x + r]; best = min(best, r2 + gr * gr); }
+    for (int x = threadIdx.x; x < w; x += blockDim.x) out[x] = edt_row_px(grow, x, w);
+}
+
+__device__ __forceinline__ uint2 pack_texel(const float4 t);
+
+// (b) + K8 for a band of kEdtBand rows (a multiple of 4: whole tile rows) per CTA; dynamic shared memory:
+// (kEdtBand + 2) * w * (2 + 4) bytes
+constexpr int kEdtBand = 8;
+__global__ void __launch_bounds__(256) k_edt_rows_opt(const ImgLevel *__restrict__ desc, int w, int h)
+{
+    extern __shared__ unsigned short grow[];
+    const int f = blockIdx.z;
+    const int y0 = blockIdx.x * kEdtBand;
+    const int ya = max(y0 - 1, 0), yb = min(y0 + kEdtBand, h - 1);          // rows held (inclusive), halo included
+    const int nr = yb - ya + 1;
+    float *ds = (float *)(grow + (size_t)(kEdtBand + 2) * w);                // (kEdtBand + 2) * w * 2 bytes is a multiple of 4
+    const unsigned short *__restrict__ g = (const unsigned short *)desc[f].labels + (size_t)ya * w;
+    for (int i = threadIdx.x; i < nr * w; i += blockDim.x) grow[i] = g[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * w; i += blockDim.x) {
+        const int r = i / w;
+        ds[i] = edt_row_px(grow + (size_t)r * w, i - r * w, w);
+    }
+    __syncthreads();
+    const int y_end = min(y0 + kEdtBand, h);
+    float *__restrict__ dt = desc[f].dt;
+    for (int i = threadIdx.x; i < (y_end - y0) * w; i += blockDim.x) dt[(size_t)y0 * w + i] = ds[(size_t)(y0 - ya) * w + i];
+    // texels, tile by tile: 16 consecutive threads write the 16 texels (128 bytes) of one 4x4 tile
+    const int tw = (w + 3) >> 2;
+    uint2 *__restrict__ opt = desc[f].opt;
+    for (int t = threadIdx.x; t < (kEdtBand / 4) * tw * 16; t += blockDim.x) {
+        const int tile = t >> 4, k = t & 15;
+        const int ty = tile / tw, tx = tile - ty * tw;
+        const int x = tx * 4 + (k & 3), y = y0 + ty * 4 + (k >> 2);
+        if (x >= w || y >= h) continue;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 1 && y <= h - 2) {
+            const float *row = ds + (size_t)(y - ya) * w;
+            const float left = x > 0 ? row[x - 1] : row[-1];                 // linear index i-1: end of the previous row
+            const float right = x < w - 1 ? row[x + 1] : row[w];             // linear index i+1: start of the next row
+            o.x = __fmul_rn(0.5f, __fsub_rn(left, right));
+            o.y = __fmul_rn(0.5f, __fsub_rn(row[x - w], row[x + w]));
+            o.z = row[x];
         }
-        out[x] = best >= kEdtInf * kEdtInf ? kEdtEmpty : sqrtf((float)best);
+        opt[opt_texel_index(x, y, tw)] = pack_texel(o);
     }
 }
 
@@ -867,13 +936,26 @@ int launch_copy_point_lists(revo_ctx *ctx, const PointListCopy *d_tab, int n)
 int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h)
 {
     {
-        dim3 grid(cdiv(w, 64), 1, n);
-        k_edt_cols<<<grid, 64, 0, ctx->stream>>>(d_desc, w, h);
+        // segments of <= 64 rows, one warp each (h <= 2048)
+        int n_seg = cdiv(h, 64);
+        n_seg = n_seg < 1 ? 1 : n_seg;
+        if (n_seg > 32) return REVO_ERR_UNSUPPORTED;
+        dim3 grid(cdiv(w, 32), 1, n);
+        k_edt_cols<<<grid, n_seg * 32, 0, ctx->stream>>>(d_desc, w, h, cdiv(h, n_seg));
         LAUNCH_CHECK(ctx);
+    }
+    const size_t smem_fused = (size_t)(kEdtBand + 2) * w * 6;
+    static const int no_fuse = getenv("REVO_EDT_NO_FUSE") ? atoi(getenv("REVO_EDT_NO_FUSE")) : 0;      // A/B switch
+    if (smem_fused <= 64 * 1024 && !no_fuse) {
+        REVO_CUDA(ctx, cudaFuncSetAttribute(k_edt_rows_opt, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        dim3 grid(cdiv(h, kEdtBand), 1, n);
+        k_edt_rows_opt<<<grid, 256, smem_fused, ctx->stream>>>(d_desc, w, h);
+        LAUNCH_CHECK(ctx);
+        return REVO_OK;
     }
     {
         dim3 grid(h, 1, n);
-        k_edt_rows<<<grid, 256, w * sizeof(int), ctx->stream>>>(d_desc, w, h);
+        k_edt_rows<<<grid, 256, w * sizeof(unsigned short), ctx->stream>>>(d_desc, w, h);
         LAUNCH_CHECK(ctx);
     }
     {

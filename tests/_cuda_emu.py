@@ -175,6 +175,8 @@ static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 
 static inline unsigned long long __brevll(unsigned long long v) { unsigned long long r = 0; for (int i = 0; i < 64; ++i) r |= ((v >> i) & 1ull) << (63 - i); return r; }
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline int __ffsll(long long v) { return v ? __builtin_ctzll((unsigned long long)v) + 1 : 0; }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c)
 {
