@@ -737,7 +737,33 @@ __global__ void __launch_bounds__(256) k_edt_rows(const ImgLevel *__restrict__ d
     for (int x = threadIdx.x; x < w; x += blockDim.x) out[x] = edt_row_px(grow, x, w);
 }
 
-__device__ __forceinline__ uint2 pack_texel(const float4 t);
+// The reference's {gx, gy, dt, .} float4 texel (imgpyramidrgbd.cpp:255-276) at linear index i; zeros in rows 0 and h-1.
+__device__ __forceinline__ float4 opt_texel(const float *__restrict__ dt, size_t i, int w, int h)
+{
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= (size_t)w && i < (size_t)w * (h - 1)) {
+        o.x = __fmul_rn(0.5f, __fsub_rn(dt[i - 1], dt[i + 1]));
+        o.y = __fmul_rn(0.5f, __fsub_rn(dt[i - w], dt[i + w]));
+        o.z = dt[i];
+    }
+    return o;
+}
+
+// Gradient components lie in [-1, 1] (|dt[a] - dt[b]| <= 2 for pixels two apart): 16-bit fixed point, step 1/32764 (a multiple of 4, so the frequent exact values 0, +-1/4, +-1/2, +-1 carry no rounding bias).
+__device__ __forceinline__ uint32_t pack_grad(float gx, float gy)
+{
+    const int qx = __float2int_rn(fminf(fmaxf(gx, -1.f), 1.f) * 32764.f);
+    const int qy = __float2int_rn(fminf(fmaxf(gy, -1.f), 1.f) * 32764.f);
+    return ((uint32_t)qx & 0xffffu) | ((uint32_t)qy << 16);
+}
+
+// K8 (device layout, internal.h: opt_texel_index): one 8-byte texel {dt float32 | snorm16 gx, gy} per pixel in 4x4 tiles.
+// dt stays float32, only the Jacobian direction is quantised (1.5e-5 absolute).  The reference's float4 array is produced on
+// demand for the accessor (k_opt_struct_f4).
+__device__ __forceinline__ uint2 pack_texel(const float4 t)
+{
+    return make_uint2(__float_as_uint(t.z), pack_grad(t.x, t.y));
+}
 
 // (b) + K8 for a band of kEdtBand rows (a multiple of 4: whole tile rows) per CTA; dynamic shared memory:
 // (kEdtBand + 2) * w * (2 + 4) bytes
@@ -780,34 +806,6 @@ __global__ void __launch_bounds__(256) k_edt_rows_opt(const ImgLevel *__restrict
         }
         opt[opt_texel_index(x, y, tw)] = pack_texel(o);
     }
-}
-
-// The reference's {gx, gy, dt, .} float4 texel (imgpyramidrgbd.cpp:255-276) at linear index i; zeros in rows 0 and h-1.
-__device__ __forceinline__ float4 opt_texel(const float *__restrict__ dt, size_t i, int w, int h)
-{
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i >= (size_t)w && i < (size_t)w * (h - 1)) {
-        o.x = __fmul_rn(0.5f, __fsub_rn(dt[i - 1], dt[i + 1]));
-        o.y = __fmul_rn(0.5f, __fsub_rn(dt[i - w], dt[i + w]));
-        o.z = dt[i];
-    }
-    return o;
-}
-
-// Gradient components lie in [-1, 1] (|dt[a] - dt[b]| <= 2 for pixels two apart): 16-bit fixed point, step 1/32764 (a multiple of 4, so the frequent exact values 0, +-1/4, +-1/2, +-1 carry no rounding bias).
-__device__ __forceinline__ uint32_t pack_grad(float gx, float gy)
-{
-    const int qx = __float2int_rn(fminf(fmaxf(gx, -1.f), 1.f) * 32764.f);
-    const int qy = __float2int_rn(fminf(fmaxf(gy, -1.f), 1.f) * 32764.f);
-    return ((uint32_t)qx & 0xffffu) | ((uint32_t)qy << 16);
-}
-
-// K8 (device layout, internal.h: opt_texel_index): one 8-byte texel {dt float32 | snorm16 gx, gy} per pixel in 4x4 tiles.
-// dt stays float32, only the Jacobian direction is quantised (1.5e-5 absolute).  The reference's float4 array is produced on
-// demand for the accessor (k_opt_struct_f4).
-__device__ __forceinline__ uint2 pack_texel(const float4 t)
-{
-    return make_uint2(__float_as_uint(t.z), pack_grad(t.x, t.y));
 }
 
 __global__ void __launch_bounds__(256) k_opt_struct(const ImgLevel *__restrict__ desc, int w, int h)
