@@ -642,8 +642,9 @@ __device__ __forceinline__ void canny_nms_body(const ImgLevel *__restrict__ desc
         pv = qv; ph = qh;
     }
 }
-// The same body at three register budgets (A/B switch REVO_NMS_MINBLOCKS: 4 = the compiler's 111 registers, 5 = at most 96,
-// 6 = at most 80 with a few spilled words); more resident warps against fewer registers for the three rows of windows.
+// The same body at three register budgets (A/B switch REVO_NMS_MINBLOCKS: 4 = the compiler's 111 registers, 5 = at most 96 (default:
+// the kernel's top stall is the gray-row load, 20 instead of 16 resident warps are worth 2 % of the build), 6 = at most 80 with a
+// few spilled words (no better than 4)).
 __global__ void __launch_bounds__(128) k_canny_nms(const ImgLevel *__restrict__ desc, int w, int h, int low, int high, int wp32, int rows_per_strip)
 {
     canny_nms_body(desc, w, h, low, high, wp32, rows_per_strip);     // warp-synchronous inside (__shfl_*_sync, __any_sync)
@@ -785,7 +786,7 @@ __global__ void __launch_bounds__(1024) k_canny_hyst(const ImgLevel *__restrict_
 // tokens = nobody awake and nothing in flight, for good.  (The round barrier of the previous version was 44 % of this
 // kernel's warp time: profiles/r2_pyramid_kernels_ncu.txt.)  wp = row pitch in words of type W.
 template <typename W>
-__global__ void __launch_bounds__(1024) k_canny_hyst_smem(const ImgLevel *__restrict__ desc, int w, int h, int wp, int P, int fuse_expand)
+__global__ void __launch_bounds__(1024) k_canny_hyst_smem(const ImgLevel *__restrict__ desc, int w, int h, int wp)
 {
     extern __shared__ unsigned long long hs_mem[];
     __shared__ unsigned flag_from_above[32];             // "your first row got a new seed" (from the warp above)
@@ -885,48 +886,10 @@ __global__ void __launch_bounds__(1024) k_canny_hyst_smem(const ImgLevel *__rest
         }
     }
     __syncthreads();
-    if (!fuse_expand) {
-        for (size_t i = threadIdx.x; i < nw; i += blockDim.x) gS[i] = S[i];
-        return;
-    }
-    // Fused output stage (what k_canny_expand + k_hist_finalize do for the other paths): the CTA owns the whole image, so the
-    // strong mask goes from shared memory straight to the edge bytes, and the patch counters of the edge histogram
-    // (generateDistHistogram, imgpyramidrgbd.cpp:111-137) live in shared memory (the candidate mask's space, no longer needed)
-    // instead of a global plane that has to be cleared, filled with atomics and read back.  The CTAs of a launch finish their
-    // floods at different times, so these stores fill the issue slots the latency-bound floods of the other CTA on the SM leave.
-    int *hcnt = (int *)C;
-    const int n_h = (L.hist_w > 0 && L.hist_h > 0) ? L.hist_w * L.hist_h : 0;
-    for (int i = threadIdx.x; i < n_h; i += blockDim.x) hcnt[i] = 0;
-    if (threadIdx.x == 0) tokens = 0;
-    __syncthreads();
-    const int chunks_x = (w + 15) / 16, wp32 = wp * (int)(sizeof(W) / 4);
-    const unsigned *S32 = (const unsigned *)S;
-    for (int t = threadIdx.x; t < chunks_x * h; t += blockDim.x) {
-        const int y = t / chunks_x, x0 = (t - y * chunks_x) * 16;
-        const unsigned bits = (S32[(size_t)y * wp32 + (x0 >> 5)] >> (x0 & 31)) & 0xffffu;
-        expand_store16(L, w, y, x0, bits);
-        if (bits && n_h) {
-            const int py = y / P;
-            if (py < L.hist_h)
-                for (unsigned mm = bits; mm;) {
-                    const int b = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const int px = (x0 + b) / P;
-                    if (px < L.hist_w) atomicAdd(hcnt + py * L.hist_w + px, 1);
-                }
-        }
-    }
-    if (!n_h) return;
-    __syncthreads();
-    int nz = 0;
-    for (int i = threadIdx.x; i < n_h; i += blockDim.x) {
-        const uint8_t v = (uint8_t)(hcnt[i] & 255);       // cv::Mat_<uchar> counters wrap (imgpyramidrgbd.cpp:126)
-        L.hist[i] = v;
-        nz += v != 0;
-    }
-    if (nz) atomicAdd(&tokens, nz);
-    __syncthreads();
-    if (threadIdx.x == 0) *L.nz_patches = tokens;
+    // (Writing the edge bytes and the patch histogram from here -- one kernel less, no mask round trip -- was measured: the
+    // CTAs of a launch finish together, so the stores of 512 threads per image do not hide under anybody's flood, and the build
+    // got 0.12 ms per 256 frames SLOWER than with the streaming k_canny_expand.  profiles/r2_pyramid_kernels_ncu.txt)
+    for (size_t i = threadIdx.x; i < nw; i += blockDim.x) gS[i] = S[i];
 }
 
 // ---- (3) bit mask -> byte maps + patch counters ------------------------------------------------------------------
@@ -964,20 +927,17 @@ static int launch_canny_bits(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w
     const int wp64 = cdiv(w, 64), wp32 = 2 * wp64;
     // a warp owns a band of up to 30 rows (16 warps at VGA: two CTAs per SM, so 256 images run in ONE wave on 148 SMs)
     static const int band = getenv("REVO_HYST_BAND") ? atoi(getenv("REVO_HYST_BAND")) : 30;
-    static const int no_fuse = getenv("REVO_CANNY_NO_FUSE") ? atoi(getenv("REVO_CANNY_NO_FUSE")) : 0;      // A/B switch
     int warps = cdiv(h, band);
     warps = warps < 1 ? 1 : (warps > 32 ? 32 : warps);
     const size_t smem = (size_t)2 * wp64 * 8 * h;
     const bool in_smem = smem <= 200 * 1024 && cdiv(h, warps) <= 32;
-    // the shared-memory hysteresis writes edge bytes and histogram itself when its candidate-mask space can hold the patch counters
-    const bool fused = in_smem && !no_fuse && (size_t)std::max(hist_w * hist_h, 0) * sizeof(int) <= smem / 2;
-    if (!fused && hist_w > 0 && hist_h > 0)
+    if (hist_w > 0 && hist_h > 0)
         REVO_CUDA(ctx, cudaMemset2DAsync(d_counts0, counts_stride, 0, (size_t)hist_w * hist_h * sizeof(int), (size_t)n, ctx->stream));
     {
         // rows per warp strip: long strips amortise the 2-row prologue, short ones keep the small levels parallel
         const int rs = h >= 400 ? NMS_RS : (h >= 200 ? 18 : 9);
         dim3 grid(cdiv(w, 32 * NMS_PX), cdiv(cdiv(h, rs), 4), n);
-        static const int mb = getenv("REVO_NMS_MINBLOCKS") ? atoi(getenv("REVO_NMS_MINBLOCKS")) : 4;
+        static const int mb = getenv("REVO_NMS_MINBLOCKS") ? atoi(getenv("REVO_NMS_MINBLOCKS")) : 5;
         if (mb == 5)
             k_canny_nms_mb5<<<grid, 128, 0, ctx->stream>>>(d_desc, w, h, low, high, wp32, rs);
         else if (mb == 6)
@@ -990,18 +950,17 @@ static int launch_canny_bits(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w
         if (in_smem) {
             if (wp32 <= 32) {
                 REVO_CUDA(ctx, cudaFuncSetAttribute(k_canny_hyst_smem<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                k_canny_hyst_smem<unsigned><<<n, warps * 32, smem, ctx->stream>>>(d_desc, w, h, wp32, patch, fused ? 1 : 0);
+                k_canny_hyst_smem<unsigned><<<n, warps * 32, smem, ctx->stream>>>(d_desc, w, h, wp32);
             } else {
                 REVO_CUDA(ctx, cudaFuncSetAttribute(k_canny_hyst_smem<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     200 * 1024));
-                k_canny_hyst_smem<unsigned long long><<<n, warps * 32, smem, ctx->stream>>>(d_desc, w, h, wp64, patch, fused ? 1 : 0);
+                k_canny_hyst_smem<unsigned long long><<<n, warps * 32, smem, ctx->stream>>>(d_desc, w, h, wp64);
             }
         } else {
             k_canny_hyst<<<n, warps * 32, 0, ctx->stream>>>(d_desc, w, h, wp64);
         }
         LAUNCH_CHECK(ctx);
     }
-    if (fused) return REVO_OK;
     {
         const int chunks_x = cdiv(w, 16);
         dim3 grid(cdiv(chunks_x * h, 256), 1, n);
