@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--levels", type=int, default=4)
     ap.add_argument("--kf-interval", type=int, default=10)
+    ap.add_argument("--track-max-clusters", type=int, default=-1,
+                    help="resident-cluster cap of the tracking kernel in the pipelined runs (-1 = the library's default for pipelines, 0 = none)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--kf-policy", choices=("interval", "vote"), default="interval",
                     help="interval: a keyframe every --kf-interval frames (the fixed workload of BASELINE.json configs[1]); vote: the "
@@ -422,7 +424,8 @@ def main():
     build_ctx = api.Context(local_rank)    # second stream: upload + pyramid build of frame k+1 overlap tracking of frame k
 
     def timed_run(src_bgr, src_depth, sample_clocks, pipelined=False, K=K, keep_history=False, policy=None):
-        be = CudaBackend(ctx, settings, build_ctx=build_ctx if pipelined else None)
+        be = CudaBackend(ctx, settings, build_ctx=build_ctx if pipelined else None,
+                         track_max_clusters=None if args.track_max_clusters < 0 else args.track_max_clusters)
         st = StreamTracker(be, B, args.kf_interval, policy or args.kf_policy)
         st.keep_history = keep_history
         sampler = ClockSampler(local_rank) if sample_clocks else None

@@ -273,10 +273,14 @@ REVO_API int revo_track_quality_batch(revo_ctx *ctx, int n, revo_pyr *const *cur
 /* Launch-shape override for revo_track_batch (0 = automatic): CTAs per pair (cluster size 1,2,4,8,16)
  * and threads per CTA. */
 REVO_API int revo_ctx_set_track_shape(revo_ctx *ctx, int ctas_per_pair, int threads_per_cta);
-/* Tracking engine: 0 = automatic (= 1), 1 = one thread-block cluster per pair (track.cu; fastest at every batch size
- * measured and the only engine of revo_track_split), 2 = chip-wide task queue (track_queue.cu: every evaluation is cut into
- * chunk tasks that any CTA of the persistent grid may run), 3 = warp-specialised clusters working on two pairs
- * (track_pp.cu).  chunk_points: minimum points per task of engine 2 (0 = automatic). */
+/* Cap on the clusters of the persistent tracking kernel that are resident at a time (0 = as many as the device holds: 74 clusters
+ * of 8 CTAs on B200).  For pipelines that build the pyramids of the next frames on a second context while this one tracks: the
+ * tracker owns every register of an SM at full residency, so a build kernel can only start when a tracker CTA retires; with a few
+ * cluster slots left free both run side by side and fill each other's stalls.  Timed alone the kernel is fastest uncapped. */
+REVO_API int revo_ctx_set_track_max_clusters(revo_ctx *ctx, int max_clusters);
+/* Kept for ABI compatibility: there is ONE tracking engine (one thread-block cluster per pair, track.cu).  engine 0 / 1 are
+ * accepted, anything else answers REVO_ERR_UNSUPPORTED (the round-1 alternatives -- task queue, ping-pong clusters -- measured
+ * slower and are no longer built); chunk_points is ignored. */
 REVO_API int revo_ctx_set_track_engine(revo_ctx *ctx, int engine, int chunk_points);
 /* Pre-size the device memory pool: later stream-ordered slab allocations up to `bytes` in total are served
  * from cached memory instead of the driver (call once before a steady-state stream starts). */

@@ -105,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "revo_pyr_timestamp", "revo_pyr_num_edges", "revo_pyr_download", "revo_pyr_upload_level", "revo_eval",
     "revo_track_level", "revo_track", "revo_track_batch", "revo_ctx_set_track_shape", "revo_split_export",
     "revo_split_open", "revo_track_split", "revo_ctx_set_track_engine", "revo_ctx_reserve", "revo_ctx_last_upload_ms", "revo_pyr_create_batch_u16", "revo_track_quality", "revo_quat_to_R9", "revo_R9_to_quat",
-    "revo_pyr_colored_pcl", "revo_pyr_copy_points_batch", "revo_track_quality_batch",
+    "revo_pyr_colored_pcl", "revo_pyr_copy_points_batch", "revo_track_quality_batch", "revo_ctx_set_track_max_clusters",
 ]
 
 
@@ -155,6 +155,7 @@ def load_library():
     lib.revo_track_batch.argtypes = [vp, C.POINTER(revo_tracker_config), i32, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp,
                                      i32, vp]
     lib.revo_ctx_set_track_shape.argtypes = [vp, i32, i32]
+    lib.revo_ctx_set_track_max_clusters.argtypes = [vp, i32]
     lib.revo_track_quality.argtypes = [vp, vp, i32, i32, C.POINTER(vp), vp, vp, i32, C.POINTER(revo_quality_result)]
     lib.revo_track_quality_batch.argtypes = [vp, i32, C.POINTER(vp), i32, vp, C.POINTER(vp), vp, vp, i32, C.POINTER(revo_quality_result)]
     lib.revo_pyr_copy_points_batch.argtypes = [vp, i32, C.POINTER(vp), i32, C.POINTER(vp)]
@@ -334,8 +335,12 @@ class Context:
     def set_track_shape(self, ctas_per_pair: int = 0, threads_per_cta: int = 0):
         self.check(self.lib.revo_ctx_set_track_shape(self.h, ctas_per_pair, threads_per_cta))
 
+    def set_track_max_clusters(self, max_clusters: int = 0):
+        """Cap on the resident clusters of the tracking kernel (0 = all): room for the build kernels of a second context."""
+        self.check(self.lib.revo_ctx_set_track_max_clusters(self.h, max_clusters))
+
     def set_track_engine(self, engine: int = 0, chunk_points: int = 0):
-        """0 = automatic, 1 = one cluster per pair, 2 = chip-wide task queue (see revo_ctx_set_track_engine)."""
+        """Kept for ABI compatibility: 0 / 1 = the cluster engine (the only one), anything else raises REVO_ERR_UNSUPPORTED."""
         self.check(self.lib.revo_ctx_set_track_engine(self.h, engine, chunk_points))
 
     def reserve(self, nbytes: int):

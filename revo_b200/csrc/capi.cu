@@ -203,7 +203,7 @@ int revo_ctx_create(int device, revo_ctx **out)
     ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0; ctx->pinned_kf = nullptr; ctx->pinned_kf_bytes = 0; ctx->pinned_kf_busy = false;
     for (int i = 0; i < 2; ++i) { ctx->stage[i] = nullptr; ctx->stage_bytes[i] = 0; ctx->stage_used[i] = false; }
     ctx->stage_next = 0;
-    ctx->track_ctas_per_pair = 0; ctx->track_threads = 0;
+    ctx->track_ctas_per_pair = 0; ctx->track_threads = 0; ctx->track_max_clusters = 0;
     for (auto &v : ctx->ev_valid) v = false;
     ctx->split_rank = 0; ctx->split_world = 1; ctx->split_local = nullptr; ctx->split_seq = 0;
     for (auto &p : ctx->split_peers) p = nullptr;
@@ -300,6 +300,13 @@ int revo_ctx_last_upload_ms(revo_ctx *ctx, float *upload_ms)
     REVO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     *upload_ms = 0.f;
     if (ctx->ev_valid[3]) REVO_CUDA(ctx, cudaEventElapsedTime(upload_ms, ctx->ev[6], ctx->ev[7]));
+    return REVO_OK;
+}
+
+int revo_ctx_set_track_max_clusters(revo_ctx *ctx, int max_clusters)
+{
+    if (!ctx || max_clusters < 0) return REVO_ERR_INVALID_ARG;
+    ctx->track_max_clusters = max_clusters;
     return REVO_OK;
 }
 

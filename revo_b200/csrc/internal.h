@@ -93,6 +93,7 @@ struct revo_ctx {
     int stage_next;
     int track_ctas_per_pair;
     int track_threads;
+    int track_max_clusters;   // cap on resident clusters of k_track (0 = all the device holds), revo_ctx_set_track_max_clusters
     // pyramid construction: the Canny / compaction chains of the levels run on their own streams between a fork after the gray /
     // depth pyramids and a join before the build-complete event (the small levels hide under level 0)
     cudaStream_t lvl_stream[REVO_MAX_LEVELS], depth_stream;

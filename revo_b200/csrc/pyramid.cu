@@ -671,9 +671,10 @@ int launch_colored_pcl(revo_ctx *ctx, const ImgLevel *d_desc_one, int w, int h, 
 //  (b) row pass: d2(x,y) = min_j (x-j)^2 + g(j,y)^2 by an outward search that stops once r^2 >= best
 //      (exact; typical DT values are small so the search is short).
 // K8: {0.5(dt[i-1]-dt[i+1]), 0.5(dt[i-w]-dt[i+w]), dt[i], 0} for rows 1..h-2, zeros elsewhere (linear indices: column 0 takes
-//     its left neighbour from the end of the previous row, like the reference).  k_edt_rows_opt does (b) and K8 in one kernel
-//     for a band of rows: the distances of band + halo rows stay in shared memory, dt is written once and never read back,
-//     and the texels are stored tile by tile (full 128-byte lines).
+//     its left neighbour from the end of the previous row, like the reference); texels are stored tile by tile (full lines).
+//     (Doing (b) and K8 in one kernel for a band of rows -- distances of band + halo rows in shared memory, dt never read
+//     back -- was measured slower than the two kernels, 1.78 vs 1.66 ms per 256 promotions: 38 KB of shared memory per CTA cost
+//     more occupancy in the latency-bound search than the saved dt read is worth.)
 // ---------------------------------------------------------------------------
 constexpr int kEdtInf = 1 << 14;
 // value of every pixel when the edge map is empty: what OpenCV's own trueDistTrans returns (cv2 4.13, IPP off)
@@ -765,55 +766,13 @@ __device__ __forceinline__ uint2 pack_texel(const float4 t)
     return make_uint2(__float_as_uint(t.z), pack_grad(t.x, t.y));
 }
 
-// (b) + K8 for a band of kEdtBand rows (a multiple of 4: whole tile rows) per CTA; dynamic shared memory:
-// (kEdtBand + 2) * w * (2 + 4) bytes
-constexpr int kEdtBand = 8;
-__global__ void __launch_bounds__(256) k_edt_rows_opt(const ImgLevel *__restrict__ desc, int w, int h)
-{
-    extern __shared__ unsigned short grow[];
-    const int f = blockIdx.z;
-    const int y0 = blockIdx.x * kEdtBand;
-    const int ya = max(y0 - 1, 0), yb = min(y0 + kEdtBand, h - 1);          // rows held (inclusive), halo included
-    const int nr = yb - ya + 1;
-    float *ds = (float *)(grow + (size_t)(kEdtBand + 2) * w);                // (kEdtBand + 2) * w * 2 bytes is a multiple of 4
-    const unsigned short *__restrict__ g = (const unsigned short *)desc[f].labels + (size_t)ya * w;
-    for (int i = threadIdx.x; i < nr * w; i += blockDim.x) grow[i] = g[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < nr * w; i += blockDim.x) {
-        const int r = i / w;
-        ds[i] = edt_row_px(grow + (size_t)r * w, i - r * w, w);
-    }
-    __syncthreads();
-    const int y_end = min(y0 + kEdtBand, h);
-    float *__restrict__ dt = desc[f].dt;
-    for (int i = threadIdx.x; i < (y_end - y0) * w; i += blockDim.x) dt[(size_t)y0 * w + i] = ds[(size_t)(y0 - ya) * w + i];
-    // texels, tile by tile: 16 consecutive threads write the 16 texels (128 bytes) of one 4x4 tile
-    const int tw = (w + 3) >> 2;
-    uint2 *__restrict__ opt = desc[f].opt;
-    for (int t = threadIdx.x; t < (kEdtBand / 4) * tw * 16; t += blockDim.x) {
-        const int tile = t >> 4, k = t & 15;
-        const int ty = tile / tw, tx = tile - ty * tw;
-        const int x = tx * 4 + (k & 3), y = y0 + ty * 4 + (k >> 2);
-        if (x >= w || y >= h) continue;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 1 && y <= h - 2) {
-            const float *row = ds + (size_t)(y - ya) * w;
-            const float left = x > 0 ? row[x - 1] : row[-1];                 // linear index i-1: end of the previous row
-            const float right = x < w - 1 ? row[x + 1] : row[w];             // linear index i+1: start of the next row
-            o.x = __fmul_rn(0.5f, __fsub_rn(left, right));
-            o.y = __fmul_rn(0.5f, __fsub_rn(row[x - w], row[x + w]));
-            o.z = row[x];
-        }
-        opt[opt_texel_index(x, y, tw)] = pack_texel(o);
-    }
-}
-
 __global__ void __launch_bounds__(256) k_opt_struct(const ImgLevel *__restrict__ desc, int w, int h)
 {
-    // one thread per pixel; a warp covers 32 consecutive pixels of a row = 8 tiles x one 32-byte tile row: full sectors
+    // a CTA covers 64 columns x 4 rows = 16 tiles; 16 consecutive threads write the 16 texels (128 bytes = one line) of a tile
     const int f = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
+    const int tile = threadIdx.x >> 4, k = threadIdx.x & 15;
+    const int x = blockIdx.x * 64 + tile * 4 + (k & 3), y = blockIdx.y * 4 + (k >> 2);
+    if (x >= w || y >= h) return;
     const float *__restrict__ dt = desc[f].dt;
     desc[f].opt[opt_texel_index(x, y, (w + 3) >> 2)] = pack_texel(opt_texel(dt, (size_t)y * w + x, w, h));
 }
@@ -942,22 +901,13 @@ int launch_keyframe(revo_ctx *ctx, const ImgLevel *d_desc, int n, int w, int h)
         k_edt_cols<<<grid, n_seg * 32, 0, ctx->stream>>>(d_desc, w, h, cdiv(h, n_seg));
         LAUNCH_CHECK(ctx);
     }
-    const size_t smem_fused = (size_t)(kEdtBand + 2) * w * 6;
-    static const int no_fuse = getenv("REVO_EDT_NO_FUSE") ? atoi(getenv("REVO_EDT_NO_FUSE")) : 0;      // A/B switch
-    if (smem_fused <= 64 * 1024 && !no_fuse) {
-        REVO_CUDA(ctx, cudaFuncSetAttribute(k_edt_rows_opt, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        dim3 grid(cdiv(h, kEdtBand), 1, n);
-        k_edt_rows_opt<<<grid, 256, smem_fused, ctx->stream>>>(d_desc, w, h);
-        LAUNCH_CHECK(ctx);
-        return REVO_OK;
-    }
     {
         dim3 grid(h, 1, n);
         k_edt_rows<<<grid, 256, w * sizeof(unsigned short), ctx->stream>>>(d_desc, w, h);
         LAUNCH_CHECK(ctx);
     }
     {
-        dim3 grid(cdiv(w, 256), h, n);
+        dim3 grid(cdiv(w, 64), cdiv(h, 4), n);
         k_opt_struct<<<grid, 256, 0, ctx->stream>>>(d_desc, w, h);
         LAUNCH_CHECK(ctx);
     }

@@ -509,7 +509,7 @@ static int launch_track_t(revo_ctx *ctx, const PairDesc *d_pairs, int n_pairs, c
         if (max_clusters < 1) max_clusters = 1;
     }
     // optional cap on the number of pairs in flight (their lookup structures should stay L2-resident)
-    const int env_maxc = getenv("REVO_TRACK_MAX_CLUSTERS") ? atoi(getenv("REVO_TRACK_MAX_CLUSTERS")) : 0;
+    const int env_maxc = getenv("REVO_TRACK_MAX_CLUSTERS") ? atoi(getenv("REVO_TRACK_MAX_CLUSTERS")) : ctx->track_max_clusters;
     if (env_maxc > 0 && max_clusters > env_maxc) max_clusters = env_maxc;
     const int n_clusters = n_pairs < max_clusters ? n_pairs : max_clusters;
     cfg.gridDim = dim3(n_clusters * ctas_per_pair);

@@ -39,6 +39,7 @@ def _inv(T: np.ndarray) -> np.ndarray:
 
 
 TRACKER_STATE_OK, TRACKER_STATE_LOST, TRACKER_STATE_NEW_KF = 0, 1, 2
+PIPELINED_TRACK_CLUSTERS = 60    # of 74 on B200 (see CudaBackend)
 HISTOGRAM_LEVEL = 2        # TrackerNew::histogramLevel (tracker.cpp:229)
 N_VOTING = 3               # TrackerSettings::nFramesHistogramVoting
 
@@ -234,9 +235,13 @@ class StreamTracker:
 class CudaBackend:
     """The product path: everything through the C ABI (revo_b200/api.py)."""
 
-    def __init__(self, ctx, settings, tracker_settings=None, build_ctx=None):
+    def __init__(self, ctx, settings, tracker_settings=None, build_ctx=None, track_max_clusters=None):
         """ctx: context (stream) that tracks and promotes keyframes; build_ctx: optional second context whose stream
-        uploads frames and builds pyramids, so that the H2D copy of frame k+1 overlaps the tracking of frame k."""
+        uploads frames and builds pyramids, so that the H2D copy of frame k+1 overlaps the tracking of frame k.
+        track_max_clusters: resident-cluster cap of the tracking kernel while a second context builds (default
+        PIPELINED_TRACK_CLUSTERS; 0 = no cap): at full residency the tracker owns every register of the SMs and the build
+        kernels can only run in its tail; with ~1/5 of the cluster slots left free both run side by side (+6 % frames/s on
+        B200, profiles/r2_pipeline_cluster_cap.txt).  Without a second context the tracker runs uncapped."""
         from . import api
 
         self.api = api
@@ -245,6 +250,8 @@ class CudaBackend:
         self.settings = settings
         self.tracker = api.TrackerNew(ctx, tracker_settings or api.TrackerSettings(), settings)
         self.campyr = api.CameraPyr(settings)
+        cap = PIPELINED_TRACK_CLUSTERS if track_max_clusters is None else track_max_clusters
+        ctx.set_track_max_clusters(cap if self.build_ctx is not ctx else 0)
 
     def reserve(self, n_streams: int):
         """Steady state of a stream batch: keyframe + previous + current (+ one being built) frame slabs and two
