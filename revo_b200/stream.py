@@ -39,7 +39,7 @@ def _inv(T: np.ndarray) -> np.ndarray:
 
 
 TRACKER_STATE_OK, TRACKER_STATE_LOST, TRACKER_STATE_NEW_KF = 0, 1, 2
-PIPELINED_TRACK_CLUSTERS = 60    # of 74 on B200 (see CudaBackend)
+PIPELINED_TRACK_CLUSTERS = 62    # of 74 on B200 (see CudaBackend)
 HISTOGRAM_LEVEL = 2        # TrackerNew::histogramLevel (tracker.cpp:229)
 N_VOTING = 3               # TrackerSettings::nFramesHistogramVoting
 
@@ -240,7 +240,7 @@ class CudaBackend:
         uploads frames and builds pyramids, so that the H2D copy of frame k+1 overlaps the tracking of frame k.
         track_max_clusters: resident-cluster cap of the tracking kernel while a second context builds (default
         PIPELINED_TRACK_CLUSTERS; 0 = no cap): at full residency the tracker owns every register of the SMs and the build
-        kernels can only run in its tail; with ~1/5 of the cluster slots left free both run side by side (+6 % frames/s on
+        kernels can only run in its tail; with a sixth of the cluster slots left free both run side by side (+2.5 % frames/s on
         B200, profiles/r2_pipeline_cluster_cap.txt).  Without a second context the tracker runs uncapped."""
         from . import api
 
