@@ -105,9 +105,44 @@ int launch_depth_u16(revo_ctx *ctx, const uint16_t *d_raw, size_t frame_px, floa
     return REVO_OK;
 }
 
+// 3-channel fast path: 16 pixels per thread = three 128-bit loads (48 bytes, 16-byte aligned when the row is) and one 128-bit
+// store: four times the bytes in flight per thread of k_gray, whose top stall is the load (long scoreboard 15.6 warps per issue).
+__global__ void __launch_bounds__(256) k_gray16(const uint8_t *__restrict__ bgr, size_t stride, size_t frame_bytes,
+                                                const ImgLevel *__restrict__ desc, int w, int h)
+{
+    const int f = blockIdx.z;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= h || x0 >= w) return;
+    const uint4 *p = (const uint4 *)(bgr + (size_t)f * frame_bytes + (size_t)y * stride + (size_t)x0 * 3);
+    const uint4 A = __ldg(p), B = __ldg(p + 1), C = __ldg(p + 2);
+    const uint32_t v[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = v[3 * q], b = v[3 * q + 1], c = v[3 * q + 2];
+        // a = B0 G0 R0 B1 | b = G1 R1 B2 G2 | c = R2 B3 G3 R3   (little endian)
+        const uint32_t y0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255);
+        const uint32_t y1 = gray_of(a >> 24, b & 255, (b >> 8) & 255);
+        const uint32_t y2 = gray_of((b >> 16) & 255, b >> 24, c & 255);
+        const uint32_t y3 = gray_of((c >> 8) & 255, (c >> 16) & 255, c >> 24);
+        o[q] = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+    }
+    *(uint4 *)(desc[f].gray + (size_t)y * w + x0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 int launch_gray(revo_ctx *ctx, const uint8_t *d_bgr, size_t stride, int ch, size_t frame_bytes, const ImgLevel *d_desc,
                 int n, int w, int h)
 {
+    static const int no16 = getenv("REVO_GRAY_NO16") ? atoi(getenv("REVO_GRAY_NO16")) : 0;      // A/B switch
+    // every frame's image and gray plane are 256-byte aligned (slab chunks, staging buffers); rows stay 16-byte aligned when
+    // the width is a multiple of 16 and the input rows are tight or 16-byte pitched
+    if (ch == 3 && !no16 && (w & 15) == 0 && (stride & 15) == 0 && (frame_bytes & 15) == 0 && (((uintptr_t)d_bgr) & 15) == 0) {
+        dim3 block(8, 32), grid(cdiv(w / 16, 8), cdiv(h, 32), n);
+        k_gray16<<<grid, block, 0, ctx->stream>>>(d_bgr, stride, frame_bytes, d_desc, w, h);
+        LAUNCH_CHECK(ctx);
+        return REVO_OK;
+    }
     dim3 block(32, 8), grid(cdiv(cdiv(w, 4), 32), cdiv(h, 8), n);
     k_gray<<<grid, block, 0, ctx->stream>>>(d_bgr, stride, ch, frame_bytes, d_desc, w, h);
     LAUNCH_CHECK(ctx);
