@@ -23,7 +23,8 @@
 // follows a rejection depends only on what is known when the try starts (accepted normal equations, next lambda): lane 0
 // of warp 1 computes it while warp 0 waits for the record exchange, so after a rejection the next evaluation starts
 // without the solve on the critical path (lm_step in track_common.cuh picks it up).  The LM step itself runs in float32
-// like the reference's Eigen / Sophus types (a dependent chain: ~0.9 k cycles against ~3.7 k in double).
+// like the reference's Eigen / Sophus types (a dependent chain: the float LDL^T + solve is ~0.9 k cycles, and a dependent FP64
+// FMA costs twice the latency of an FP32 one on this chip, profiles/r2_lm_probe.txt).
 // No tensor cores: there is no dense contraction here.
 #include <cooperative_groups.h>
 #include <math.h>
