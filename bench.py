@@ -67,14 +67,15 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_ms: int = 20):
         self.index = index
+        self.period_ms = period_ms
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms),
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -428,7 +429,9 @@ def main():
                          track_max_clusters=None if args.track_max_clusters < 0 else args.track_max_clusters)
         st = StreamTracker(be, B, args.kf_interval, policy or args.kf_policy)
         st.keep_history = keep_history
-        sampler = ClockSampler(local_rank) if sample_clocks else None
+        # rank 0 samples its GPU every 20 ms; the other ranks every 250 ms (eight 50 Hz nvidia-smi loops on one box disturb the
+        # ranks' host threads) -- their medians and throttle reasons are merged into the reported block below
+        sampler = ClockSampler(local_rank, 20 if rank == 0 else 250) if sample_clocks else None
         if sampler:
             sampler.start()     # sampled from the warm-up on: the GPU is under the same load throughout
         st.start(src_bgr[0], src_depth[0])
@@ -469,6 +472,13 @@ def main():
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
+        if clocks is not None and dist is not None:
+            every = [None] * world
+            dist.all_gather_object(every, clocks)
+            meds = [c["sm_mhz"] for c in every if c and c.get("sm_mhz") is not None]
+            clocks = dict(clocks, sm_mhz=min(meds) if meds else clocks.get("sm_mhz"),
+                          reasons=sorted(set(r for c in every if c for r in c.get("reasons", []))),
+                          per_rank_sm_mhz=[c.get("sm_mhz") if c else None for c in every])
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
