@@ -748,16 +748,19 @@ __global__ void __launch_bounds__(1024) k_edt_cols(const ImgLevel *__restrict__ 
     }
 }
 
-// one row of (b): squared distance of pixel x from the column distances of its row
-__device__ __forceinline__ float edt_row_px(const unsigned short *__restrict__ grow, int x, int w)
+// one row of (b): squared distance of pixel x from the column distances of its row.  [jmin, jmax]: the columns of the row whose
+// column distance is finite -- a column without any edge can never win, so the search never leaves that span (an empty or
+// nearly empty edge map would otherwise cost O(w) steps per pixel)
+__device__ __forceinline__ float edt_row_px(const unsigned short *__restrict__ grow, int x, int jmin, int jmax)
 {
+    if (jmin > jmax) return kEdtEmpty;
     const int g0 = grow[x];
     int best = g0 * g0;
-    const int rmax = max(x, w - 1 - x);
+    const int rmax = max(x - jmin, jmax - x);
     for (int r = 1; r <= rmax && r * r < best; ++r) {
         const int r2 = r * r;
-        if (x - r >= 0) { const int gl = grow[x - r]; best = min(best, r2 + gl * gl); }
-        if (x + r < w) { const int gr = grow[x + r]; best = min(best, r2 + gr * gr); }
+        if (x - r >= jmin) { const int gl = grow[x - r]; best = min(best, r2 + gl * gl); }
+        if (x + r <= jmax) { const int gr = grow[x + r]; best = min(best, r2 + gr * gr); }
     }
     return best >= kEdtInf * kEdtInf ? kEdtEmpty : sqrtf((float)best);
 }
@@ -765,12 +768,23 @@ __device__ __forceinline__ float edt_row_px(const unsigned short *__restrict__ g
 __global__ void __launch_bounds__(256) k_edt_rows(const ImgLevel *__restrict__ desc, int w, int h)
 {
     extern __shared__ unsigned short grow[];
+    __shared__ int span_lo;
+    __shared__ int span_hi;
     const int f = blockIdx.z, y = blockIdx.x;
     const unsigned short *__restrict__ g = (const unsigned short *)desc[f].labels + (size_t)y * w;
-    for (int i = threadIdx.x; i < w; i += blockDim.x) grow[i] = g[i];
+    if (threadIdx.x == 0) { span_lo = w; span_hi = -1; }
     __syncthreads();
+    int lo = w, hi = -1;
+    for (int i = threadIdx.x; i < w; i += blockDim.x) {
+        const unsigned short v = g[i];
+        grow[i] = v;
+        if (v < kEdtInf) { lo = min(lo, i); hi = max(hi, i); }
+    }
+    if (hi >= 0) { atomicMin(&span_lo, lo); atomicMax(&span_hi, hi); }
+    __syncthreads();
+    const int jmin = span_lo, jmax = span_hi;
     float *__restrict__ out = desc[f].dt + (size_t)y * w;
-    for (int x = threadIdx.x; x < w; x += blockDim.x) out[x] = edt_row_px(grow, x, w);
+    for (int x = threadIdx.x; x < w; x += blockDim.x) out[x] = edt_row_px(grow, x, jmin, jmax);
 }
 
 // The reference's {gx, gy, dt, .} float4 texel (imgpyramidrgbd.cpp:255-276) at linear index i; zeros in rows 0 and h-1.

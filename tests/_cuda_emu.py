@@ -199,6 +199,8 @@ using std::min;
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); }
 static inline int atomicSub(int *p, int v) { return __sync_fetch_and_sub(p, v); }
+static inline int atomicMin(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+static inline int atomicMax(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
 static inline void __nanosleep(unsigned) { sched_yield(); }
 static inline void __threadfence_block() { __sync_synchronize(); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __sync_fetch_and_add(p, v); }

@@ -191,3 +191,21 @@ def test_colored_point_cloud_kernels_on_host(pyr_emu, orc32):
                 assert rc == 0 and n.value == want.shape[1], (lvl, dense, n.value, want.shape)
                 assert np.array_equal(out[:n.value].T, want), (lvl, dense)
         assert want.shape[1] > 100
+
+
+def test_distance_transform_of_sparse_and_empty_edge_maps_on_host(pyr_emu, orc32):
+    """k_edt_cols / k_edt_rows where the search span matters: a flat image (no edge at all: every distance is OpenCV's 65536)
+    and an image whose only edges sit in a narrow vertical band (most columns have no edge: the row search is clamped to the
+    span of columns that have one) -- bit-exact against the oracle's cv2-pinned distance transform."""
+    p = synth_pair(7, 160, 120)
+    _, depth = p["key"]
+    flat = np.full((120, 160, 3), 90, np.uint8)
+    po = oracle_pyramid(orc32, p["cam"], 2, flat, depth)
+    assert not po.edges[0].any() and float(po.dt[0].min()) == 65536.0
+    compare(run_pyramid(pyr_emu, flat, depth, p["cam"], 2), po, 2)
+    band = flat.copy()
+    band[20:100, 70:74] = 230                                   # one bright bar: edges in columns ~69..74 only
+    po = oracle_pyramid(orc32, p["cam"], 2, band, depth)
+    cols = np.nonzero(po.edges[0].any(axis=0))[0]
+    assert 0 < cols.size < 12 and float(po.dt[0].max()) > 60.0
+    compare(run_pyramid(pyr_emu, band, depth, p["cam"], 2), po, 2)
