@@ -16,6 +16,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     out_dir, B, n_frames = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    policy = sys.argv[4] if len(sys.argv) > 4 else "interval"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     sys.path.insert(0, ROOT)
@@ -26,9 +27,11 @@ def main():
     w, h = 160, 120
     cam = synth.intrinsics(w, h)
     seeds = [300 + rank * B + s for s in range(B)]
-    streams = [synth.make_stream(sd, n_frames, w, h) for sd in seeds]
+    fast = policy == "vote"                 # fast odd streams: their vote asks for keyframes
+    streams = [synth.make_stream(sd, n_frames, w, h, max_trans=0.01 + 0.04 * (fast and sd % 2), max_rot_deg=0.5 + 2.5 * (fast and sd % 2))
+               for sd in seeds]
     be = OracleBackend(cam, 3)
-    st = StreamTracker(be, B, kf_interval=3)
+    st = StreamTracker(be, B, kf_interval=3, kf_policy=policy)
     frame = lambda i: (np.stack([s["frames"][i][0] for s in streams]), np.stack([s["frames"][i][1] for s in streams]))
     st.start(*frame(0))
     dist.barrier()
@@ -41,7 +44,7 @@ def main():
     frames = torch.tensor([float(B * (n_frames - 1))], dtype=torch.float64)
     dist.all_reduce(frames)                             # whole-job units
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), T_w_c=st.T_w_c, seeds=np.array(seeds), dt=dt.numpy(), frames=frames.numpy(),
-             evals=st.total_evals)
+             evals=st.total_evals, retracks=st.n_retracks)
     dist.destroy_process_group()
 
 

@@ -13,7 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _single_process(seeds, n_frames):
+def _single_process(seeds, n_frames, policy="interval"):
     sys.path.insert(0, ROOT)
     from oracle.stream_backend import OracleBackend
     from revo_b200 import synth
@@ -21,8 +21,10 @@ def _single_process(seeds, n_frames):
 
     w, h = 160, 120
     cam = synth.intrinsics(w, h)
-    streams = [synth.make_stream(sd, n_frames, w, h) for sd in seeds]
-    st = StreamTracker(OracleBackend(cam, 3), len(seeds), kf_interval=3)
+    fast = policy == "vote"
+    streams = [synth.make_stream(sd, n_frames, w, h, max_trans=0.01 + 0.04 * (fast and sd % 2), max_rot_deg=0.5 + 2.5 * (fast and sd % 2))
+               for sd in seeds]
+    st = StreamTracker(OracleBackend(cam, 3), len(seeds), kf_interval=3, kf_policy=policy)
     frame = lambda i: (np.stack([s["frames"][i][0] for s in streams]), np.stack([s["frames"][i][1] for s in streams]))
     st.start(*frame(0))
     for i in range(1, n_frames):
@@ -54,6 +56,23 @@ def test_two_rank_gloo_sharding_equals_single_process(tmp_path):
     st, _ = _single_process([300, 301, 302, 303], n_frames)
     both = np.concatenate([ranks[0]["T_w_c"], ranks[1]["T_w_c"]])
     assert np.array_equal(both, st.T_w_c)                        # same streams, same poses, bit for bit
+    assert int(ranks[0]["evals"]) + int(ranks[1]["evals"]) == st.total_evals
+
+
+def test_two_rank_gloo_sharding_with_the_vote_policy(tmp_path):
+    """The same sharding with the reference's keyframe policy (StreamTracker(kf_policy="vote")): every rank votes, promotes and
+    re-aligns its own streams only -- the keyframe switches of the fast streams happen on whichever rank owns them, and the
+    sharded job reproduces the single-process poses bit for bit."""
+    B, n_frames = 2, 8
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29543", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "tests", "_shard_worker.py"), str(tmp_path), str(B), str(n_frames), "vote"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ranks = [np.load(tmp_path / f"rank{k}.npz") for k in range(2)]
+    st, _ = _single_process([300, 301, 302, 303], n_frames, policy="vote")
+    assert np.array_equal(np.concatenate([ranks[0]["T_w_c"], ranks[1]["T_w_c"]]), st.T_w_c)
+    assert int(ranks[0]["retracks"]) + int(ranks[1]["retracks"]) == st.n_retracks >= 1
     assert int(ranks[0]["evals"]) + int(ranks[1]["evals"]) == st.total_evals
 
 
