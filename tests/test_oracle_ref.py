@@ -97,12 +97,13 @@ def test_optimizer_of_the_reference_equals_oracle(orc32, seed):
     assert r["n_evals"] == q["n_evals"] and np.array_equal(r["R"], q["R"].astype(np.float32)) and np.array_equal(r["T"], q["T"].astype(np.float32))
 
 
-@pytest.mark.parametrize("seed", [1, 23])
-def test_tracker_of_the_reference_equals_oracle(orc32, seed):
-    """TrackerNew::trackFrames with checkInitializationValues / evalCostFunction (tracker.cpp:265-393)."""
+@pytest.mark.parametrize("seed,w,h", [(1, 320, 240), (23, 320, 240), (2, 640, 480)])
+def test_tracker_of_the_reference_equals_oracle(orc32, seed, w, h):
+    """TrackerNew::trackFrames with checkInitializationValues / evalCostFunction (tracker.cpp:265-393); the last case is the
+    benchmark's frame size (3 levels: the compiled reference divides by zero at a fourth)."""
     from revo_b200 import synth
 
-    p, ok, oc, rk, rc = _pyramids(orc32, seed, 320, 240)
+    p, ok, oc, rk, rc = _pyramids(orc32, seed, w, h)
     ocfg = orc32.default_cfg()
     trk = RF.RefTracker(rk, ocfg)
     bad = synth.se3_exp([0.4, 0.3, -0.2, 0.2, -0.15, 0.1])
